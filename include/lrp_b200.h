@@ -1,0 +1,162 @@
+/*
+ * lrp_b200.h — C ABI of the B200-native AttnLRP hot path (liblrp_b200.so).
+ *
+ * The reference (rachtibat/LRP-eXplains-Transformers, `lxt` 2.1) has no FFI: its hot path is Python
+ * autograd glue over stock PyTorch kernels.  This header is the boundary a maintainer would bind instead
+ * (ctypes stub shown in INTEGRATION.md).  Every entry point cites the reference code it replaces.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; all pointers are DEVICE pointers owned by the caller unless stated;
+ *   - bf16 tensors are `uint16_t`-sized IEEE bfloat16, fp32 tensors are `float`;
+ *   - row-major, innermost dimension contiguous, leading dimensions given in ELEMENTS;
+ *   - `stream` is a `cudaStream_t` passed as `void*` (0 = legacy default stream); kernels are enqueued,
+ *     never synchronised;
+ *   - return value 0 on success, negative `LRP_ERR_*` otherwise; `lrp_last_error()` gives the
+ *     thread-local message.  Nothing throws, nothing allocates device memory (workspaces are passed in);
+ *   - re-entrant from any host thread (the autograd engine calls backward rules from its own thread).
+ */
+#ifndef LRP_B200_H_
+#define LRP_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LRP_OK 0
+#define LRP_ERR_ARG (-1)      /* invalid argument / unsupported shape */
+#define LRP_ERR_CUDA (-2)     /* CUDA runtime or driver error */
+#define LRP_ERR_NO_DEVICE (-3) /* no sm_100 device visible */
+
+#define LRP_ACT_SILU 0
+#define LRP_ACT_GELU_TANH 1
+#define LRP_ACT_GELU_ERF 2
+
+/* library ABI version (major*1000 + minor) */
+int lrp_version(void);
+/* thread-local description of the last error returned on this thread ("" if none) */
+const char* lrp_last_error(void);
+/* 0 if an sm_100 device is present and usable, LRP_ERR_NO_DEVICE otherwise */
+int lrp_check_device(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * Fused GEMM epilogue:  out = resid + alpha * acc * rowscale[m] * colscale[n] + bias[n]
+ * NULL pointers disable the corresponding term.  `out` is bf16 or fp32 (out_is_f32); `shadow_bf16`
+ * optionally receives a bf16 copy of the same values (the next GEMM's A operand).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct lrp_epilogue {
+  void* out;
+  int32_t out_is_f32;
+  void* shadow_bf16;
+  const float* resid_f32; /* may alias `out` when out_is_f32 (in-place accumulate) */
+  const float* rowscale;  /* [M] fp32 */
+  const float* colscale;  /* [N] fp32 */
+  const float* bias;      /* [N] fp32 */
+  float alpha;
+  int64_t ldc;            /* leading dimension of out / shadow / resid, in elements */
+} lrp_epilogue_t;
+
+/* Generic tcgen05 GEMM, A [M,K] bf16.  b_layout 0: B is [N,K] (NT);  b_layout 1: B is [K,N] (NN).
+ * tile_n = 0 lets the library choose (128 or 256). */
+int lrp_gemm_bf16(const void* A, int64_t lda, const void* B, int64_t ldb, int b_layout, int M, int N, int K,
+                  const lrp_epilogue_t* epi, int tile_n, void* stream);
+
+/* nn.Linear forward  y[T,N] = x[T,K] W[N,K]^T (+bias) with the fused epilogue above.
+ * Replaces: every `nn.Linear` on the path (transformers modeling_llama.py:183,262-264,288), left unpatched
+ * by the reference and therefore executed by cuBLAS there. */
+int lrp_linear_fwd(const void* x, int64_t ldx, const void* W, int64_t ldw, int T, int N, int K,
+                   const lrp_epilogue_t* epi, void* stream);
+
+/* GxI-space ε-LRP backward of nn.Linear  g_x[T,K] = epilogue(g_y[T,N] W[N,K]); the epilogue carries the
+ * rules that follow it in the reference graph (RMSNorm identity rule `g*w*rstd`: lxt/efficient/patches.py
+ * :111-123; residual accumulation; divide_gradient: lxt/efficient/rules.py:103-127).  W is read in its
+ * stored [N,K] layout (no transposed copy). */
+int lrp_linear_dgrad_fused(const void* gy, int64_t ldg, const void* W, int64_t ldw, int T, int N, int K,
+                           const lrp_epilogue_t* epi, void* stream);
+
+/* Relevance-space ε-LRP rule of nn.Linear (lxt/explicit/functional.py:325-364, `linear_epsilon_fn`):
+ *     z = x W^T + b ;  s = R_out / (z + eps) ;  R_in = x ⊙ (s W)
+ * One launch: a persistent kernel whose first tile phase forms z and s (s kept in `s_ws`, [T,N] bf16,
+ * L2-resident between phases) and whose second phase contracts s with W and multiplies by x.
+ * x [T,K] bf16, W [N,K] bf16, bias [N] fp32 or NULL, r_out [T,N] (bf16 or fp32), r_in [T,K] (same dtype
+ * as r_out).  `flags_ws` is an int32 scratch of lrp_linear_eps_flags_count(T) entries, zero on entry. */
+int lrp_linear_eps_bwd(const void* x, const void* W, const float* bias, const void* r_out, int r_is_f32,
+                       void* r_in, void* s_ws, int32_t* flags_ws, int T, int N, int K, float eps, void* stream);
+int64_t lrp_linear_eps_flags_count(int T);
+
+/* ------------------------------------------------------------------------------------------------
+ * RMSNorm with the identity rule (lxt/efficient/patches.py:111-123 `rms_norm_forward`,
+ * lxt/efficient/models/gemma3.py:11-12 `gemma3_norm`; relevance form lxt/explicit/functional.py:463-495).
+ *   fwd: y = (x * rsqrt(mean(x^2)+eps)) [cast to bf16] * (w + w_offset)   rstd saved (fp32 [T])
+ *   bwd (GxI): g_x = g_y * (w + w_offset) * rstd       (the variance path is detached)
+ * x_is_f32 selects the dtype of x / g_x; y / g_y are bf16.  w is bf16 [d]; w_offset 0 (Llama) or 1 (Gemma).
+ * ---------------------------------------------------------------------------------------------- */
+int lrp_rmsnorm_fwd(const void* x, int x_is_f32, const void* w, float w_offset, float eps, void* y, float* rstd,
+                    int T, int d, void* stream);
+int lrp_rmsnorm_bwd(const void* gy, const void* w, float w_offset, const float* rstd, void* gx, int gx_is_f32,
+                    int accumulate, int T, int d, void* stream);
+
+/* LayerNorm with detached std (lxt/efficient/patches.py:126-142 `layer_norm_forward`), bf16 in/out.
+ *   fwd: y = (x-mean)/sqrt(var+eps) * w + b ; saves mean,rstd.  bwd: g_x = (g_y*w*rstd) - mean_d(g_y*w*rstd) */
+int lrp_layernorm_fwd(const void* x, const void* w, const void* b, float eps, void* y, float* mean, float* rstd,
+                      int T, int d, void* stream);
+int lrp_layernorm_bwd(const void* gy, const void* w, const float* rstd, void* gx, int T, int d, void* stream);
+
+/* Rotary embedding applied in place to the q and k slices of a packed qkv buffer [T, ld] (bf16):
+ * heads are contiguous D-wide slices; rotate_half convention (transformers modeling_llama.py:146-168).
+ * `inverse`=1 applies the transposed rotation (the backward of RoPE, which is linear in q,k).
+ * positions: token t has position (t % S).  cos/sin tables: fp32 [S, D/2]. */
+int lrp_rope_inplace(void* qk, int64_t ld, int n_heads_total, int D, const float* cos_t, const float* sin_t,
+                     int T, int S, int inverse, void* stream);
+
+/* Gated MLP point-wise part with the identity rule on the activation and the uniform rule on the product
+ * (lxt/efficient/patches.py:145-157 `gated_mlp_forward`, lxt/efficient/rules.py:69-127).
+ *   fwd: a = act(gate) * up                          gu = [T, 2I] bf16 (gate | up), a = [T, I] bf16
+ *   bwd: g_up = (g_a/2) * act(gate);  g_gate = (g_a/2) * up * act(gate)/(gate + 1e-10)     (bf16 roundings
+ *        of act(gate) and of the ratio follow the reference's bf16 tensors) */
+int lrp_gated_act_fwd(const void* gu, void* a, int T, int I, int act, void* stream);
+int lrp_gated_act_bwd(const void* ga, const void* gu, void* ggu, int T, int I, int act, void* stream);
+
+/* Identity rule on a plain element-wise non-linearity (lxt/efficient/rules.py:88-100,
+ * lxt/efficient/patches.py:159-169 `mlp_forward`, :206-211 `non_linear_forward`):
+ *   fwd: y = act(x);   bwd: g_x = g_y * act(x)/(x + 1e-10) */
+int lrp_act_identity_fwd(const void* x, void* y, int64_t n, int act, void* stream);
+int lrp_act_identity_bwd(const void* gy, const void* x, void* gx, int64_t n, int act, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Flash AttnLRP (lxt/efficient/patches.py:171-203: SDPA with dQ/4, dK/4, dV/2; softmax is propagated as
+ * its ordinary backward = Deep-Taylor rule in GxI space, lxt/explicit/functional.py:276-322).
+ * No [B,H,S,S] tensor is materialised.  q [B,S,H,D], k/v [B,S,Hkv,D] given as strided views
+ * (row strides in elements: token stride `ld*`, head stride D), o [B,S,H,D] contiguous, lse fp32 [B,H,S].
+ * causal: 0/1; window: 0 = none, else sliding window size (keys j with i-j < window).
+ * bwd writes dq,dk,dv with the same strides as q,k,v, already scaled by q_div,k_div,v_div (4,4,2 for
+ * AttnLRP; 1,1,1 gives the plain gradient; q_div=k_div=0 is CP-LRP: dq=dk=0 is written).
+ * `dq_acc_ws` fp32 [B,S,H,D] scratch (zero-filled by the call).
+ * ---------------------------------------------------------------------------------------------- */
+int lrp_attn_fwd(const void* q, const void* k, const void* v, int64_t ldq, int64_t ldk, int64_t ldv, void* o,
+                 float* lse, int B, int S, int H, int Hkv, int D, float scale, int causal, int window,
+                 void* stream);
+int lrp_attn_bwd(const void* q, const void* k, const void* v, int64_t ldq, int64_t ldk, int64_t ldv,
+                 const void* o, const void* d_o, const float* lse, void* dq, void* dk, void* dv, int64_t lddq,
+                 int64_t lddk, int64_t lddv, float* dq_acc_ws, float* delta_ws, int B, int S, int H, int Hkv, int D,
+                 float scale, int causal, int window, float q_div, float k_div, float v_div, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Ends of the path (examples/quantized_llama.py:35-47)
+ * ---------------------------------------------------------------------------------------------- */
+/* h[t,:] = float(emb[ids[t],:]) * scale   (ids int64 on device; emb bf16 [V,d]; h fp32 [T,d]) */
+int lrp_embed_gather(const int64_t* ids, const void* emb, float scale, float* h, int T, int d, void* stream);
+/* argmax over logits[b,:] (fp32 [B,V]) -> idx[b] (int32), val[b] */
+int lrp_argmax_rows(const float* logits, int32_t* idx, float* val, int B, int V, void* stream);
+/* relevance[t] = sum_d x[t,d] * g[t,d]  (x,g fp32) — `(emb * emb.grad).float().sum(-1)` */
+int lrp_gxi_reduce(const float* x, const float* g, float* rel, int T, int d, void* stream);
+/* bf16 variant of the same reduction (x, g bf16) */
+int lrp_gxi_reduce_bf16(const void* x, const void* g, float* rel, int T, int d, void* stream);
+/* out_bf16 = bf16(in_f32), n elements */
+int lrp_cast_f32_to_bf16(const float* in, void* out, int64_t n, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LRP_B200_H_ */

@@ -1,0 +1,315 @@
+// Persistent, warp-specialised tcgen05 GEMM for sm_100a.
+//
+//   D[M,N] = epilogue( A[M,K] (bf16, row-major)  x  B )           fp32 accumulation in TMEM
+//     B layout 0 ("NT"): B is [N,K] row-major  (y = x W^T, the nn.Linear forward)
+//     B layout 1 ("NN"): B is [K,N] row-major  (g_x = g_y W,  the LRP / GxI backward of nn.Linear:
+//                        the weight is consumed in its stored layout through an MN-major smem descriptor)
+//   epilogue:  out = resid + alpha * acc * rowscale[m] * colscale[n] + bias[n]     (every term optional)
+//              written as bf16 or fp32, plus an optional bf16 shadow copy.
+//
+// This is the single kernel every Linear on the AttnLRP path runs through (reference call sites:
+// transformers modeling_llama.py:183,262-264,288 forward; autograd dgrad of the same in backward; the
+// fused epilogue terms replace lxt/efficient/patches.py:111-123 (RMSNorm backward g*w*rstd), the residual
+// adds, and lxt/efficient/rules.py:125-127 (divide_gradient) which otherwise are separate HBM round trips).
+//
+// Structure (one CTA per SM, 192 threads):
+//   warp 0      : TMA producer   (cp.async.bulk.tensor -> 128B-swizzled smem ring, mbarrier complete_tx)
+//   warp 1      : MMA issuer     (one elected lane issues tcgen05.mma 128xBNx16, accumulators in TMEM,
+//                                 tcgen05.commit releases smem stages / publishes accumulators)
+//   warps 2..5  : epilogue       (tcgen05.ld TMEM -> registers -> fused epilogue -> global)
+//   TMEM holds two accumulator stages so the epilogue of tile i overlaps the mainloop of tile i+1.
+#include "ptx_sm100.cuh"
+#include "lrp_internal.h"
+
+namespace lrp {
+
+constexpr int BM = 128;
+constexpr int BK = 64;  // 64 bf16 = 128 B = one swizzle row
+constexpr int UMMA_K = 16;
+constexpr int GEMM_THREADS = 192;
+constexpr int GROUP_M = 16;  // rasterisation: 16 m-blocks share each streamed B panel through L2
+
+template <int BN>
+struct GemmCfg {
+  static constexpr int A_BYTES = BM * BK * 2;
+  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = (BN == 256) ? 4 : 6;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
+};
+
+struct GemmParams {
+  int M, N, K;
+  // epilogue
+  void* out;
+  __nv_bfloat16* shadow;
+  const float* resid;
+  const float* rowscale;
+  const float* colscale;
+  const float* bias;
+  float alpha;
+  int64_t ldc;
+  int out_is_f32;
+};
+
+__device__ __forceinline__ void tile_coords(int t, int num_m, int num_n, int& m_blk, int& n_blk) {
+  const int tiles_per_group = GROUP_M * num_n;
+  const int group = t / tiles_per_group;
+  const int first_m = group * GROUP_M;
+  const int gsize = min(GROUP_M, num_m - first_m);
+  const int in_group = t - group * tiles_per_group;
+  m_blk = first_m + in_group % gsize;
+  n_blk = in_group / gsize;
+}
+
+template <int BN, bool B_MN>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
+                 const GemmParams p) {
+  using Cfg = GemmCfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
+  uint64_t* full_bar = bars;                       // [STAGES]
+  uint64_t* empty_bar = bars + Cfg::STAGES;        // [STAGES]
+  uint64_t* tmem_full = bars + 2 * Cfg::STAGES;    // [2]
+  uint64_t* tmem_empty = tmem_full + 2;            // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  const int num_m = (p.M + BM - 1) / BM;
+  const int num_n = (p.N + BN - 1) / BN;
+  const int num_tiles = num_m * num_n;
+  const int num_k = (p.K + BK - 1) / BK;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tma_a);
+    tma_prefetch_desc(&tma_b);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < Cfg::STAGES; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full[i], 1);
+      mbar_init(&tmem_empty[i], 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ================= TMA producer =================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        int m_blk, n_blk;
+        tile_coords(t, num_m, num_n, m_blk, n_blk);
+        for (int kb = 0; kb < num_k; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
+          uint8_t* sb = sa + Cfg::A_BYTES;
+          mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+          tma_load_2d(sa, &tma_a, &full_bar[stage], kb * BK, m_blk * BM);
+          if constexpr (!B_MN) {
+            tma_load_2d(sb, &tma_b, &full_bar[stage], kb * BK, n_blk * BN);
+          } else {
+#pragma unroll
+            for (int j = 0; j < BN / 64; ++j)
+              tma_load_2d(sb + j * (64 * BK * 2), &tma_b, &full_bar[stage], n_blk * BN + j * 64, kb * BK);
+          }
+          if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer =================
+    constexpr uint32_t idesc = make_idesc_bf16(BM, BN, 0, B_MN ? 1 : 0);
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_base + acc * BN;
+      for (int kb = 0; kb < num_k; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+          const uint32_t sb = sa + Cfg::A_BYTES;
+          const uint64_t adesc = make_sdesc_sw128(sa, 16, 1024);
+          const uint64_t bdesc = B_MN ? make_sdesc_sw128(sb, 64 * BK * 2, 1024) : make_sdesc_sw128(sb, 16, 1024);
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            const uint64_t a_adv = uint64_t((k * UMMA_K * 2) >> 4);
+            const uint64_t b_adv = B_MN ? uint64_t((k * UMMA_K * 128) >> 4) : uint64_t((k * UMMA_K * 2) >> 4);
+            tc_mma_ss(tmem_d, adesc + a_adv, bdesc + b_adv, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          tc_commit(&empty_bar[stage]);                     // smem stage reusable once these MMAs retire
+          if (kb == num_k - 1) tc_commit(&tmem_full[acc]);  // accumulator complete
+        }
+        __syncwarp();
+        if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+      }
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  } else {
+    // ================= epilogue warps =================
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      int m_blk, n_blk;
+      tile_coords(t, num_m, num_n, m_blk, n_blk);
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+      const int m = m_blk * BM + q * 32 + lane;
+      const bool row_ok = m < p.M;
+      const float rs = (p.rowscale != nullptr && row_ok) ? p.rowscale[m] * p.alpha : p.alpha;
+      const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + acc * BN;
+      const int64_t row_off = int64_t(m) * p.ldc;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t v[32];
+        tmem_ld32(taddr + c * 32, v);
+        tmem_ld_wait();
+        const int n0 = n_blk * BN + c * 32;
+        if (row_ok && n0 < p.N) {
+#pragma unroll
+          for (int j8 = 0; j8 < 4; ++j8) {
+            const int n = n0 + j8 * 8;
+            if (n < p.N) {  // N is a multiple of 8 (checked on the host)
+              float f[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(v[j8 * 8 + j]) * rs;
+              if (p.colscale != nullptr) {
+                const float4 c0 = *reinterpret_cast<const float4*>(p.colscale + n);
+                const float4 c1 = *reinterpret_cast<const float4*>(p.colscale + n + 4);
+                f[0] *= c0.x; f[1] *= c0.y; f[2] *= c0.z; f[3] *= c0.w;
+                f[4] *= c1.x; f[5] *= c1.y; f[6] *= c1.z; f[7] *= c1.w;
+              }
+              if (p.bias != nullptr) {
+                const float4 b0 = *reinterpret_cast<const float4*>(p.bias + n);
+                const float4 b1 = *reinterpret_cast<const float4*>(p.bias + n + 4);
+                f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
+                f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
+              }
+              if (p.resid != nullptr) {
+                const float4 r0 = *reinterpret_cast<const float4*>(p.resid + row_off + n);
+                const float4 r1 = *reinterpret_cast<const float4*>(p.resid + row_off + n + 4);
+                f[0] += r0.x; f[1] += r0.y; f[2] += r0.z; f[3] += r0.w;
+                f[4] += r1.x; f[5] += r1.y; f[6] += r1.z; f[7] += r1.w;
+              }
+              if (p.out_is_f32) {
+                float* o = reinterpret_cast<float*>(p.out) + row_off + n;
+                *reinterpret_cast<float4*>(o) = make_float4(f[0], f[1], f[2], f[3]);
+                *reinterpret_cast<float4*>(o + 4) = make_float4(f[4], f[5], f[6], f[7]);
+              } else {
+                __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + row_off + n;
+                *reinterpret_cast<uint4*>(o) = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]),
+                                                          pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+              }
+              if (p.shadow != nullptr) {
+                *reinterpret_cast<uint4*>(p.shadow + row_off + n) =
+                    make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]),
+                               pack_bf16x2(f[6], f[7]));
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+template <int BN, bool B_MN>
+static int launch_gemm(const void* A, int64_t lda, const void* B, int64_t ldb, const GemmParams& p,
+                       cudaStream_t stream) {
+  using Cfg = GemmCfg<BN>;
+  CUtensorMap ta, tb;
+  // A: [M, K] row-major, box = 64 (k) x 128 (m)
+  if (int e = make_tmap_2d_bf16(&ta, A, uint64_t(p.K), uint64_t(p.M), uint64_t(lda), 64, BM)) return e;
+  if (!B_MN) {
+    // B: [N, K] row-major, box = 64 (k) x BN (n)
+    if (int e = make_tmap_2d_bf16(&tb, B, uint64_t(p.K), uint64_t(p.N), uint64_t(ldb), 64, BN)) return e;
+  } else {
+    // B: [K, N] row-major, box = 64 (n) x 64 (k)
+    if (int e = make_tmap_2d_bf16(&tb, B, uint64_t(p.N), uint64_t(p.K), uint64_t(ldb), 64, BK)) return e;
+  }
+  auto kern = gemm_bf16_kernel<BN, B_MN>;
+  static bool attr_done = false;  // idempotent; benign race
+  if (!attr_done) {
+    cudaError_t ce = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    if (ce != cudaSuccess) return set_error(LRP_ERR_CUDA, cudaGetErrorString(ce));
+    attr_done = true;
+  }
+  const int num_tiles = ((p.M + BM - 1) / BM) * ((p.N + BN - 1) / BN);
+  const int grid = num_tiles < sm_count() ? num_tiles : sm_count();
+  kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(ta, tb, p);
+  cudaError_t ce = cudaGetLastError();
+  if (ce != cudaSuccess) return set_error(LRP_ERR_CUDA, cudaGetErrorString(ce));
+  return LRP_OK;
+}
+
+int gemm_bf16(const void* A, int64_t lda, const void* B, int64_t ldb, int b_layout, int M, int N, int K,
+              const lrp_epilogue_t* epi, int force_bn, cudaStream_t stream) {
+  if (M <= 0 || N <= 0 || K <= 0) return set_error(LRP_ERR_ARG, "gemm: empty problem");
+  if ((N % 8) != 0 || (K % 8) != 0) return set_error(LRP_ERR_ARG, "gemm: N and K must be multiples of 8");
+  if ((lda % 8) != 0 || (ldb % 8) != 0) return set_error(LRP_ERR_ARG, "gemm: lda/ldb must be multiples of 8");
+  if ((reinterpret_cast<uintptr_t>(A) & 15) || (reinterpret_cast<uintptr_t>(B) & 15))
+    return set_error(LRP_ERR_ARG, "gemm: A/B must be 16-byte aligned");
+  if (epi == nullptr || epi->out == nullptr) return set_error(LRP_ERR_ARG, "gemm: missing output");
+  if ((epi->ldc % 8) != 0) return set_error(LRP_ERR_ARG, "gemm: ldc must be a multiple of 8");
+  GemmParams p;
+  p.M = M; p.N = N; p.K = K;
+  p.out = epi->out;
+  p.shadow = reinterpret_cast<__nv_bfloat16*>(epi->shadow_bf16);
+  p.resid = epi->resid_f32;
+  p.rowscale = epi->rowscale;
+  p.colscale = epi->colscale;
+  p.bias = epi->bias;
+  p.alpha = epi->alpha;
+  p.ldc = epi->ldc;
+  p.out_is_f32 = epi->out_is_f32;
+  int bn = force_bn;
+  if (bn == 0) {
+    // 256-wide tiles when they still fill the machine; otherwise 128-wide for more parallelism
+    const int64_t tiles256 = int64_t((M + BM - 1) / BM) * ((N + 255) / 256);
+    bn = (N >= 256 && tiles256 >= sm_count()) ? 256 : 128;
+  }
+  if (bn == 256) {
+    return b_layout == 0 ? launch_gemm<256, false>(A, lda, B, ldb, p, stream)
+                         : launch_gemm<256, true>(A, lda, B, ldb, p, stream);
+  } else if (bn == 128) {
+    return b_layout == 0 ? launch_gemm<128, false>(A, lda, B, ldb, p, stream)
+                         : launch_gemm<128, true>(A, lda, B, ldb, p, stream);
+  }
+  return set_error(LRP_ERR_ARG, "gemm: unsupported tile width");
+}
+
+}  // namespace lrp

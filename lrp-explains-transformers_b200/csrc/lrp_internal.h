@@ -1,0 +1,30 @@
+// Internal host-side declarations shared by the translation units of liblrp_b200.so.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/lrp_b200.h"
+
+namespace lrp {
+
+int set_error(int code, const char* msg);  // stores a thread-local message, returns code
+int sm_count();                            // SM count of the current device (cached)
+
+// Encode a 2-D bf16 tiled tensor map with 128-byte swizzle.
+//   dim0 = contiguous extent (elements), dim1 = rows, ld = row pitch (elements), box0 x box1 = tile.
+int make_tmap_2d_bf16(CUtensorMap* out, const void* base, uint64_t dim0, uint64_t dim1, uint64_t ld,
+                      uint32_t box0, uint32_t box1);
+
+int gemm_bf16(const void* A, int64_t lda, const void* B, int64_t ldb, int b_layout, int M, int N, int K,
+              const lrp_epilogue_t* epi, int force_bn, cudaStream_t stream);
+
+int linear_eps_bwd(const void* x, const void* W, const float* bias, const void* r_out, int r_is_f32, void* r_in,
+                   void* s_ws, int32_t* flags_ws, int T, int N, int K, float eps, cudaStream_t stream);
+
+#define LRP_CHECK_LAUNCH()                                                   \
+  do {                                                                       \
+    cudaError_t ce__ = cudaGetLastError();                                   \
+    if (ce__ != cudaSuccess) return set_error(LRP_ERR_CUDA, cudaGetErrorString(ce__)); \
+  } while (0)
+
+}  // namespace lrp

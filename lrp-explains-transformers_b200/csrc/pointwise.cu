@@ -1,0 +1,553 @@
+// HBM-bound kernels of the AttnLRP path: norms with the identity rule, RoPE, the gated-MLP point-wise rules,
+// the ends of the path (embedding gather, arg-max seed, Gradient x Input reduction).
+// All are single-pass, 16-byte vectorised, coalesced along the contiguous feature dimension; grids are sized
+// in rows (>> 148 SMs x resident CTAs at the benchmark shapes).
+#include "ptx_sm100.cuh"
+#include "lrp_internal.h"
+
+namespace lrp {
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+template <int THREADS>
+__device__ __forceinline__ float block_sum(float v, float* red) {
+  v = warp_sum(v);
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  if (l == 0) red[w] = v;
+  __syncthreads();
+  float t = (l < THREADS / 32) ? red[l] : 0.f;
+  t = warp_sum(t);
+  __syncthreads();
+  return t;
+}
+
+__device__ __forceinline__ float round_bf16(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
+
+__device__ __forceinline__ void load8(const __nv_bfloat16* p, float (&f)[8]) {
+  const uint4 u = *reinterpret_cast<const uint4*>(p);
+  f[0] = bf16_lo(u.x); f[1] = bf16_hi(u.x); f[2] = bf16_lo(u.y); f[3] = bf16_hi(u.y);
+  f[4] = bf16_lo(u.z); f[5] = bf16_hi(u.z); f[6] = bf16_lo(u.w); f[7] = bf16_hi(u.w);
+}
+__device__ __forceinline__ void load8(const float* p, float (&f)[8]) {
+  const float4 a = *reinterpret_cast<const float4*>(p);
+  const float4 b = *reinterpret_cast<const float4*>(p + 4);
+  f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+}
+__device__ __forceinline__ void store8(__nv_bfloat16* p, const float (&f)[8]) {
+  *reinterpret_cast<uint4*>(p) = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]),
+                                            pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+}
+__device__ __forceinline__ void store8(float* p, const float (&f)[8]) {
+  *reinterpret_cast<float4*>(p) = make_float4(f[0], f[1], f[2], f[3]);
+  *reinterpret_cast<float4*>(p + 4) = make_float4(f[4], f[5], f[6], f[7]);
+}
+
+// ------------------------------------------------------------------------------------------------
+// RMSNorm, identity rule
+// ------------------------------------------------------------------------------------------------
+constexpr int NORM_THREADS = 256;
+
+// Llama (w_offset == 0): y = bf16( w * bf16(x * rstd) )      [patches.py:118-123: downcast, then weight *]
+// Gemma (w_offset != 0): y = bf16( (x * rstd) * (w_offset + w) )   [gemma3.py:11-12 + HF Gemma3RMSNorm.forward]
+template <typename TIn>
+__global__ void __launch_bounds__(NORM_THREADS) rmsnorm_fwd_kernel(const TIn* __restrict__ x,
+                                                                   const __nv_bfloat16* __restrict__ w,
+                                                                   float w_offset, float eps,
+                                                                   __nv_bfloat16* __restrict__ y,
+                                                                   float* __restrict__ rstd_out, int d) {
+  __shared__ float red[NORM_THREADS / 32];
+  const int64_t row = blockIdx.x;
+  const TIn* xr = x + row * d;
+  float ss = 0.f;
+  for (int i = threadIdx.x * 8; i < d; i += NORM_THREADS * 8) {
+    float f[8];
+    load8(xr + i, f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) ss += f[j] * f[j];
+  }
+  ss = block_sum<NORM_THREADS>(ss, red);
+  const float rstd = rsqrtf(ss / float(d) + eps);
+  if (threadIdx.x == 0 && rstd_out != nullptr) rstd_out[row] = rstd;
+  __nv_bfloat16* yr = y + row * d;
+  for (int i = threadIdx.x * 8; i < d; i += NORM_THREADS * 8) {
+    float f[8], wf[8], o[8];
+    load8(xr + i, f);
+    load8(w + i, wf);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      if (w_offset == 0.f)
+        o[j] = wf[j] * round_bf16(f[j] * rstd);
+      else
+        o[j] = (f[j] * rstd) * (w_offset + wf[j]);
+    }
+    store8(yr + i, o);
+  }
+}
+
+// GxI backward: g_x = g_y * (w + w_offset) * rstd  (variance path detached = identity rule)
+template <typename TOut>
+__global__ void __launch_bounds__(NORM_THREADS) rmsnorm_bwd_kernel(const __nv_bfloat16* __restrict__ gy,
+                                                                   const __nv_bfloat16* __restrict__ w,
+                                                                   float w_offset,
+                                                                   const float* __restrict__ rstd,
+                                                                   TOut* __restrict__ gx, int accumulate, int d) {
+  const int64_t row = blockIdx.x;
+  const float r = rstd[row];
+  for (int i = threadIdx.x * 8; i < d; i += NORM_THREADS * 8) {
+    float g[8], wf[8], o[8];
+    load8(gy + row * d + i, g);
+    load8(w + i, wf);
+    if (accumulate) load8(gx + row * d + i, o);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float v;
+      if (sizeof(TOut) == 2 && w_offset == 0.f)
+        v = round_bf16(g[j] * wf[j]) * r;  // bf16 autograd: mul-by-weight node rounds before the rstd node
+      else
+        v = g[j] * (wf[j] + w_offset) * r;
+      o[j] = accumulate ? o[j] + v : v;
+    }
+    store8(gx + row * d + i, o);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// LayerNorm with detached std (ViT path), bf16 or fp32 rows
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(NORM_THREADS) layernorm_fwd_kernel(const T* __restrict__ x, const T* __restrict__ w,
+                                                                     const T* __restrict__ b, float eps,
+                                                                     T* __restrict__ y, float* __restrict__ mean_out,
+                                                                     float* __restrict__ rstd_out, int d) {
+  __shared__ float red[NORM_THREADS / 32];
+  const int64_t row = blockIdx.x;
+  const T* xr = x + row * d;
+  float s = 0.f;
+  for (int i = threadIdx.x * 8; i < d; i += NORM_THREADS * 8) {
+    float f[8];
+    load8(xr + i, f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s += f[j];
+  }
+  const float mean = block_sum<NORM_THREADS>(s, red) / float(d);
+  float ss = 0.f;
+  for (int i = threadIdx.x * 8; i < d; i += NORM_THREADS * 8) {
+    float f[8];
+    load8(xr + i, f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) ss += (f[j] - mean) * (f[j] - mean);
+  }
+  const float var = block_sum<NORM_THREADS>(ss, red) / float(d);
+  const float rstd = 1.f / sqrtf(var + eps);
+  if (threadIdx.x == 0) {
+    if (mean_out) mean_out[row] = mean;
+    if (rstd_out) rstd_out[row] = rstd;
+  }
+  for (int i = threadIdx.x * 8; i < d; i += NORM_THREADS * 8) {
+    float f[8], wf[8], bf[8], o[8];
+    load8(xr + i, f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] = (f[j] - mean) * rstd;
+    if (w != nullptr) {
+      load8(w + i, wf);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] *= wf[j];
+    }
+    if (b != nullptr) {
+      load8(b + i, bf);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] += bf[j];
+    }
+    store8(y + row * d + i, o);
+  }
+}
+
+// y = (x - mean(x)) * rstd * w + b with rstd detached:  g_x = u - mean_d(u),  u = g_y * w * rstd
+template <typename T>
+__global__ void __launch_bounds__(NORM_THREADS) layernorm_bwd_kernel(const T* __restrict__ gy, const T* __restrict__ w,
+                                                                     const float* __restrict__ rstd,
+                                                                     T* __restrict__ gx, int d) {
+  __shared__ float red[NORM_THREADS / 32];
+  const int64_t row = blockIdx.x;
+  const float r = rstd[row];
+  float s = 0.f;
+  for (int i = threadIdx.x * 8; i < d; i += NORM_THREADS * 8) {
+    float g[8], wf[8];
+    load8(gy + row * d + i, g);
+    if (w != nullptr) load8(w + i, wf);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s += g[j] * (w != nullptr ? wf[j] : 1.f) * r;
+  }
+  const float mu = block_sum<NORM_THREADS>(s, red) / float(d);
+  for (int i = threadIdx.x * 8; i < d; i += NORM_THREADS * 8) {
+    float g[8], wf[8], o[8];
+    load8(gy + row * d + i, g);
+    if (w != nullptr) load8(w + i, wf);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] = g[j] * (w != nullptr ? wf[j] : 1.f) * r - mu;
+    store8(gx + row * d + i, o);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// RoPE in place on packed heads (rotate_half convention)
+// ------------------------------------------------------------------------------------------------
+// one thread handles 8 consecutive "pair" indices i..i+7 of one head: x1 = x[i], x2 = x[i + D/2]
+__global__ void __launch_bounds__(256) rope_kernel(__nv_bfloat16* __restrict__ qk, int64_t ld, int n_heads, int D,
+                                                   const float* __restrict__ cos_t, const float* __restrict__ sin_t,
+                                                   int64_t T, int S, int inverse) {
+  const int half = D >> 1;
+  const int chunks_per_head = half >> 3;
+  const int64_t total = T * int64_t(n_heads) * chunks_per_head;
+  for (int64_t idx = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; idx < total;
+       idx += int64_t(gridDim.x) * blockDim.x) {
+    const int c = int(idx % chunks_per_head);
+    const int64_t r = idx / chunks_per_head;
+    const int h = int(r % n_heads);
+    const int64_t t = r / n_heads;
+    const int pos = int(t % S);
+    __nv_bfloat16* p = qk + t * ld + int64_t(h) * D + c * 8;
+    float x1[8], x2[8], cs[8], sn[8], y1[8], y2[8];
+    load8(p, x1);
+    load8(p + half, x2);
+    load8(cos_t + int64_t(pos) * half + c * 8, cs);
+    load8(sin_t + int64_t(pos) * half + c * 8, sn);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float s = inverse ? -sn[j] : sn[j];
+      y1[j] = x1[j] * cs[j] - x2[j] * s;
+      y2[j] = x2[j] * cs[j] + x1[j] * s;
+    }
+    store8(p, y1);
+    store8(p + half, y2);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// activations + identity / uniform rules
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float act_eval(float x, int act) {
+  if (act == LRP_ACT_SILU) return x / (1.f + __expf(-x));
+  if (act == LRP_ACT_GELU_TANH) {
+    const float k = 0.7978845608028654f;
+    return 0.5f * x * (1.f + tanhf(k * (x + 0.044715f * x * x * x)));
+  }
+  return 0.5f * x * (1.f + erff(x * 0.7071067811865476f));
+}
+
+// a = bf16( bf16(act(gate)) * up )
+__global__ void __launch_bounds__(256) gated_act_fwd_kernel(const __nv_bfloat16* __restrict__ gu,
+                                                            __nv_bfloat16* __restrict__ a, int64_t T, int I, int act) {
+  const int chunks = I >> 3;
+  const int64_t total = T * chunks;
+  for (int64_t idx = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; idx < total;
+       idx += int64_t(gridDim.x) * blockDim.x) {
+    const int64_t t = idx / chunks;
+    const int c = int(idx - t * chunks) * 8;
+    float g[8], u[8], o[8];
+    load8(gu + t * 2 * I + c, g);
+    load8(gu + t * 2 * I + I + c, u);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] = round_bf16(act_eval(g[j], act)) * u[j];
+    store8(a + t * I + c, o);
+  }
+}
+
+// g_half = g_a / 2                      (divide_gradient, rules.py:125-127)
+// g_up   = bf16(g_half * s)             s = bf16(act(gate))
+// g_gate = bf16( bf16(s / (gate + 1e-10)) * bf16(g_half * up) )      (identity rule, rules.py:88-100)
+__global__ void __launch_bounds__(256) gated_act_bwd_kernel(const __nv_bfloat16* __restrict__ ga,
+                                                            const __nv_bfloat16* __restrict__ gu,
+                                                            __nv_bfloat16* __restrict__ ggu, int64_t T, int I, int act) {
+  const int chunks = I >> 3;
+  const int64_t total = T * chunks;
+  for (int64_t idx = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; idx < total;
+       idx += int64_t(gridDim.x) * blockDim.x) {
+    const int64_t t = idx / chunks;
+    const int c = int(idx - t * chunks) * 8;
+    float g[8], u[8], d[8], og[8], ou[8];
+    load8(gu + t * 2 * I + c, g);
+    load8(gu + t * 2 * I + I + c, u);
+    load8(ga + t * I + c, d);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float s = round_bf16(act_eval(g[j], act));
+      const float gh = d[j] * 0.5f;
+      ou[j] = gh * s;
+      const float ratio = round_bf16(s / round_bf16(g[j] + 1e-10f));
+      og[j] = ratio * round_bf16(gh * u[j]);
+    }
+    store8(ggu + t * 2 * I + c, og);
+    store8(ggu + t * 2 * I + I + c, ou);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) act_identity_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, int64_t n8,
+                                                               int act) {
+  for (int64_t idx = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; idx < n8; idx += int64_t(gridDim.x) * blockDim.x) {
+    float f[8], o[8];
+    load8(x + idx * 8, f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] = act_eval(f[j], act);
+    store8(y + idx * 8, o);
+  }
+}
+template <typename T>
+__global__ void __launch_bounds__(256) act_identity_bwd_kernel(const T* __restrict__ gy, const T* __restrict__ x,
+                                                               T* __restrict__ gx, int64_t n8, int act) {
+  for (int64_t idx = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; idx < n8; idx += int64_t(gridDim.x) * blockDim.x) {
+    float f[8], g[8], o[8];
+    load8(x + idx * 8, f);
+    load8(gy + idx * 8, g);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float s = act_eval(f[j], act);
+      float den = f[j] + 1e-10f;
+      if (sizeof(T) == 2) { s = round_bf16(s); den = round_bf16(den); }
+      float ratio = s / den;
+      if (sizeof(T) == 2) ratio = round_bf16(ratio);
+      o[j] = ratio * g[j];
+    }
+    store8(gx + idx * 8, o);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// ends of the path
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) embed_gather_kernel(const int64_t* __restrict__ ids,
+                                                           const __nv_bfloat16* __restrict__ emb, float scale,
+                                                           float* __restrict__ h, int d) {
+  const int64_t t = blockIdx.x;
+  const int64_t id = ids[t];
+  for (int i = threadIdx.x * 8; i < d; i += blockDim.x * 8) {
+    float f[8];
+    load8(emb + id * d + i, f);
+    if (scale != 1.f) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] = round_bf16(f[j] * scale);  // HF scales the bf16 embedding in bf16
+    }
+    store8(h + t * d + i, f);
+  }
+}
+
+__global__ void __launch_bounds__(1024) argmax_rows_kernel(const float* __restrict__ logits, int32_t* __restrict__ idx,
+                                                           float* __restrict__ val, int V) {
+  __shared__ float sv[32];
+  __shared__ int si[32];
+  const float* row = logits + int64_t(blockIdx.x) * V;
+  float best = -INFINITY;
+  int bi = 0x7fffffff;
+  for (int i = threadIdx.x; i < V; i += blockDim.x) {
+    const float v = row[i];
+    if (v > best || (v == best && i < bi)) { best = v; bi = i; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+  }
+  if ((threadIdx.x & 31) == 0) { sv[threadIdx.x >> 5] = best; si[threadIdx.x >> 5] = bi; }
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    best = threadIdx.x < (blockDim.x >> 5) ? sv[threadIdx.x] : -INFINITY;
+    bi = threadIdx.x < (blockDim.x >> 5) ? si[threadIdx.x] : 0x7fffffff;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+    }
+    if (threadIdx.x == 0) { idx[blockIdx.x] = bi; if (val) val[blockIdx.x] = best; }
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) gxi_reduce_kernel(const T* __restrict__ x, const T* __restrict__ g,
+                                                         float* __restrict__ rel, int64_t Tn, int d) {
+  // one warp per row
+  const int64_t row = blockIdx.x * int64_t(blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= Tn) return;
+  const int lane = threadIdx.x & 31;
+  float s = 0.f;
+  for (int i = lane * 8; i < d; i += 32 * 8) {
+    float a[8], b[8];
+    load8(x + row * d + i, a);
+    load8(g + row * d + i, b);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float p = a[j] * b[j];
+      if (sizeof(T) == 2) p = round_bf16(p);  // (emb * emb.grad) is a bf16 tensor before .float().sum(-1)
+      s += p;
+    }
+  }
+  s = warp_sum(s);
+  if (lane == 0) rel[row] = s;
+}
+
+__global__ void __launch_bounds__(256) cast_f32_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out,
+                                                            int64_t n8) {
+  for (int64_t idx = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; idx < n8; idx += int64_t(gridDim.x) * blockDim.x) {
+    float f[8];
+    load8(in + idx * 8, f);
+    store8(out + idx * 8, f);
+  }
+}
+
+static inline int grid_for(int64_t work_items, int threads) {
+  int64_t g = (work_items + threads - 1) / threads;
+  const int64_t cap = int64_t(sm_count()) * 16;
+  return int(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
+}  // namespace lrp
+
+using namespace lrp;
+typedef __nv_bfloat16 bf16;
+
+extern "C" {
+
+int lrp_rmsnorm_fwd(const void* x, int x_is_f32, const void* w, float w_offset, float eps, void* y, float* rstd,
+                    int T, int d, void* stream) {
+  if (T <= 0 || d <= 0 || (d % 8) != 0) return set_error(LRP_ERR_ARG, "rmsnorm_fwd: d must be a positive multiple of 8");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (x_is_f32)
+    rmsnorm_fwd_kernel<float><<<T, NORM_THREADS, 0, st>>>((const float*)x, (const bf16*)w, w_offset, eps, (bf16*)y, rstd, d);
+  else
+    rmsnorm_fwd_kernel<bf16><<<T, NORM_THREADS, 0, st>>>((const bf16*)x, (const bf16*)w, w_offset, eps, (bf16*)y, rstd, d);
+  LRP_CHECK_LAUNCH();
+  return LRP_OK;
+}
+
+int lrp_rmsnorm_bwd(const void* gy, const void* w, float w_offset, const float* rstd, void* gx, int gx_is_f32,
+                    int accumulate, int T, int d, void* stream) {
+  if (T <= 0 || d <= 0 || (d % 8) != 0) return set_error(LRP_ERR_ARG, "rmsnorm_bwd: d must be a positive multiple of 8");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (gx_is_f32)
+    rmsnorm_bwd_kernel<float><<<T, NORM_THREADS, 0, st>>>((const bf16*)gy, (const bf16*)w, w_offset, rstd, (float*)gx, accumulate, d);
+  else
+    rmsnorm_bwd_kernel<bf16><<<T, NORM_THREADS, 0, st>>>((const bf16*)gy, (const bf16*)w, w_offset, rstd, (bf16*)gx, accumulate, d);
+  LRP_CHECK_LAUNCH();
+  return LRP_OK;
+}
+
+int lrp_layernorm_fwd(const void* x, const void* w, const void* b, float eps, void* y, float* mean, float* rstd, int T,
+                      int d, int is_f32, void* stream) {
+  if (T <= 0 || d <= 0 || (d % 8) != 0) return set_error(LRP_ERR_ARG, "layernorm_fwd: d must be a positive multiple of 8");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (is_f32)
+    layernorm_fwd_kernel<float><<<T, NORM_THREADS, 0, st>>>((const float*)x, (const float*)w, (const float*)b, eps, (float*)y, mean, rstd, d);
+  else
+    layernorm_fwd_kernel<bf16><<<T, NORM_THREADS, 0, st>>>((const bf16*)x, (const bf16*)w, (const bf16*)b, eps, (bf16*)y, mean, rstd, d);
+  LRP_CHECK_LAUNCH();
+  return LRP_OK;
+}
+
+int lrp_layernorm_bwd(const void* gy, const void* w, const float* rstd, void* gx, int T, int d, int is_f32,
+                      void* stream) {
+  if (T <= 0 || d <= 0 || (d % 8) != 0) return set_error(LRP_ERR_ARG, "layernorm_bwd: d must be a positive multiple of 8");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (is_f32)
+    layernorm_bwd_kernel<float><<<T, NORM_THREADS, 0, st>>>((const float*)gy, (const float*)w, rstd, (float*)gx, d);
+  else
+    layernorm_bwd_kernel<bf16><<<T, NORM_THREADS, 0, st>>>((const bf16*)gy, (const bf16*)w, rstd, (bf16*)gx, d);
+  LRP_CHECK_LAUNCH();
+  return LRP_OK;
+}
+
+int lrp_rope_inplace(void* qk, int64_t ld, int n_heads_total, int D, const float* cos_t, const float* sin_t, int T,
+                     int S, int inverse, void* stream) {
+  if (T <= 0 || n_heads_total <= 0 || D <= 0 || (D % 16) != 0 || (ld % 8) != 0 || S <= 0)
+    return set_error(LRP_ERR_ARG, "rope: D must be a multiple of 16 and ld a multiple of 8");
+  const int64_t total = int64_t(T) * n_heads_total * (D / 16);
+  rope_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>((bf16*)qk, ld, n_heads_total, D, cos_t,
+                                                                                  sin_t, T, S, inverse);
+  LRP_CHECK_LAUNCH();
+  return LRP_OK;
+}
+
+int lrp_gated_act_fwd(const void* gu, void* a, int T, int I, int act, void* stream) {
+  if (T <= 0 || I <= 0 || (I % 8) != 0) return set_error(LRP_ERR_ARG, "gated_act_fwd: I must be a positive multiple of 8");
+  if (act < 0 || act > 2) return set_error(LRP_ERR_ARG, "gated_act_fwd: unknown activation");
+  const int64_t total = int64_t(T) * (I / 8);
+  gated_act_fwd_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>((const bf16*)gu, (bf16*)a, T, I, act);
+  LRP_CHECK_LAUNCH();
+  return LRP_OK;
+}
+
+int lrp_gated_act_bwd(const void* ga, const void* gu, void* ggu, int T, int I, int act, void* stream) {
+  if (T <= 0 || I <= 0 || (I % 8) != 0) return set_error(LRP_ERR_ARG, "gated_act_bwd: I must be a positive multiple of 8");
+  if (act < 0 || act > 2) return set_error(LRP_ERR_ARG, "gated_act_bwd: unknown activation");
+  const int64_t total = int64_t(T) * (I / 8);
+  gated_act_bwd_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>((const bf16*)ga, (const bf16*)gu,
+                                                                                          (bf16*)ggu, T, I, act);
+  LRP_CHECK_LAUNCH();
+  return LRP_OK;
+}
+
+int lrp_act_identity_fwd(const void* x, void* y, int64_t n, int act, int is_f32, void* stream) {
+  if (n <= 0 || (n % 8) != 0) return set_error(LRP_ERR_ARG, "act_identity_fwd: n must be a positive multiple of 8");
+  if (act < 0 || act > 2) return set_error(LRP_ERR_ARG, "act_identity_fwd: unknown activation");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (is_f32)
+    act_identity_fwd_kernel<float><<<grid_for(n / 8, 256), 256, 0, st>>>((const float*)x, (float*)y, n / 8, act);
+  else
+    act_identity_fwd_kernel<bf16><<<grid_for(n / 8, 256), 256, 0, st>>>((const bf16*)x, (bf16*)y, n / 8, act);
+  LRP_CHECK_LAUNCH();
+  return LRP_OK;
+}
+
+int lrp_act_identity_bwd(const void* gy, const void* x, void* gx, int64_t n, int act, int is_f32, void* stream) {
+  if (n <= 0 || (n % 8) != 0) return set_error(LRP_ERR_ARG, "act_identity_bwd: n must be a positive multiple of 8");
+  if (act < 0 || act > 2) return set_error(LRP_ERR_ARG, "act_identity_bwd: unknown activation");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (is_f32)
+    act_identity_bwd_kernel<float><<<grid_for(n / 8, 256), 256, 0, st>>>((const float*)gy, (const float*)x, (float*)gx, n / 8, act);
+  else
+    act_identity_bwd_kernel<bf16><<<grid_for(n / 8, 256), 256, 0, st>>>((const bf16*)gy, (const bf16*)x, (bf16*)gx, n / 8, act);
+  LRP_CHECK_LAUNCH();
+  return LRP_OK;
+}
+
+int lrp_embed_gather(const int64_t* ids, const void* emb, float scale, float* h, int T, int d, void* stream) {
+  if (T <= 0 || d <= 0 || (d % 8) != 0) return set_error(LRP_ERR_ARG, "embed_gather: d must be a positive multiple of 8");
+  embed_gather_kernel<<<T, 256, 0, static_cast<cudaStream_t>(stream)>>>(ids, (const bf16*)emb, scale, h, d);
+  LRP_CHECK_LAUNCH();
+  return LRP_OK;
+}
+
+int lrp_argmax_rows(const float* logits, int32_t* idx, float* val, int B, int V, void* stream) {
+  if (B <= 0 || V <= 0) return set_error(LRP_ERR_ARG, "argmax_rows: empty input");
+  argmax_rows_kernel<<<B, 1024, 0, static_cast<cudaStream_t>(stream)>>>(logits, idx, val, V);
+  LRP_CHECK_LAUNCH();
+  return LRP_OK;
+}
+
+int lrp_gxi_reduce(const float* x, const float* g, float* rel, int T, int d, void* stream) {
+  if (T <= 0 || d <= 0 || (d % 8) != 0) return set_error(LRP_ERR_ARG, "gxi_reduce: d must be a positive multiple of 8");
+  gxi_reduce_kernel<float><<<(T + 7) / 8, 256, 0, static_cast<cudaStream_t>(stream)>>>(x, g, rel, T, d);
+  LRP_CHECK_LAUNCH();
+  return LRP_OK;
+}
+
+int lrp_gxi_reduce_bf16(const void* x, const void* g, float* rel, int T, int d, void* stream) {
+  if (T <= 0 || d <= 0 || (d % 8) != 0) return set_error(LRP_ERR_ARG, "gxi_reduce: d must be a positive multiple of 8");
+  gxi_reduce_kernel<bf16><<<(T + 7) / 8, 256, 0, static_cast<cudaStream_t>(stream)>>>((const bf16*)x, (const bf16*)g, rel, T, d);
+  LRP_CHECK_LAUNCH();
+  return LRP_OK;
+}
+
+int lrp_cast_f32_to_bf16(const float* in, void* out, int64_t n, void* stream) {
+  if (n <= 0 || (n % 8) != 0) return set_error(LRP_ERR_ARG, "cast: n must be a positive multiple of 8");
+  cast_f32_bf16_kernel<<<grid_for(n / 8, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(in, (bf16*)out, n / 8);
+  LRP_CHECK_LAUNCH();
+  return LRP_OK;
+}
+
+}  // extern "C"
