@@ -97,11 +97,13 @@ int lrp_rmsnorm_fwd(const void* x, int x_is_f32, const void* w, float w_offset, 
 int lrp_rmsnorm_bwd(const void* gy, const void* w, float w_offset, const float* rstd, void* gx, int gx_is_f32,
                     int accumulate, int T, int d, void* stream);
 
-/* LayerNorm with detached std (lxt/efficient/patches.py:126-142 `layer_norm_forward`), bf16 in/out.
+/* LayerNorm with detached std (lxt/efficient/patches.py:126-142 `layer_norm_forward`); x,w,b,y all bf16 or
+ * all fp32 (is_f32).
  *   fwd: y = (x-mean)/sqrt(var+eps) * w + b ; saves mean,rstd.  bwd: g_x = (g_y*w*rstd) - mean_d(g_y*w*rstd) */
 int lrp_layernorm_fwd(const void* x, const void* w, const void* b, float eps, void* y, float* mean, float* rstd,
-                      int T, int d, void* stream);
-int lrp_layernorm_bwd(const void* gy, const void* w, const float* rstd, void* gx, int T, int d, void* stream);
+                      int T, int d, int is_f32, void* stream);
+int lrp_layernorm_bwd(const void* gy, const void* w, const float* rstd, void* gx, int T, int d, int is_f32,
+                      void* stream);
 
 /* Rotary embedding applied in place to the q and k slices of a packed qkv buffer [T, ld] (bf16):
  * heads are contiguous D-wide slices; rotate_half convention (transformers modeling_llama.py:146-168).
@@ -121,8 +123,8 @@ int lrp_gated_act_bwd(const void* ga, const void* gu, void* ggu, int T, int I, i
 /* Identity rule on a plain element-wise non-linearity (lxt/efficient/rules.py:88-100,
  * lxt/efficient/patches.py:159-169 `mlp_forward`, :206-211 `non_linear_forward`):
  *   fwd: y = act(x);   bwd: g_x = g_y * act(x)/(x + 1e-10) */
-int lrp_act_identity_fwd(const void* x, void* y, int64_t n, int act, void* stream);
-int lrp_act_identity_bwd(const void* gy, const void* x, void* gx, int64_t n, int act, void* stream);
+int lrp_act_identity_fwd(const void* x, void* y, int64_t n, int act, int is_f32, void* stream);
+int lrp_act_identity_bwd(const void* gy, const void* x, void* gx, int64_t n, int act, int is_f32, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Flash AttnLRP (lxt/efficient/patches.py:171-203: SDPA with dQ/4, dK/4, dV/2; softmax is propagated as

@@ -1,0 +1,617 @@
+// Flash AttnLRP for sm_100a: attention forward and the LRP (Gradient x Input) backward on tcgen05 tensor
+// cores with TMEM accumulators and TMA-staged, 128B-swizzled operand tiles.  No [B,H,S,S] tensor exists in HBM.
+//
+// Rule being implemented (reference: lxt/efficient/patches.py:171-203 `wrap_attention_forward`): the two
+// attention matmuls get the uniform rule, which in GxI space is dQ/4, dK/4, dV/2 around an ordinary
+// softmax-attention backward (the softmax Deep-Taylor rule of lxt/explicit/functional.py:276-322 is the
+// plain softmax backward in GxI space).  CP-LRP (patches.py:249-258) is q_div = k_div = 0.
+//
+// Every operand tile lives in shared memory as 128 rows x (D/64) blocks of 64 bf16 (= 128 B, one swizzle
+// row).  The same bytes serve as a K-major operand (contraction along the row) or as an MN-major operand
+// (contraction across rows) purely by the choice of UMMA descriptor, so P and dS are written once by the
+// softmax threads and consumed three times (dV = P^T dO, dK = dS^T Q, dQ = dS K).
+//
+// Thread roles (160 threads): warps 0-3 own one query row each (row r <-> TMEM lane r, so soft-max needs no
+// shuffles); warp 4 lane 0 issues all TMA loads and all tcgen05.mma.
+#include <math.h>
+#include <string.h>
+#include "ptx_sm100.cuh"
+#include "lrp_internal.h"
+
+namespace lrp {
+
+constexpr int ATT_TILE = 128;       // query rows per CTA tile == keys per tile
+constexpr int ATT_THREADS = 160;
+constexpr float LOG2E = 1.4426950408889634f;
+constexpr float LN2 = 0.6931471805599453f;
+
+struct AttnParams {
+  int B, S, H, Hkv, D;
+  float scale, scale_log2;
+  int causal, window;
+  // forward
+  __nv_bfloat16* o;   // [B,S,H,D]
+  float* lse;         // [B,H,S]
+  // backward
+  const float* delta; // [B,H,S]
+  float* dq_acc;      // [B,S,H,D] fp32
+  __nv_bfloat16* dk;  // [B,S,Hkv,D] strided by lddk
+  __nv_bfloat16* dv;
+  int64_t lddk, lddv;
+  float inv_k_div, inv_v_div;
+};
+
+__device__ __forceinline__ bool is_masked(int qpos, int kpos, int S, int causal, int window) {
+  if (kpos >= S) return true;
+  if (causal && kpos > qpos) return true;
+  if (window > 0 && qpos - kpos >= window) return true;
+  return false;
+}
+
+// write 32 consecutive bf16 columns [c*32, c*32+32) of row r into a [128][128] tile stored as two
+// [128 rows][64 cols] 128B-swizzled blocks
+__device__ __forceinline__ void store_row_chunk_sw128(uint8_t* tile, int r, int c, const float (&f)[32]) {
+  uint8_t* rowp = tile + (c >> 1) * 16384 + r * 128;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int chunk = ((c & 1) * 4 + q) ^ (r & 7);
+    *reinterpret_cast<uint4*>(rowp + chunk * 16) =
+        make_uint4(pack_bf16x2(f[q * 8 + 0], f[q * 8 + 1]), pack_bf16x2(f[q * 8 + 2], f[q * 8 + 3]),
+                   pack_bf16x2(f[q * 8 + 4], f[q * 8 + 5]), pack_bf16x2(f[q * 8 + 6], f[q * 8 + 7]));
+  }
+}
+
+// ---- UMMA issue helpers (single thread) -------------------------------------------------------
+// C[128 x N] (+)= A_kmajor[128 x K] * B_kmajor[N x K]^T, K = KB*64, tiles as [rows][64]-blocks of 16 KiB
+template <int N>
+__device__ __forceinline__ void mma_kk(uint32_t tmem_d, uint32_t a_base, uint32_t b_base, int ktot, bool acc_first) {
+  constexpr uint32_t idesc = make_idesc_bf16(128, N, 0, 0);
+  for (int kk = 0; kk < ktot / 16; ++kk) {
+    const uint32_t off = (kk >> 2) * 16384 + (kk & 3) * 32;
+    tc_mma_ss(tmem_d, make_sdesc_sw128(a_base + off, 16, 1024), make_sdesc_sw128(b_base + off, 16, 1024), idesc,
+              (acc_first || kk > 0) ? 1u : 0u);
+  }
+}
+// C[128 x N] (+)= A_kmajor[128 x 128] * B_mnmajor[128(k) x N]
+template <int N>
+__device__ __forceinline__ void mma_kmn(uint32_t tmem_d, uint32_t a_base, uint32_t b_base, bool acc_first) {
+  constexpr uint32_t idesc = make_idesc_bf16(128, N, 0, 1);
+  for (int kk = 0; kk < 8; ++kk) {
+    const uint32_t aoff = (kk >> 2) * 16384 + (kk & 3) * 32;
+    tc_mma_ss(tmem_d, make_sdesc_sw128(a_base + aoff, 16, 1024), make_sdesc_sw128(b_base + kk * 2048, 16384, 1024),
+              idesc, (acc_first || kk > 0) ? 1u : 0u);
+  }
+}
+// C[128 x N] (+)= A_mnmajor[128(k) x 128(m)]^T * B_mnmajor[128(k) x N]
+template <int N>
+__device__ __forceinline__ void mma_mnmn(uint32_t tmem_d, uint32_t a_base, uint32_t b_base, bool acc_first) {
+  constexpr uint32_t idesc = make_idesc_bf16(128, N, 1, 1);
+  for (int kk = 0; kk < 8; ++kk) {
+    tc_mma_ss(tmem_d, make_sdesc_sw128(a_base + kk * 2048, 16384, 1024),
+              make_sdesc_sw128(b_base + kk * 2048, 16384, 1024), idesc, (acc_first || kk > 0) ? 1u : 0u);
+  }
+}
+
+template <int D>
+__device__ __forceinline__ void load_tile(uint8_t* dst, const CUtensorMap* tm, uint64_t* bar, int col0, int row0, int b) {
+#pragma unroll
+  for (int kb = 0; kb < D / 64; ++kb) tma_load_3d(dst + kb * 16384, tm, bar, col0 + kb * 64, row0, b);
+}
+
+// =================================================================================================
+// forward
+// =================================================================================================
+template <int D>
+__global__ void __launch_bounds__(ATT_THREADS, 1)
+attn_fwd_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__ CUtensorMap tmk,
+                const __grid_constant__ CUtensorMap tmv, const AttnParams p) {
+  constexpr int TILE_BYTES = ATT_TILE * D * 2;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;
+  uint8_t* sK = sQ + TILE_BYTES;       // 2 stages
+  uint8_t* sV = sK + 2 * TILE_BYTES;   // 2 stages
+  uint8_t* sP = sV + 2 * TILE_BYTES;   // 32 KiB
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 32768);
+  uint64_t* q_full = bars;
+  uint64_t* k_full = bars + 1;    // [2]
+  uint64_t* v_full = bars + 3;    // [2]
+  uint64_t* kv_empty = bars + 5;  // [2]
+  uint64_t* s_full = bars + 7;
+  uint64_t* p_full = bars + 8;
+  uint64_t* o_full = bars + 9;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int qt = gridDim.x - 1 - blockIdx.x;  // heaviest causal tiles first
+  const int h = blockIdx.y, b = blockIdx.z;
+  const int hk = h / (p.H / p.Hkv);
+  const int q0 = qt * ATT_TILE;
+  const int nkv = (p.S + ATT_TILE - 1) / ATT_TILE;
+  const int j_hi = p.causal ? min(qt, nkv - 1) : nkv - 1;
+  const int j_lo = p.window > 0 ? max(0, q0 - p.window + 1) / ATT_TILE : 0;
+  const int n = j_hi - j_lo + 1;
+
+  if (warp == 4 && lane == 0) {
+    tma_prefetch_desc(&tmq); tma_prefetch_desc(&tmk); tma_prefetch_desc(&tmv);
+    mbar_init(q_full, 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(&k_full[i], 1); mbar_init(&v_full[i], 1); mbar_init(&kv_empty[i], 1); }
+    mbar_init(s_full, 1);
+    mbar_init(p_full, 128);
+    mbar_init(o_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 4) { tmem_alloc(tmem_slot, 256); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_S = tmem_base, tmem_O = tmem_base + 128;
+
+  if (warp == 4) {
+    if (lane == 0) {
+      mbar_expect_tx(q_full, TILE_BYTES);
+      load_tile<D>(sQ, &tmq, q_full, h * D, q0, b);
+      mbar_expect_tx(&k_full[0], TILE_BYTES);
+      load_tile<D>(sK, &tmk, &k_full[0], hk * D, j_lo * ATT_TILE, b);
+      mbar_expect_tx(&v_full[0], TILE_BYTES);
+      load_tile<D>(sV, &tmv, &v_full[0], hk * D, j_lo * ATT_TILE, b);
+      for (int jj = 0; jj < n; ++jj) {
+        const int st = jj & 1;
+        if (jj + 1 < n) {
+          const int ns = st ^ 1;
+          if (jj >= 1) mbar_wait(&kv_empty[ns], ((jj - 1) >> 1) & 1);
+          mbar_expect_tx(&k_full[ns], TILE_BYTES);
+          load_tile<D>(sK + ns * TILE_BYTES, &tmk, &k_full[ns], hk * D, (j_lo + jj + 1) * ATT_TILE, b);
+          mbar_expect_tx(&v_full[ns], TILE_BYTES);
+          load_tile<D>(sV + ns * TILE_BYTES, &tmv, &v_full[ns], hk * D, (j_lo + jj + 1) * ATT_TILE, b);
+        }
+        if (jj == 0) mbar_wait(q_full, 0);
+        mbar_wait(&k_full[st], (jj >> 1) & 1);
+        tc_fence_after();
+        mma_kk<128>(tmem_S, smem_u32(sQ), smem_u32(sK + st * TILE_BYTES), D, false);
+        tc_commit(s_full);
+        mbar_wait(p_full, jj & 1);
+        mbar_wait(&v_full[st], (jj >> 1) & 1);
+        tc_fence_after();
+        mma_kmn<D>(tmem_O, smem_u32(sP), smem_u32(sV + st * TILE_BYTES), jj > 0);
+        tc_commit(&kv_empty[st]);
+        tc_commit(o_full);
+      }
+    }
+    __syncwarp();
+  } else {
+    const int r = warp * 32 + lane;
+    const int qpos = q0 + r;
+    const uint32_t lane_base = uint32_t(warp * 32) << 16;
+    float m_used = -INFINITY, l = 0.f;
+    for (int jj = 0; jj < n; ++jj) {
+      const int j = j_lo + jj;
+      const int kbase = j * ATT_TILE;
+      const bool need_mask = (p.causal && kbase + ATT_TILE - 1 > q0) || (kbase + ATT_TILE > p.S) ||
+                             (p.window > 0 && q0 + ATT_TILE - 1 - kbase >= p.window);
+      mbar_wait(s_full, jj & 1);
+      tc_fence_after();
+      // pass 1: row maximum
+      float mx = -INFINITY;
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t v[32];
+        tmem_ld32(tmem_S + lane_base + c * 32, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          float t = __uint_as_float(v[i]) * p.scale_log2;
+          if (need_mask && is_masked(qpos, kbase + c * 32 + i, p.S, p.causal, p.window)) t = -INFINITY;
+          mx = fmaxf(mx, t);
+        }
+      }
+      const float m_new = fmaxf(m_used, mx);
+      float alpha = 1.f;
+      if (jj == 0) {
+        m_used = m_new;
+      } else {
+        mbar_wait(o_full, (jj - 1) & 1);  // P.V of the previous tile retired: sP and O may be touched
+        tc_fence_after();
+        const bool want = m_new > m_used + 8.f;   // lazy rescale: only when the max moved by > 2^8
+        if (__any_sync(0xffffffffu, want)) {
+          if (want) {
+            alpha = (m_used == -INFINITY) ? 0.f : exp2f(m_used - m_new);
+            m_used = m_new;
+          }
+#pragma unroll 1
+          for (int c = 0; c < D / 32; ++c) {
+            uint32_t v[32];
+            tmem_ld32(tmem_O + lane_base + c * 32, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
+            tmem_st32(tmem_O + lane_base + c * 32, v);
+          }
+          tmem_st_wait();
+        }
+      }
+      // pass 2: probabilities -> smem (bf16), running sum
+      float lsum = 0.f;
+      const float msub = (m_used == -INFINITY) ? 0.f : m_used;
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t v[32];
+        float f[32];
+        tmem_ld32(tmem_S + lane_base + c * 32, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          float pe = exp2f(__uint_as_float(v[i]) * p.scale_log2 - msub);
+          if (need_mask && is_masked(qpos, kbase + c * 32 + i, p.S, p.causal, p.window)) pe = 0.f;
+          f[i] = pe;
+          lsum += pe;
+        }
+        store_row_chunk_sw128(sP, r, c, f);
+      }
+      l = l * alpha + lsum;
+      fence_proxy_async_smem();
+      tc_fence_before();
+      mbar_arrive(p_full);
+    }
+    mbar_wait(o_full, (n - 1) & 1);
+    tc_fence_after();
+    const float inv_l = l > 0.f ? 1.f / l : 0.f;
+    if (qpos < p.S) p.lse[(int64_t(b) * p.H + h) * p.S + qpos] = l > 0.f ? (m_used + log2f(l)) * LN2 : -INFINITY;
+    __nv_bfloat16* orow = p.o + ((int64_t(b) * p.S + qpos) * p.H + h) * D;
+#pragma unroll 1
+    for (int c = 0; c < D / 32; ++c) {
+      uint32_t v[32];
+      tmem_ld32(tmem_O + lane_base + c * 32, v);
+      tmem_ld_wait();
+      if (qpos < p.S) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          float f[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(v[q * 8 + i]) * inv_l;
+          *reinterpret_cast<uint4*>(orow + c * 32 + q * 8) =
+              make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]),
+                         pack_bf16x2(f[6], f[7]));
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) tmem_dealloc(tmem_base, 256);
+}
+
+// =================================================================================================
+// backward
+// =================================================================================================
+template <int D>
+__global__ void __launch_bounds__(ATT_THREADS, 1)
+attn_bwd_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__ CUtensorMap tmk,
+                const __grid_constant__ CUtensorMap tmv, const __grid_constant__ CUtensorMap tmdo,
+                const AttnParams p) {
+  constexpr int TILE_BYTES = ATT_TILE * D * 2;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sK = smem;
+  uint8_t* sV = sK + TILE_BYTES;
+  uint8_t* sQ = sV + TILE_BYTES;
+  uint8_t* sdO = sQ + TILE_BYTES;
+  uint8_t* sP = sdO + TILE_BYTES;
+  uint8_t* sdS = sP + 32768;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sdS + 32768);
+  uint64_t* kv_full = bars;
+  uint64_t* qdo_full = bars + 1;
+  uint64_t* s_full = bars + 2;
+  uint64_t* p_full = bars + 3;
+  uint64_t* dq_full = bars + 4;
+  uint64_t* dq_empty = bars + 5;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int jt = blockIdx.x, hk = blockIdx.y, b = blockIdx.z;
+  const int G = p.H / p.Hkv;
+  const int k0 = jt * ATT_TILE;
+  const int nq = (p.S + ATT_TILE - 1) / ATT_TILE;
+  const int i_lo = p.causal ? jt : 0;
+  const int i_hi = p.window > 0 ? min(nq - 1, (k0 + ATT_TILE - 1 + p.window - 1) / ATT_TILE) : nq - 1;
+  const int ni = i_hi - i_lo + 1;
+  const int n_it = ni > 0 ? ni * G : 0;
+
+  if (warp == 4 && lane == 0) {
+    tma_prefetch_desc(&tmq); tma_prefetch_desc(&tmk); tma_prefetch_desc(&tmv); tma_prefetch_desc(&tmdo);
+    mbar_init(kv_full, 1);
+    mbar_init(qdo_full, 1);
+    mbar_init(s_full, 1);
+    mbar_init(p_full, 128);
+    mbar_init(dq_full, 1);
+    mbar_init(dq_empty, 128);
+    fence_barrier_init();
+  }
+  if (warp == 4) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_S = tmem_base, tmem_dP = tmem_base + 128, tmem_dV = tmem_base + 256, tmem_dK = tmem_base + 256 + D;
+
+  if (warp == 4) {
+    if (lane == 0 && n_it > 0) {
+      mbar_expect_tx(kv_full, 2 * TILE_BYTES);
+      load_tile<D>(sK, &tmk, kv_full, hk * D, k0, b);
+      load_tile<D>(sV, &tmv, kv_full, hk * D, k0, b);
+      for (int it = 0; it < n_it; ++it) {
+        const int g = it / ni, i = i_lo + (it - g * ni);
+        const int h = hk * G + g;
+        mbar_expect_tx(qdo_full, 2 * TILE_BYTES);
+        load_tile<D>(sQ, &tmq, qdo_full, h * D, i * ATT_TILE, b);
+        load_tile<D>(sdO, &tmdo, qdo_full, h * D, i * ATT_TILE, b);
+        if (it == 0) mbar_wait(kv_full, 0);
+        mbar_wait(qdo_full, it & 1);
+        if (it > 0) mbar_wait(dq_empty, (it - 1) & 1);
+        tc_fence_after();
+        mma_kk<128>(tmem_S, smem_u32(sQ), smem_u32(sK), D, false);    // S  = Q K^T
+        mma_kk<128>(tmem_dP, smem_u32(sdO), smem_u32(sV), D, false);  // dP = dO V^T
+        tc_commit(s_full);
+        mbar_wait(p_full, it & 1);
+        tc_fence_after();
+        mma_mnmn<D>(tmem_dV, smem_u32(sP), smem_u32(sdO), it > 0);    // dV += P^T dO
+        mma_mnmn<D>(tmem_dK, smem_u32(sdS), smem_u32(sQ), it > 0);    // dK += dS^T Q
+        mma_kmn<D>(tmem_S, smem_u32(sdS), smem_u32(sK), false);       // dQ  = dS K   (reuses the S columns)
+        tc_commit(dq_full);
+        mbar_wait(dq_full, it & 1);  // Q/dO/P/dS smem reusable
+      }
+    }
+    __syncwarp();
+  } else {
+    const int r = warp * 32 + lane;
+    const uint32_t lane_base = uint32_t(warp * 32) << 16;
+    for (int it = 0; it < n_it; ++it) {
+      const int g = it / ni, i = i_lo + (it - g * ni);
+      const int h = hk * G + g;
+      const int qpos = i * ATT_TILE + r;
+      const bool valid = qpos < p.S;
+      float lse2 = 0.f, delta = 0.f;
+      if (valid) {
+        lse2 = p.lse[(int64_t(b) * p.H + h) * p.S + qpos] * LOG2E;
+        delta = p.delta[(int64_t(b) * p.H + h) * p.S + qpos];
+      }
+      const bool row_ok = valid && lse2 != -INFINITY;
+      const bool need_mask = (p.causal && k0 + ATT_TILE - 1 > i * ATT_TILE) || (k0 + ATT_TILE > p.S) ||
+                             (p.window > 0 && i * ATT_TILE + ATT_TILE - 1 - k0 >= p.window);
+      mbar_wait(s_full, it & 1);
+      tc_fence_after();
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t vs[32], vd[32];
+        float fp[32], fd[32];
+        tmem_ld32(tmem_S + lane_base + c * 32, vs);
+        tmem_ld32(tmem_dP + lane_base + c * 32, vd);
+        tmem_ld_wait();
+#pragma unroll
+        for (int x = 0; x < 32; ++x) {
+          float pe = 0.f;
+          if (row_ok && !(need_mask && is_masked(qpos, k0 + c * 32 + x, p.S, p.causal, p.window)))
+            pe = exp2f(__uint_as_float(vs[x]) * p.scale_log2 - lse2);
+          fp[x] = pe;
+          fd[x] = pe * (__uint_as_float(vd[x]) - delta) * p.scale;
+        }
+        store_row_chunk_sw128(sP, r, c, fp);
+        store_row_chunk_sw128(sdS, r, c, fd);
+      }
+      fence_proxy_async_smem();
+      tc_fence_before();
+      mbar_arrive(p_full);
+      mbar_wait(dq_full, it & 1);
+      tc_fence_after();
+      float* dqrow = p.dq_acc + ((int64_t(b) * p.S + qpos) * p.H + h) * D;
+#pragma unroll 1
+      for (int c = 0; c < D / 32; ++c) {
+        uint32_t v[32];
+        tmem_ld32(tmem_S + lane_base + c * 32, v);
+        tmem_ld_wait();
+        if (valid) {
+#pragma unroll
+          for (int q = 0; q < 8; ++q)
+            red_add_v4(dqrow + c * 32 + q * 4, __uint_as_float(v[q * 4]), __uint_as_float(v[q * 4 + 1]),
+                       __uint_as_float(v[q * 4 + 2]), __uint_as_float(v[q * 4 + 3]));
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(dq_empty);
+    }
+    // dK, dV of this key tile
+    const int kpos = k0 + r;
+    if (n_it > 0) {
+#pragma unroll 1
+      for (int which = 0; which < 2; ++which) {
+        const uint32_t src = which == 0 ? tmem_dV : tmem_dK;
+        const float sc = which == 0 ? p.inv_v_div : p.inv_k_div;
+        __nv_bfloat16* dst = which == 0 ? p.dv + (int64_t(b) * p.S + kpos) * p.lddv + hk * D
+                                        : p.dk + (int64_t(b) * p.S + kpos) * p.lddk + hk * D;
+#pragma unroll 1
+        for (int c = 0; c < D / 32; ++c) {
+          uint32_t v[32];
+          tmem_ld32(src + lane_base + c * 32, v);
+          tmem_ld_wait();
+          if (kpos < p.S) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+              *reinterpret_cast<uint4*>(dst + c * 32 + q * 8) = make_uint4(
+                  pack_bf16x2(__uint_as_float(v[q * 8]) * sc, __uint_as_float(v[q * 8 + 1]) * sc),
+                  pack_bf16x2(__uint_as_float(v[q * 8 + 2]) * sc, __uint_as_float(v[q * 8 + 3]) * sc),
+                  pack_bf16x2(__uint_as_float(v[q * 8 + 4]) * sc, __uint_as_float(v[q * 8 + 5]) * sc),
+                  pack_bf16x2(__uint_as_float(v[q * 8 + 6]) * sc, __uint_as_float(v[q * 8 + 7]) * sc));
+          }
+        }
+      }
+    } else if (kpos < p.S) {
+      // key tile attended by nobody (cannot happen with causal / full attention, kept for windowed edge cases)
+      for (int c = 0; c < D; c += 8) {
+        *reinterpret_cast<uint4*>(p.dv + (int64_t(b) * p.S + kpos) * p.lddv + hk * D + c) = make_uint4(0, 0, 0, 0);
+        *reinterpret_cast<uint4*>(p.dk + (int64_t(b) * p.S + kpos) * p.lddk + hk * D + c) = make_uint4(0, 0, 0, 0);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) tmem_dealloc(tmem_base, 512);
+}
+
+// delta[b,h,s] = sum_d o[b,s,h,d] * dO[b,s,h,d]   (one warp per row)
+__global__ void __launch_bounds__(256) attn_delta_kernel(const __nv_bfloat16* __restrict__ o,
+                                                         const __nv_bfloat16* __restrict__ d_o, float* __restrict__ delta,
+                                                         int B, int S, int H, int D) {
+  const int64_t row = blockIdx.x * int64_t(blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int64_t rows = int64_t(B) * S * H;
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31;
+  float s = 0.f;
+  for (int i = lane * 2; i < D; i += 64) {
+    const uint32_t a = *reinterpret_cast<const uint32_t*>(o + row * D + i);
+    const uint32_t c = *reinterpret_cast<const uint32_t*>(d_o + row * D + i);
+    s += bf16_lo(a) * bf16_lo(c) + bf16_hi(a) * bf16_hi(c);
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+  if (lane == 0) {
+    const int h = int(row % H);
+    const int64_t bs = row / H;
+    const int sidx = int(bs % S);
+    const int64_t b = bs / S;
+    delta[(b * H + h) * S + sidx] = s;
+  }
+}
+
+// dq[b,s,h,:] = bf16(dq_acc * inv_q_div), dq strided by lddq
+__global__ void __launch_bounds__(256) attn_dq_finish_kernel(const float* __restrict__ acc, __nv_bfloat16* __restrict__ dq,
+                                                             int64_t lddq, int64_t rows, int HD, float inv_q_div) {
+  const int chunks = HD >> 3;
+  const int64_t total = rows * chunks;
+  for (int64_t idx = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; idx < total; idx += int64_t(gridDim.x) * blockDim.x) {
+    const int64_t t = idx / chunks;
+    const int c = int(idx - t * chunks) * 8;
+    const float4 a = *reinterpret_cast<const float4*>(acc + t * HD + c);
+    const float4 b4 = *reinterpret_cast<const float4*>(acc + t * HD + c + 4);
+    *reinterpret_cast<uint4*>(dq + t * lddq + c) =
+        make_uint4(pack_bf16x2(a.x * inv_q_div, a.y * inv_q_div), pack_bf16x2(a.z * inv_q_div, a.w * inv_q_div),
+                   pack_bf16x2(b4.x * inv_q_div, b4.y * inv_q_div), pack_bf16x2(b4.z * inv_q_div, b4.w * inv_q_div));
+  }
+}
+
+template <int D>
+static int fwd_smem_bytes() { return 5 * ATT_TILE * D * 2 + 32768 + 1024 + 256; }
+template <int D>
+static int bwd_smem_bytes() { return 4 * ATT_TILE * D * 2 + 65536 + 1024 + 256; }
+
+static int check_common(const void* q, const void* k, const void* v, int64_t ldq, int64_t ldk, int64_t ldv, int B, int S,
+                        int H, int Hkv, int D) {
+  if (B <= 0 || S <= 0 || H <= 0 || Hkv <= 0) return set_error(LRP_ERR_ARG, "attn: empty problem");
+  if (H % Hkv != 0) return set_error(LRP_ERR_ARG, "attn: H must be a multiple of Hkv");
+  if (D != 64 && D != 128) return set_error(LRP_ERR_ARG, "attn: head_dim must be 64 or 128");
+  if ((ldq % 8) || (ldk % 8) || (ldv % 8)) return set_error(LRP_ERR_ARG, "attn: row strides must be multiples of 8");
+  if ((uintptr_t(q) & 15) || (uintptr_t(k) & 15) || (uintptr_t(v) & 15))
+    return set_error(LRP_ERR_ARG, "attn: q/k/v must be 16-byte aligned");
+  return LRP_OK;
+}
+
+template <int D>
+static int launch_fwd(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnParams& p,
+                      cudaStream_t st) {
+  auto kern = attn_fwd_kernel<D>;
+  static bool done = false;
+  if (!done) {
+    cudaError_t ce = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, fwd_smem_bytes<D>());
+    if (ce != cudaSuccess) return set_error(LRP_ERR_CUDA, cudaGetErrorString(ce));
+    done = true;
+  }
+  dim3 grid((p.S + ATT_TILE - 1) / ATT_TILE, p.H, p.B);
+  kern<<<grid, ATT_THREADS, fwd_smem_bytes<D>(), st>>>(tq, tk, tv, p);
+  LRP_CHECK_LAUNCH();
+  return LRP_OK;
+}
+
+template <int D>
+static int launch_bwd(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const CUtensorMap& tdo,
+                      const AttnParams& p, cudaStream_t st) {
+  auto kern = attn_bwd_kernel<D>;
+  static bool done = false;
+  if (!done) {
+    cudaError_t ce = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bwd_smem_bytes<D>());
+    if (ce != cudaSuccess) return set_error(LRP_ERR_CUDA, cudaGetErrorString(ce));
+    done = true;
+  }
+  dim3 grid((p.S + ATT_TILE - 1) / ATT_TILE, p.Hkv, p.B);
+  kern<<<grid, ATT_THREADS, bwd_smem_bytes<D>(), st>>>(tq, tk, tv, tdo, p);
+  LRP_CHECK_LAUNCH();
+  return LRP_OK;
+}
+
+}  // namespace lrp
+
+using namespace lrp;
+
+extern "C" {
+
+int lrp_attn_fwd(const void* q, const void* k, const void* v, int64_t ldq, int64_t ldk, int64_t ldv, void* o, float* lse,
+                 int B, int S, int H, int Hkv, int D, float scale, int causal, int window, void* stream) {
+  if (int e = check_common(q, k, v, ldq, ldk, ldv, B, S, H, Hkv, D)) return e;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  CUtensorMap tq, tk, tv;
+  if (int e = make_tmap_3d_bf16(&tq, q, uint64_t(H) * D, S, B, ldq, uint64_t(S) * ldq, 64, ATT_TILE)) return e;
+  if (int e = make_tmap_3d_bf16(&tk, k, uint64_t(Hkv) * D, S, B, ldk, uint64_t(S) * ldk, 64, ATT_TILE)) return e;
+  if (int e = make_tmap_3d_bf16(&tv, v, uint64_t(Hkv) * D, S, B, ldv, uint64_t(S) * ldv, 64, ATT_TILE)) return e;
+  AttnParams p;
+  memset(&p, 0, sizeof(p));
+  p.B = B; p.S = S; p.H = H; p.Hkv = Hkv; p.D = D;
+  p.scale = scale; p.scale_log2 = scale * LOG2E;
+  p.causal = causal; p.window = window;
+  p.o = reinterpret_cast<__nv_bfloat16*>(o);
+  p.lse = lse;
+  return D == 128 ? launch_fwd<128>(tq, tk, tv, p, st) : launch_fwd<64>(tq, tk, tv, p, st);
+}
+
+int lrp_attn_bwd(const void* q, const void* k, const void* v, int64_t ldq, int64_t ldk, int64_t ldv, const void* o,
+                 const void* d_o, const float* lse, void* dq, void* dk, void* dv, int64_t lddq, int64_t lddk, int64_t lddv,
+                 float* dq_acc_ws, float* delta_ws, int B, int S, int H, int Hkv, int D, float scale, int causal, int window,
+                 float q_div, float k_div, float v_div, void* stream) {
+  if (int e = check_common(q, k, v, ldq, ldk, ldv, B, S, H, Hkv, D)) return e;
+  if ((lddq % 8) || (lddk % 8) || (lddv % 8)) return set_error(LRP_ERR_ARG, "attn_bwd: gradient strides must be multiples of 8");
+  if (dq_acc_ws == nullptr || delta_ws == nullptr) return set_error(LRP_ERR_ARG, "attn_bwd: missing workspace");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  CUtensorMap tq, tk, tv, tdo;
+  if (int e = make_tmap_3d_bf16(&tq, q, uint64_t(H) * D, S, B, ldq, uint64_t(S) * ldq, 64, ATT_TILE)) return e;
+  if (int e = make_tmap_3d_bf16(&tk, k, uint64_t(Hkv) * D, S, B, ldk, uint64_t(S) * ldk, 64, ATT_TILE)) return e;
+  if (int e = make_tmap_3d_bf16(&tv, v, uint64_t(Hkv) * D, S, B, ldv, uint64_t(S) * ldv, 64, ATT_TILE)) return e;
+  const int64_t HD = int64_t(H) * D;
+  if (int e = make_tmap_3d_bf16(&tdo, d_o, uint64_t(HD), S, B, HD, uint64_t(S) * HD, 64, ATT_TILE)) return e;
+  const int64_t rows = int64_t(B) * S * H;
+  attn_delta_kernel<<<unsigned((rows + 7) / 8), 256, 0, st>>>((const __nv_bfloat16*)o, (const __nv_bfloat16*)d_o, delta_ws, B, S, H, D);
+  LRP_CHECK_LAUNCH();
+  cudaError_t ce = cudaMemsetAsync(dq_acc_ws, 0, size_t(rows) * D * sizeof(float), st);
+  if (ce != cudaSuccess) return set_error(LRP_ERR_CUDA, cudaGetErrorString(ce));
+  AttnParams p;
+  memset(&p, 0, sizeof(p));
+  p.B = B; p.S = S; p.H = H; p.Hkv = Hkv; p.D = D;
+  p.scale = scale; p.scale_log2 = scale * LOG2E;
+  p.causal = causal; p.window = window;
+  p.lse = const_cast<float*>(lse);
+  p.delta = delta_ws;
+  p.dq_acc = dq_acc_ws;
+  p.dk = reinterpret_cast<__nv_bfloat16*>(dk);
+  p.dv = reinterpret_cast<__nv_bfloat16*>(dv);
+  p.lddk = lddk; p.lddv = lddv;
+  p.inv_k_div = k_div > 0.f ? 1.f / k_div : 0.f;
+  p.inv_v_div = v_div > 0.f ? 1.f / v_div : 0.f;
+  if (int e = (D == 128 ? launch_bwd<128>(tq, tk, tv, tdo, p, st) : launch_bwd<64>(tq, tk, tv, tdo, p, st))) return e;
+  const int64_t tok = int64_t(B) * S;
+  const int64_t total = tok * (HD / 8);
+  int64_t g = (total + 255) / 256;
+  if (g > int64_t(sm_count()) * 16) g = int64_t(sm_count()) * 16;
+  attn_dq_finish_kernel<<<unsigned(g), 256, 0, st>>>(dq_acc_ws, (__nv_bfloat16*)dq, lddq, tok, int(HD),
+                                                    q_div > 0.f ? 1.f / q_div : 0.f);
+  LRP_CHECK_LAUNCH();
+  return LRP_OK;
+}
+
+}  // extern "C"

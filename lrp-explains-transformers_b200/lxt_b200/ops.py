@@ -1,0 +1,286 @@
+"""Thin torch-tensor wrappers over the C ABI.  PyTorch is used for device memory and streams only.
+
+Every function launches hand-written sm_100a kernels from liblrp_b200.so on the CURRENT torch CUDA stream and
+raises if the tensors are not CUDA tensors of the documented dtype/layout — there is no eager fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import torch
+
+from . import _capi
+from ._capi import Epilogue, check
+
+ACT_SILU, ACT_GELU_TANH, ACT_GELU_ERF = 0, 1, 2
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _p(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _need(t: torch.Tensor, dtype, name: str) -> None:
+    if not t.is_cuda:
+        raise _capi.LrpError(f"{name}: expected a CUDA tensor (the B200 path has no CPU fallback)")
+    if t.dtype != dtype:
+        raise _capi.LrpError(f"{name}: expected dtype {dtype}, got {t.dtype}")
+
+
+def _rowmajor2d(t: torch.Tensor, name: str) -> int:
+    if t.dim() != 2 or t.stride(1) != 1:
+        raise _capi.LrpError(f"{name}: expected a 2-D tensor with contiguous rows")
+    return t.stride(0)
+
+
+def make_epilogue(out: torch.Tensor, *, resid: Optional[torch.Tensor] = None, rowscale=None, colscale=None, bias=None,
+                  shadow: Optional[torch.Tensor] = None, alpha: float = 1.0) -> Epilogue:
+    ldc = _rowmajor2d(out, "out")
+    e = Epilogue()
+    e.out = out.data_ptr()
+    e.out_is_f32 = 1 if out.dtype == torch.float32 else 0
+    if out.dtype not in (torch.float32, torch.bfloat16):
+        raise _capi.LrpError("gemm output must be bf16 or fp32")
+    for name, t in (("resid", resid), ("rowscale", rowscale), ("colscale", colscale), ("bias", bias)):
+        if t is not None:
+            _need(t, torch.float32, name)
+    if resid is not None and _rowmajor2d(resid, "resid") != ldc:
+        raise _capi.LrpError("resid must share the output's leading dimension")
+    if shadow is not None:
+        _need(shadow, torch.bfloat16, "shadow")
+        if _rowmajor2d(shadow, "shadow") != ldc:
+            raise _capi.LrpError("shadow must share the output's leading dimension")
+    e.shadow_bf16 = _p(shadow)
+    e.resid_f32 = _p(resid)
+    e.rowscale = _p(rowscale)
+    e.colscale = _p(colscale)
+    e.bias = _p(bias)
+    e.alpha = alpha
+    e.ldc = ldc
+    return e
+
+
+def gemm(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor, *, b_layout: int, tile_n: int = 0, **epi) -> torch.Tensor:
+    """out = epilogue(a @ b.T) for b_layout 0 (b is [N,K]) or epilogue(a @ b) for b_layout 1 (b is [K,N])."""
+    _need(a, torch.bfloat16, "a")
+    _need(b, torch.bfloat16, "b")
+    lda, ldb = _rowmajor2d(a, "a"), _rowmajor2d(b, "b")
+    M, K = a.shape
+    N = b.shape[0] if b_layout == 0 else b.shape[1]
+    if (b.shape[1] if b_layout == 0 else b.shape[0]) != K:
+        raise _capi.LrpError(f"gemm: inner dimensions differ ({tuple(a.shape)} vs {tuple(b.shape)}, layout {b_layout})")
+    if tuple(out.shape) != (M, N):
+        raise _capi.LrpError(f"gemm: output shape {tuple(out.shape)} != {(M, N)}")
+    e = make_epilogue(out, **epi)
+    check(_capi.lib().lrp_gemm_bf16(a.data_ptr(), lda, b.data_ptr(), ldb, b_layout, M, N, K, C.byref(e), tile_n, _stream()),
+          "lrp_gemm_bf16")
+    return out
+
+
+def linear_fwd(x: torch.Tensor, w: torch.Tensor, out: torch.Tensor, **epi) -> torch.Tensor:
+    """y = x W^T (+ fused epilogue).  x [T,K] bf16, w [N,K] bf16."""
+    return gemm(x, w, out, b_layout=0, **epi)
+
+
+def linear_dgrad(gy: torch.Tensor, w: torch.Tensor, out: torch.Tensor, **epi) -> torch.Tensor:
+    """g_x = g_y W (+ fused epilogue).  gy [T,N] bf16, w [N,K] bf16 read in place (no transpose copy)."""
+    return gemm(gy, w, out, b_layout=1, **epi)
+
+
+def rmsnorm_fwd(x: torch.Tensor, w: torch.Tensor, eps: float, *, w_offset: float = 0.0, want_rstd: bool = True):
+    """x [T,d] (bf16 or fp32) -> (y bf16 [T,d], rstd fp32 [T])"""
+    if x.dtype not in (torch.float32, torch.bfloat16):
+        raise _capi.LrpError("rmsnorm_fwd: x must be bf16 or fp32")
+    _need(x, x.dtype, "x")
+    _need(w, torch.bfloat16, "w")
+    T, d = x.shape
+    if not x.is_contiguous():
+        raise _capi.LrpError("rmsnorm_fwd: x must be contiguous")
+    y = torch.empty((T, d), dtype=torch.bfloat16, device=x.device)
+    rstd = torch.empty((T,), dtype=torch.float32, device=x.device) if want_rstd else None
+    check(_capi.lib().lrp_rmsnorm_fwd(x.data_ptr(), int(x.dtype == torch.float32), w.data_ptr(), w_offset, eps,
+                                      y.data_ptr(), _p(rstd), T, d, _stream()), "lrp_rmsnorm_fwd")
+    return y, rstd
+
+
+def rmsnorm_bwd(gy: torch.Tensor, w: torch.Tensor, rstd: torch.Tensor, *, w_offset: float = 0.0,
+                out: Optional[torch.Tensor] = None, out_dtype=torch.bfloat16, accumulate: bool = False) -> torch.Tensor:
+    _need(gy, torch.bfloat16, "gy")
+    _need(w, torch.bfloat16, "w")
+    _need(rstd, torch.float32, "rstd")
+    T, d = gy.shape
+    if not gy.is_contiguous():
+        raise _capi.LrpError("rmsnorm_bwd: gy must be contiguous")
+    if out is None:
+        out = torch.empty((T, d), dtype=out_dtype, device=gy.device)
+    check(_capi.lib().lrp_rmsnorm_bwd(gy.data_ptr(), w.data_ptr(), w_offset, rstd.data_ptr(), out.data_ptr(),
+                                      int(out.dtype == torch.float32), int(accumulate), T, d, _stream()), "lrp_rmsnorm_bwd")
+    return out
+
+
+def layernorm_fwd(x: torch.Tensor, w: Optional[torch.Tensor], b: Optional[torch.Tensor], eps: float):
+    if x.dtype not in (torch.float32, torch.bfloat16) or not x.is_cuda or not x.is_contiguous():
+        raise _capi.LrpError("layernorm_fwd: x must be a contiguous CUDA bf16/fp32 tensor")
+    T, d = x.shape
+    y = torch.empty_like(x)
+    mean = torch.empty((T,), dtype=torch.float32, device=x.device)
+    rstd = torch.empty((T,), dtype=torch.float32, device=x.device)
+    check(_capi.lib().lrp_layernorm_fwd(x.data_ptr(), _p(w), _p(b), eps, y.data_ptr(), mean.data_ptr(), rstd.data_ptr(), T, d,
+                                        int(x.dtype == torch.float32), _stream()), "lrp_layernorm_fwd")
+    return y, mean, rstd
+
+
+def layernorm_bwd(gy: torch.Tensor, w: Optional[torch.Tensor], rstd: torch.Tensor) -> torch.Tensor:
+    if gy.dtype not in (torch.float32, torch.bfloat16) or not gy.is_cuda or not gy.is_contiguous():
+        raise _capi.LrpError("layernorm_bwd: gy must be a contiguous CUDA bf16/fp32 tensor")
+    T, d = gy.shape
+    gx = torch.empty_like(gy)
+    check(_capi.lib().lrp_layernorm_bwd(gy.data_ptr(), _p(w), rstd.data_ptr(), gx.data_ptr(), T, d,
+                                        int(gy.dtype == torch.float32), _stream()), "lrp_layernorm_bwd")
+    return gx
+
+
+def rope_inplace(qk: torch.Tensor, n_heads: int, D: int, cos: torch.Tensor, sin: torch.Tensor, S: int, *, inverse: bool = False):
+    """rotate the first n_heads*D columns of qk [T, ld] in place; cos/sin fp32 [S, D/2]."""
+    _need(qk, torch.bfloat16, "qk")
+    _need(cos, torch.float32, "cos")
+    _need(sin, torch.float32, "sin")
+    ld = _rowmajor2d(qk, "qk")
+    check(_capi.lib().lrp_rope_inplace(qk.data_ptr(), ld, n_heads, D, cos.data_ptr(), sin.data_ptr(), qk.shape[0], S,
+                                       int(inverse), _stream()), "lrp_rope_inplace")
+    return qk
+
+
+def gated_act_fwd(gu: torch.Tensor, act: int = ACT_SILU) -> torch.Tensor:
+    _need(gu, torch.bfloat16, "gu")
+    T, I2 = gu.shape
+    if not gu.is_contiguous():
+        raise _capi.LrpError("gated_act_fwd: gu must be contiguous")
+    a = torch.empty((T, I2 // 2), dtype=torch.bfloat16, device=gu.device)
+    check(_capi.lib().lrp_gated_act_fwd(gu.data_ptr(), a.data_ptr(), T, I2 // 2, act, _stream()), "lrp_gated_act_fwd")
+    return a
+
+
+def gated_act_bwd(ga: torch.Tensor, gu: torch.Tensor, act: int = ACT_SILU, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    _need(ga, torch.bfloat16, "ga")
+    _need(gu, torch.bfloat16, "gu")
+    T, I2 = gu.shape
+    if not (ga.is_contiguous() and gu.is_contiguous()):
+        raise _capi.LrpError("gated_act_bwd: inputs must be contiguous")
+    if out is None:
+        out = torch.empty_like(gu)
+    check(_capi.lib().lrp_gated_act_bwd(ga.data_ptr(), gu.data_ptr(), out.data_ptr(), T, I2 // 2, act, _stream()),
+          "lrp_gated_act_bwd")
+    return out
+
+
+def act_identity_fwd(x: torch.Tensor, act: int) -> torch.Tensor:
+    if x.dtype not in (torch.float32, torch.bfloat16) or not x.is_cuda or not x.is_contiguous():
+        raise _capi.LrpError("act_identity_fwd: x must be a contiguous CUDA bf16/fp32 tensor")
+    y = torch.empty_like(x)
+    check(_capi.lib().lrp_act_identity_fwd(x.data_ptr(), y.data_ptr(), x.numel(), act, int(x.dtype == torch.float32), _stream()),
+          "lrp_act_identity_fwd")
+    return y
+
+
+def act_identity_bwd(gy: torch.Tensor, x: torch.Tensor, act: int) -> torch.Tensor:
+    if gy.dtype != x.dtype or not gy.is_cuda or not gy.is_contiguous() or not x.is_contiguous():
+        raise _capi.LrpError("act_identity_bwd: gy/x must be contiguous CUDA tensors of the same dtype")
+    gx = torch.empty_like(x)
+    check(_capi.lib().lrp_act_identity_bwd(gy.data_ptr(), x.data_ptr(), gx.data_ptr(), x.numel(), act,
+                                           int(x.dtype == torch.float32), _stream()), "lrp_act_identity_bwd")
+    return gx
+
+
+def _bshd(t: torch.Tensor, name: str):
+    """accept [B,S,H,D] tensors whose last dim is contiguous, head stride D, batch stride S*token stride"""
+    _need(t, torch.bfloat16, name)
+    B, S, H, D = t.shape
+    if t.stride(3) != 1 or (H > 1 and t.stride(2) != D) or (B > 1 and t.stride(0) != S * t.stride(1)):
+        raise _capi.LrpError(f"{name}: expected [B,S,H,D] with strides (S*ld, ld, D, 1), got {t.stride()}")
+    return t.stride(1)
+
+
+def attn_fwd(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, scale: float, *, causal: bool = True, window: int = 0):
+    """q [B,S,H,D], k/v [B,S,Hkv,D] (views into a packed buffer are fine) -> (o [B,S,H,D] bf16, lse fp32 [B,H,S])"""
+    ldq, ldk, ldv = _bshd(q, "q"), _bshd(k, "k"), _bshd(v, "v")
+    B, S, H, D = q.shape
+    Hkv = k.shape[2]
+    o = torch.empty((B, S, H, D), dtype=torch.bfloat16, device=q.device)
+    lse = torch.empty((B, H, S), dtype=torch.float32, device=q.device)
+    check(_capi.lib().lrp_attn_fwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), ldq, ldk, ldv, o.data_ptr(), lse.data_ptr(),
+                                   B, S, H, Hkv, D, scale, int(causal), window, _stream()), "lrp_attn_fwd")
+    return o, lse
+
+
+def attn_bwd(q, k, v, o, d_o, lse, scale: float, *, causal: bool = True, window: int = 0, q_div: float = 4.0,
+             k_div: float = 4.0, v_div: float = 2.0, dq=None, dk=None, dv=None, dq_acc=None, delta=None):
+    """LRP backward of attention: returns (dq, dk, dv) already divided by (q_div, k_div, v_div)."""
+    ldq, ldk, ldv = _bshd(q, "q"), _bshd(k, "k"), _bshd(v, "v")
+    B, S, H, D = q.shape
+    Hkv = k.shape[2]
+    _need(o, torch.bfloat16, "o")
+    _need(d_o, torch.bfloat16, "d_o")
+    if not (o.is_contiguous() and d_o.is_contiguous()):
+        raise _capi.LrpError("attn_bwd: o and d_o must be contiguous [B,S,H,D]")
+    if dq is None:
+        dq = torch.empty((B, S, H, D), dtype=torch.bfloat16, device=q.device)
+    if dk is None:
+        dk = torch.empty((B, S, Hkv, D), dtype=torch.bfloat16, device=q.device)
+    if dv is None:
+        dv = torch.empty((B, S, Hkv, D), dtype=torch.bfloat16, device=q.device)
+    lddq, lddk, lddv = _bshd(dq, "dq"), _bshd(dk, "dk"), _bshd(dv, "dv")
+    if dq_acc is None:
+        dq_acc = torch.empty((B, S, H, D), dtype=torch.float32, device=q.device)
+    if delta is None:
+        delta = torch.empty((B, H, S), dtype=torch.float32, device=q.device)
+    check(_capi.lib().lrp_attn_bwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), ldq, ldk, ldv, o.data_ptr(), d_o.data_ptr(),
+                                   lse.data_ptr(), dq.data_ptr(), dk.data_ptr(), dv.data_ptr(), lddq, lddk, lddv,
+                                   dq_acc.data_ptr(), delta.data_ptr(), B, S, H, Hkv, D, scale, int(causal), window,
+                                   q_div, k_div, v_div, _stream()), "lrp_attn_bwd")
+    return dq, dk, dv
+
+
+def embed_gather(ids: torch.Tensor, emb: torch.Tensor, scale: float = 1.0) -> torch.Tensor:
+    _need(ids, torch.int64, "ids")
+    _need(emb, torch.bfloat16, "emb")
+    T = ids.numel()
+    d = emb.shape[1]
+    h = torch.empty((T, d), dtype=torch.float32, device=emb.device)
+    check(_capi.lib().lrp_embed_gather(ids.data_ptr(), emb.data_ptr(), scale, h.data_ptr(), T, d, _stream()), "lrp_embed_gather")
+    return h
+
+
+def argmax_rows(logits: torch.Tensor):
+    _need(logits, torch.float32, "logits")
+    B, V = logits.shape
+    idx = torch.empty((B,), dtype=torch.int32, device=logits.device)
+    val = torch.empty((B,), dtype=torch.float32, device=logits.device)
+    check(_capi.lib().lrp_argmax_rows(logits.data_ptr(), idx.data_ptr(), val.data_ptr(), B, V, _stream()), "lrp_argmax_rows")
+    return idx, val
+
+
+def gxi_reduce(x: torch.Tensor, g: torch.Tensor) -> torch.Tensor:
+    """relevance[t] = sum_d x[t,d]*g[t,d]; x,g both fp32 or both bf16, contiguous [T,d]"""
+    if x.dtype != g.dtype or x.shape != g.shape or not (x.is_contiguous() and g.is_contiguous()):
+        raise _capi.LrpError("gxi_reduce: x and g must be contiguous tensors of identical dtype/shape")
+    T, d = x.shape
+    rel = torch.empty((T,), dtype=torch.float32, device=x.device)
+    if x.dtype == torch.float32:
+        check(_capi.lib().lrp_gxi_reduce(x.data_ptr(), g.data_ptr(), rel.data_ptr(), T, d, _stream()), "lrp_gxi_reduce")
+    else:
+        _need(x, torch.bfloat16, "x")
+        check(_capi.lib().lrp_gxi_reduce_bf16(x.data_ptr(), g.data_ptr(), rel.data_ptr(), T, d, _stream()), "lrp_gxi_reduce_bf16")
+    return rel
+
+
+def cast_bf16(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    _need(x, torch.float32, "x")
+    if out is None:
+        out = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
+    check(_capi.lib().lrp_cast_f32_to_bf16(x.data_ptr(), out.data_ptr(), x.numel(), _stream()), "lrp_cast_f32_to_bf16")
+    return out
