@@ -19,13 +19,13 @@
     }                                                                               \
   } while (0)
 
-__global__ void fill_bf16(__nv_bfloat16* p, size_t n, uint32_t seed, float scale) {
+__global__ void fill_bf16(__nv_bfloat16* p, size_t n, uint32_t seed, float scale, float offset = 0.f) {
   size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x;
   if (i >= n) return;
   uint32_t x = uint32_t(i) * 2654435761u + seed;
   x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
   float u = (x & 0xffffff) / float(0x1000000) - 0.5f;
-  p[i] = __float2bfloat16(u * scale);
+  p[i] = __float2bfloat16(u * scale + offset);
 }
 __global__ void fill_f32(float* p, size_t n, uint32_t seed, float scale, float offset) {
   size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x;
@@ -176,6 +176,79 @@ static void perf_case(int M, int N, int K, int b_layout, int tile_n, int mode) {
   cudaFree(A); cudaFree(B); cudaFree(Cb); cudaFree(Cf);
 }
 
+
+// ---- fused eps-LRP Linear rule -------------------------------------------------------------------
+__global__ void ref_z(const __nv_bfloat16* x, const __nv_bfloat16* W, const float* bias, int T, int N, int K, float* z) {
+  int n = blockIdx.x * blockDim.x + threadIdx.x, t = blockIdx.y;
+  if (n >= N) return;
+  float acc = 0.f;
+  for (int k = 0; k < K; ++k) acc += __bfloat162float(x[size_t(t) * K + k]) * __bfloat162float(W[size_t(n) * K + k]);
+  z[size_t(t) * N + n] = acc + (bias ? bias[n] : 0.f);
+}
+__global__ void ref_rin(const __nv_bfloat16* x, const __nv_bfloat16* W, const float* z, const float* R, int T, int N, int K,
+                        float eps, float* rin) {
+  int k = blockIdx.x * blockDim.x + threadIdx.x, t = blockIdx.y;
+  if (k >= K) return;
+  float acc = 0.f;
+  for (int n = 0; n < N; ++n) {
+    float s = R[size_t(t) * N + n] / (z[size_t(t) * N + n] + eps);
+    acc += __bfloat162float(__float2bfloat16(s)) * __bfloat162float(W[size_t(n) * K + k]);
+  }
+  rin[size_t(t) * K + k] = acc * __bfloat162float(x[size_t(t) * K + k]);
+}
+
+static void eps_case(int T, int N, int K, bool with_bias, bool perf) {
+  __nv_bfloat16 *x, *W, *s_ws;
+  float *R, *Rin, *z, *ref, *bias;
+  int32_t* flags;
+  CK(cudaMalloc(&x, size_t(T) * K * 2)); CK(cudaMalloc(&W, size_t(N) * K * 2)); CK(cudaMalloc(&s_ws, size_t(T) * N * 2));
+  CK(cudaMalloc(&R, size_t(T) * N * 4)); CK(cudaMalloc(&Rin, size_t(T) * K * 4)); CK(cudaMalloc(&z, size_t(T) * N * 4));
+  CK(cudaMalloc(&ref, size_t(T) * K * 4)); CK(cudaMalloc(&bias, size_t(N) * 4));
+  const int64_t nf = lrp_linear_eps_flags_count(T);
+  CK(cudaMalloc(&flags, nf * 4));
+  // positive operands keep z away from 0 so that the comparison is well conditioned
+  fill_bf16<<<(size_t(T) * K + 255) / 256, 256>>>(x, size_t(T) * K, 21u, 1.f, 1.f);
+  fill_bf16<<<(size_t(N) * K + 255) / 256, 256>>>(W, size_t(N) * K, 23u, 1.f, 1.f);
+  fill_f32<<<(size_t(T) * N + 255) / 256, 256>>>(R, size_t(T) * N, 25u, 2.f, 0.f);
+  fill_f32<<<(N + 255) / 256, 256>>>(bias, N, 27u, 1.f, 1.f);
+  CK(cudaMemset(Rin, 0xff, size_t(T) * K * 4));
+  CK(cudaMemset(flags, 0, nf * 4));
+  int rc = lrp_linear_eps_bwd(x, W, with_bias ? bias : nullptr, R, 1, Rin, s_ws, flags, T, N, K, 1e-6f, 0);
+  if (rc) { printf("FAIL eps rc=%d %s\n", rc, lrp_last_error()); g_fail++; return; }
+  cudaError_t ce = cudaDeviceSynchronize();
+  if (ce != cudaSuccess) { printf("FAIL eps exec %s\n", cudaGetErrorString(ce)); exit(3); }
+  if (!perf) {
+    ref_z<<<dim3((N + 127) / 128, T), 128>>>(x, W, with_bias ? bias : nullptr, T, N, K, z);
+    ref_rin<<<dim3((K + 127) / 128, T), 128>>>(x, W, z, R, T, N, K, 1e-6f, ref);
+    CK(cudaDeviceSynchronize());
+    std::vector<float> a(size_t(T) * K), b(size_t(T) * K);
+    CK(cudaMemcpy(a.data(), Rin, a.size() * 4, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(b.data(), ref, b.size() * 4, cudaMemcpyDeviceToHost));
+    double num = 0, den = 0;
+    for (size_t i = 0; i < a.size(); ++i) { double d = double(a[i]) - b[i]; if (!(a[i] == a[i])) d = 1e30; num += d * d; den += double(b[i]) * b[i]; }
+    double rel = sqrt(num / (den + 1e-30));
+    bool ok = rel < 2e-3;
+    printf("%s eps-linear T=%d N=%d K=%d bias=%d rel_l2=%.3e\n", ok ? "ok  " : "FAIL", T, N, K, int(with_bias), rel);
+    if (!ok) g_fail++;
+  } else {
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    const int iters = 5;
+    float tot = 0;
+    for (int i = 0; i < iters; ++i) {
+      CK(cudaMemsetAsync(flags, 0, nf * 4));
+      cudaEventRecord(e0);
+      lrp_linear_eps_bwd(x, W, nullptr, R, 1, Rin, s_ws, flags, T, N, K, 1e-6f, 0);
+      cudaEventRecord(e1);
+      CK(cudaDeviceSynchronize());
+      float ms; cudaEventElapsedTime(&ms, e0, e1); tot += ms;
+    }
+    tot /= iters;
+    printf("perf eps-linear T=%d N=%d K=%d: %.3f ms  %.1f TFLOP/s (4TKN)\n", T, N, K, tot, 4.0 * T * N * K / tot * 1e-9);
+  }
+  cudaFree(x); cudaFree(W); cudaFree(s_ws); cudaFree(R); cudaFree(Rin); cudaFree(z); cudaFree(ref); cudaFree(bias); cudaFree(flags);
+}
+
 int main(int argc, char** argv) {
   bool perf = argc > 1 && !strcmp(argv[1], "--perf");
   if (lrp_check_device() != 0) { printf("no device: %s\n", lrp_last_error()); return 1; }
@@ -190,6 +263,10 @@ int main(int argc, char** argv) {
   check_case(128 * 40, 256 * 8, 512, 0, 256, 0);
   check_case(128 * 40, 256 * 8, 512, 1, 256, 1);
   check_case(128 * 37, 128 * 9, 192, 1, 128, 0);
+  eps_case(128, 256, 256, false, false);
+  eps_case(300, 520, 200, true, false);
+  eps_case(1500, 1024, 768, true, false);
+  eps_case(4096, 2048, 1024, false, false);
   printf(g_fail ? "SELFTEST FAILED (%d)\n" : "SELFTEST PASSED\n", g_fail);
   if (perf) {
     perf_case(8192, 4096, 4096, 0, 256, 0);
@@ -201,6 +278,8 @@ int main(int argc, char** argv) {
     perf_case(16384, 4096, 28672, 1, 256, 1);
     perf_case(16384, 14336, 4096, 1, 256, 0);
     perf_case(16384, 6144, 4096, 0, 256, 0);
+    eps_case(16384, 4096, 4096, false, true);
+    eps_case(16384, 14336, 4096, false, true);
   }
   return g_fail ? 1 : 0;
 }
