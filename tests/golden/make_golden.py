@@ -1,0 +1,184 @@
+"""Generate golden vectors by running the REAL reference (rachtibat/LRP-eXplains-Transformers, `lxt` 2.1).
+
+Run in the build container (the reference is not available on the GPU box):
+
+    PYTHONPATH=/root/reference python tests/golden/make_golden.py
+
+Writes small .npz fixtures next to this file.  Nothing here is imported by the product or by the GPU tests; the
+tests only read the .npz files.  Fixtures:
+
+  rules.npz        lxt.explicit.functional / lxt.explicit.rules / lxt.efficient.rules on seeded inputs
+                   (shapes of the reference's own tests/test_rules.py, tests/test_functional.py + the BASELINE
+                   "2-layer 128-d MLP" epsilon-rule case)
+  llama_tiny_*.npz lxt.efficient.monkey_patch(modeling_llama) on seeded tiny HuggingFace Llama models:
+                   token ids, weights (bf16 bit patterns), relevance from an fp32 run and from a bf16 run.
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+
+import lxt.explicit.functional as lf  # noqa: E402  (the reference)
+import lxt.explicit.rules as lrules  # noqa: E402
+import lxt.efficient.rules as erules  # noqa: E402
+from lxt.efficient import monkey_patch  # noqa: E402
+from transformers import LlamaConfig, LlamaForCausalLM  # noqa: E402
+from transformers.models.llama import modeling_llama  # noqa: E402
+
+from oracle.attnlrp_oracle import random_llama_weights  # noqa: E402  (weight generator only)
+
+
+def bf16_bits(t: torch.Tensor) -> np.ndarray:
+    return t.to(torch.bfloat16).view(torch.int16).numpy().astype(np.uint16)
+
+
+def gen_rules():
+    out = {}
+    g = torch.Generator().manual_seed(1234)
+    rn = lambda *s: torch.randn(*s, generator=g)
+
+    # tests/test_rules.py:9-24 : EpsilonRule(partial(F.linear, W, b)) vs lf.linear_epsilon
+    x, W, b, R = rn(1, 5), rn(5, 5), rn(5), rn(1, 5)
+    xx = x.clone().requires_grad_()
+    y = lf.linear_epsilon(xx, W, b, 1e-6)
+    y.backward(R)
+    out.update(le_x=x, le_W=W, le_b=b, le_R=R, le_y=y.detach(), le_Rin=xx.grad.clone())
+    xx = x.clone().requires_grad_()
+    import functools
+    rule = lrules.EpsilonRule(functools.partial(torch.nn.functional.linear, weight=W, bias=b), epsilon=1e-6)
+    y2 = rule(xx)
+    y2.backward(R)
+    out.update(le_rule_Rin=xx.grad.clone())
+
+    # tests/test_functional.py:57-76 shapes
+    x, W, R = rn(16, 10), rn(5, 10), rn(16, 5)
+    xx = x.clone().requires_grad_()
+    lf.linear_epsilon(xx, W, None, 1e-9).backward(R)
+    out.update(lin_x=x, lin_W=W, lin_R=R, lin_Rin=xx.grad.clone())
+
+    # BASELINE config[0]: 2-layer 128-d MLP under the epsilon rule, CPU fp32
+    x, W1, b1, W2, b2, R = rn(8, 128), rn(128, 128) * 0.1, rn(128) * 0.1, rn(128, 128) * 0.1, rn(128) * 0.1, rn(8, 128)
+    xx = x.clone().requires_grad_()
+    h1 = lf.linear_epsilon(xx, W1, b1, 1e-6)
+    h2 = lf.linear_epsilon(h1, W2, b2, 1e-6)
+    h2.backward(R)
+    out.update(mlp_x=x, mlp_W1=W1, mlp_b1=b1, mlp_W2=W2, mlp_b2=b2, mlp_R=R, mlp_h1=h1.detach(), mlp_Rin=xx.grad.clone())
+
+    # matmul (test_functional.py:29-54)
+    a, bb, R = rn(2, 10, 32), rn(2, 32, 5), rn(2, 10, 5)
+    aa, b2_ = a.clone().requires_grad_(), bb.clone().requires_grad_()
+    lf.matmul(aa, b2_, False, 1e-9).backward(R)
+    out.update(mm_a=a, mm_b=bb, mm_R=R, mm_Ra=aa.grad.clone(), mm_Rb=b2_.grad.clone())
+
+    # softmax (test_functional.py:8-26, called with inplace as keyword)
+    x, R = rn(16, 10, 32), rn(16, 10, 32)
+    xx = x.clone().requires_grad_()
+    lf.softmax(xx, -1, None, 1.0, inplace=False).backward(R)
+    out.update(sm_x=x, sm_R=R, sm_Rin=xx.grad.clone())
+
+    # add2 / mul2 / rms_norm_identity
+    a, bb, R = rn(16, 10, 32), rn(16, 10, 32), rn(16, 10, 32)
+    aa, b2_ = a.clone().requires_grad_(), bb.clone().requires_grad_()
+    lf.add2(aa, b2_, False, 1e-8).backward(R)
+    out.update(add_a=a, add_b=bb, add_R=R, add_Ra=aa.grad.clone(), add_Rb=b2_.grad.clone())
+    aa, b2_ = a.clone().requires_grad_(), bb.clone().requires_grad_()
+    lf.mul2(aa, b2_).backward(R)
+    out.update(mul_Ra=aa.grad.clone(), mul_Rb=b2_.grad.clone())
+    x, w, R = rn(1, 4, 32), rn(32), rn(1, 4, 32)
+    xx = x.clone().requires_grad_()
+    yn = lf.rms_norm_identity(xx, w, 1e-6)
+    yn.backward(R)
+    out.update(rms_x=x, rms_w=w, rms_R=R, rms_y=yn.detach(), rms_Rin=xx.grad.clone())
+
+    # UniformEpsilonRule on a matmul module (rules.py:253-282)
+    class MM(torch.nn.Module):
+        def forward(self, p, q):
+            return torch.matmul(p, q)
+    a, bb, R = rn(2, 6, 16), rn(2, 16, 8), rn(2, 6, 8)
+    aa, b2_ = a.clone().requires_grad_(), bb.clone().requires_grad_()
+    lrules.UniformEpsilonRule(MM(), epsilon=1e-6)(aa, b2_).backward(R)
+    out.update(ue_a=a, ue_b=bb, ue_R=R, ue_Ra=aa.grad.clone(), ue_Rb=b2_.grad.clone())
+
+    # efficient rules: identity_rule_implicit(silu / gelu), divide_gradient
+    x, gout = rn(4, 64), rn(4, 64)
+    for name, fn in (("silu", torch.nn.functional.silu), ("gelu", torch.nn.functional.gelu),
+                     ("gelu_tanh", lambda t: torch.nn.functional.gelu(t, approximate="tanh"))):
+        xx = x.clone().requires_grad_()
+        erules.identity_rule_implicit(fn, xx).backward(gout)
+        out[f"id_{name}_g"] = xx.grad.clone()
+    xx = x.clone().requires_grad_()
+    erules.divide_gradient(xx * 1.0, 4).backward(gout)
+    out.update(id_x=x, id_gout=gout, div4_g=xx.grad.clone())
+    np.savez_compressed(os.path.join(HERE, "rules.npz"), **{k: v.numpy() for k, v in out.items()})
+    print("rules.npz:", len(out), "arrays")
+
+
+_patched = False
+
+
+def gen_llama(name, cfg, B, S, seed):
+    global _patched
+    if not _patched:
+        monkey_patch(modeling_llama, verbose=True)
+        _patched = True
+    w = random_llama_weights(cfg, seed=seed, std=0.02, dtype=torch.bfloat16)
+    # make the norm weights non-trivial so that the w*rstd path is exercised
+    g = torch.Generator().manual_seed(seed + 100)
+    for lw in w["layers"]:
+        lw["ln1"] = (1 + 0.1 * torch.randn(cfg["d"], generator=g)).to(torch.bfloat16)
+        lw["ln2"] = (1 + 0.1 * torch.randn(cfg["d"], generator=g)).to(torch.bfloat16)
+    w["norm"] = (1 + 0.1 * torch.randn(cfg["d"], generator=g)).to(torch.bfloat16)
+    ids = torch.randint(0, cfg["V"], (B, S), generator=torch.Generator().manual_seed(seed + 1))
+    hf_cfg = LlamaConfig(hidden_size=cfg["d"], intermediate_size=cfg["I"], num_hidden_layers=cfg["L"],
+                         num_attention_heads=cfg["H"], num_key_value_heads=cfg["Hkv"], head_dim=cfg["D"],
+                         vocab_size=cfg["V"], rms_norm_eps=cfg["eps"],
+                         rope_parameters={"rope_type": "default", "rope_theta": cfg["theta"]},
+                         max_position_embeddings=max(512, S), attention_bias=False, tie_word_embeddings=False)
+    res = {}
+    for dt, tag in ((torch.float32, "fp32"), (torch.bfloat16, "bf16")):
+        for impl in ("sdpa", "eager"):
+            hf_cfg._attn_implementation = impl
+            model = LlamaForCausalLM(hf_cfg).to(dt).eval()
+            sd = {"model.embed_tokens.weight": w["emb"], "model.norm.weight": w["norm"], "lm_head.weight": w["lm_head"]}
+            for i, lw in enumerate(w["layers"]):
+                p = f"model.layers.{i}."
+                sd.update({p + "self_attn.q_proj.weight": lw["wq"], p + "self_attn.k_proj.weight": lw["wk"],
+                           p + "self_attn.v_proj.weight": lw["wv"], p + "self_attn.o_proj.weight": lw["wo"],
+                           p + "mlp.gate_proj.weight": lw["wg"], p + "mlp.up_proj.weight": lw["wu"],
+                           p + "mlp.down_proj.weight": lw["wd"], p + "input_layernorm.weight": lw["ln1"],
+                           p + "post_attention_layernorm.weight": lw["ln2"]})
+            missing = model.load_state_dict({k: v.to(dt) for k, v in sd.items()}, strict=True)
+            for p_ in model.parameters():
+                p_.requires_grad_(False)
+            # examples/quantized_llama.py:35-47
+            emb = model.get_input_embeddings()(ids)
+            emb = emb.detach().requires_grad_()
+            logits = model(inputs_embeds=emb, use_cache=False).logits
+            max_logits, max_idx = torch.max(logits[:, -1, :], dim=-1)
+            max_logits.sum().backward()
+            rel = (emb * emb.grad).float().sum(-1)
+            res[f"rel_{tag}_{impl}"] = rel.detach().numpy()
+            res[f"idx_{tag}_{impl}"] = max_idx.numpy()
+            res[f"gemb_{tag}_{impl}"] = emb.grad.float().numpy()
+    print(name, "sdpa-vs-eager fp32 rel diff",
+          float(np.linalg.norm(res["rel_fp32_sdpa"] - res["rel_fp32_eager"]) / np.linalg.norm(res["rel_fp32_eager"])),
+          " bf16-vs-fp32", float(np.linalg.norm(res["rel_bf16_sdpa"] - res["rel_fp32_sdpa"]) / np.linalg.norm(res["rel_fp32_sdpa"])))
+    save = dict(ids=ids.numpy(), cfg_keys=np.array(list(cfg.keys())), cfg_vals=np.array([float(v) for v in cfg.values()]))
+    save.update({"w_emb": bf16_bits(w["emb"]), "w_norm": bf16_bits(w["norm"]), "w_lm_head": bf16_bits(w["lm_head"])})
+    for i, lw in enumerate(w["layers"]):
+        for k, v in lw.items():
+            save[f"w_l{i}_{k}"] = bf16_bits(v)
+    save.update(res)
+    np.savez_compressed(os.path.join(HERE, f"{name}.npz"), **save)
+
+
+if __name__ == "__main__":
+    torch.manual_seed(0)
+    gen_rules()
+    gen_llama("llama_tiny_d64", dict(d=256, I=512, H=4, Hkv=2, D=64, L=2, V=256, eps=1e-5, theta=10000.0), B=2, S=160, seed=0)
+    gen_llama("llama_tiny_d128", dict(d=256, I=384, H=2, Hkv=1, D=128, L=2, V=320, eps=1e-5, theta=500000.0), B=1, S=130, seed=7)
