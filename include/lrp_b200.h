@@ -37,6 +37,8 @@ extern "C" {
 int lrp_version(void);
 /* thread-local description of the last error returned on this thread ("" if none) */
 const char* lrp_last_error(void);
+/* number of GPU kernels (and memset nodes) this library has enqueued in this process so far */
+int64_t lrp_launch_count(void);
 /* 0 if an sm_100 device is present and usable, LRP_ERR_NO_DEVICE otherwise */
 int lrp_check_device(void);
 
@@ -115,8 +117,8 @@ int lrp_rope_inplace(void* qk, int64_t ld, int n_heads_total, int D, const float
 /* Gated MLP point-wise part with the identity rule on the activation and the uniform rule on the product
  * (lxt/efficient/patches.py:145-157 `gated_mlp_forward`, lxt/efficient/rules.py:69-127).
  *   fwd: a = act(gate) * up                          gu = [T, 2I] bf16 (gate | up), a = [T, I] bf16
- *   bwd: g_up = (g_a/2) * act(gate);  g_gate = (g_a/2) * up * act(gate)/(gate + 1e-10)     (bf16 roundings
- *        of act(gate) and of the ratio follow the reference's bf16 tensors) */
+ *   bwd: g_up = (g_a/2) * act(gate);  g_gate = (g_a/2) * up * act(gate)/(gate + 1e-10)
+ *        (fp32 arithmetic on the bf16 inputs, one rounding per output) */
 int lrp_gated_act_fwd(const void* gu, void* a, int T, int I, int act, void* stream);
 int lrp_gated_act_bwd(const void* ga, const void* gu, void* ggu, int T, int I, int act, void* stream);
 

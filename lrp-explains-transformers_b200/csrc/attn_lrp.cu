@@ -590,6 +590,7 @@ int lrp_attn_bwd(const void* q, const void* k, const void* v, int64_t ldq, int64
   LRP_CHECK_LAUNCH();
   cudaError_t ce = cudaMemsetAsync(dq_acc_ws, 0, size_t(rows) * D * sizeof(float), st);
   if (ce != cudaSuccess) return set_error(LRP_ERR_CUDA, cudaGetErrorString(ce));
+  note_launch();  // the memset node
   AttnParams p;
   memset(&p, 0, sizeof(p));
   p.B = B; p.S = S; p.H = H; p.Hkv = Hkv; p.D = D;

@@ -2,6 +2,7 @@
 // entry points declared in include/lrp_b200.h.
 #include <stdio.h>
 #include <string.h>
+#include <atomic>
 #include <mutex>
 #include "lrp_internal.h"
 
@@ -14,6 +15,9 @@ int set_error(int code, const char* msg) {
   g_err[sizeof(g_err) - 1] = 0;
   return code;
 }
+
+static std::atomic<long long> g_launches{0};
+void note_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
 int sm_count() {
   static int cached = 0;
@@ -96,6 +100,8 @@ extern "C" {
 int lrp_version(void) { return 1000; }
 
 const char* lrp_last_error(void) { return g_err; }
+
+int64_t lrp_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
 int lrp_check_device(void) {
   int n = 0;

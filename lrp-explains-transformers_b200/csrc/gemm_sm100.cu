@@ -271,8 +271,7 @@ static int launch_gemm(const void* A, int64_t lda, const void* B, int64_t ldb, c
   const int num_tiles = ((p.M + BM - 1) / BM) * ((p.N + BN - 1) / BN);
   const int grid = num_tiles < sm_count() ? num_tiles : sm_count();
   kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(ta, tb, p);
-  cudaError_t ce = cudaGetLastError();
-  if (ce != cudaSuccess) return set_error(LRP_ERR_CUDA, cudaGetErrorString(ce));
+  LRP_CHECK_LAUNCH();
   return LRP_OK;
 }
 

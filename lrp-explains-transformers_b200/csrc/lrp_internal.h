@@ -9,6 +9,7 @@ namespace lrp {
 
 int set_error(int code, const char* msg);  // stores a thread-local message, returns code
 int sm_count();                            // SM count of the current device (cached)
+void note_launch(int n = 1);               // process-wide count of kernels this library enqueued
 
 // Encode a 2-D bf16 tiled tensor map with 128-byte swizzle.
 //   dim0 = contiguous extent (elements), dim1 = rows, ld = row pitch (elements), box0 x box1 = tile.
@@ -29,6 +30,7 @@ int linear_eps_bwd(const void* x, const void* W, const float* bias, const void* 
   do {                                                                       \
     cudaError_t ce__ = cudaGetLastError();                                   \
     if (ce__ != cudaSuccess) return set_error(LRP_ERR_CUDA, cudaGetErrorString(ce__)); \
+    note_launch();                                                           \
   } while (0)
 
 }  // namespace lrp

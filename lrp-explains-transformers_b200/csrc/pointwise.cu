@@ -51,8 +51,9 @@ __device__ __forceinline__ void store8(float* p, const float (&f)[8]) {
 // ------------------------------------------------------------------------------------------------
 constexpr int NORM_THREADS = 256;
 
-// Llama (w_offset == 0): y = bf16( w * bf16(x * rstd) )      [patches.py:118-123: downcast, then weight *]
-// Gemma (w_offset != 0): y = bf16( (x * rstd) * (w_offset + w) )   [gemma3.py:11-12 + HF Gemma3RMSNorm.forward]
+// y = bf16( (x * rstd) * (w_offset + w) ), all arithmetic in fp32 with one final rounding.
+//   Llama: w_offset = 0 (patches.py:111-123; the reference's intermediate bf16 downcast before `weight *` is a
+//   storage artefact of its bf16 tensors, not part of the rule);  Gemma: w_offset = 1 (gemma3.py:11-12).
 template <typename TIn>
 __global__ void __launch_bounds__(NORM_THREADS) rmsnorm_fwd_kernel(const TIn* __restrict__ x,
                                                                    const __nv_bfloat16* __restrict__ w,
@@ -79,10 +80,7 @@ __global__ void __launch_bounds__(NORM_THREADS) rmsnorm_fwd_kernel(const TIn* __
     load8(w + i, wf);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      if (w_offset == 0.f)
-        o[j] = wf[j] * round_bf16(f[j] * rstd);
-      else
-        o[j] = (f[j] * rstd) * (w_offset + wf[j]);
+      o[j] = (f[j] * rstd) * (w_offset + wf[j]);
     }
     store8(yr + i, o);
   }
@@ -104,11 +102,7 @@ __global__ void __launch_bounds__(NORM_THREADS) rmsnorm_bwd_kernel(const __nv_bf
     if (accumulate) load8(gx + row * d + i, o);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      float v;
-      if (sizeof(TOut) == 2 && w_offset == 0.f)
-        v = round_bf16(g[j] * wf[j]) * r;  // bf16 autograd: mul-by-weight node rounds before the rstd node
-      else
-        v = g[j] * (wf[j] + w_offset) * r;
+      const float v = g[j] * (wf[j] + w_offset) * r;
       o[j] = accumulate ? o[j] + v : v;
     }
     store8(gx + row * d + i, o);
@@ -239,7 +233,7 @@ __device__ __forceinline__ float act_eval(float x, int act) {
   return 0.5f * x * (1.f + erff(x * 0.7071067811865476f));
 }
 
-// a = bf16( bf16(act(gate)) * up )
+// a = bf16( act(gate) * up )
 __global__ void __launch_bounds__(256) gated_act_fwd_kernel(const __nv_bfloat16* __restrict__ gu,
                                                             __nv_bfloat16* __restrict__ a, int64_t T, int I, int act) {
   const int chunks = I >> 3;
@@ -252,14 +246,15 @@ __global__ void __launch_bounds__(256) gated_act_fwd_kernel(const __nv_bfloat16*
     load8(gu + t * 2 * I + c, g);
     load8(gu + t * 2 * I + I + c, u);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) o[j] = round_bf16(act_eval(g[j], act)) * u[j];
+    for (int j = 0; j < 8; ++j) o[j] = act_eval(g[j], act) * u[j];
     store8(a + t * I + c, o);
   }
 }
 
-// g_half = g_a / 2                      (divide_gradient, rules.py:125-127)
-// g_up   = bf16(g_half * s)             s = bf16(act(gate))
-// g_gate = bf16( bf16(s / (gate + 1e-10)) * bf16(g_half * up) )      (identity rule, rules.py:88-100)
+// g_half = g_a / 2                           (divide_gradient, rules.py:125-127)
+// g_up   = g_half * s                        s = act(gate)
+// g_gate = (s / (gate + 1e-10)) * (g_half * up)                      (identity rule, rules.py:88-100)
+// fp32 arithmetic on the bf16 inputs, one rounding on each output.
 __global__ void __launch_bounds__(256) gated_act_bwd_kernel(const __nv_bfloat16* __restrict__ ga,
                                                             const __nv_bfloat16* __restrict__ gu,
                                                             __nv_bfloat16* __restrict__ ggu, int64_t T, int I, int act) {
@@ -275,11 +270,10 @@ __global__ void __launch_bounds__(256) gated_act_bwd_kernel(const __nv_bfloat16*
     load8(ga + t * I + c, d);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const float s = round_bf16(act_eval(g[j], act));
+      const float s = act_eval(g[j], act);
       const float gh = d[j] * 0.5f;
       ou[j] = gh * s;
-      const float ratio = round_bf16(s / round_bf16(g[j] + 1e-10f));
-      og[j] = ratio * round_bf16(gh * u[j]);
+      og[j] = (s / (g[j] + 1e-10f)) * (gh * u[j]);
     }
     store8(ggu + t * 2 * I + c, og);
     store8(ggu + t * 2 * I + I + c, ou);
@@ -306,12 +300,7 @@ __global__ void __launch_bounds__(256) act_identity_bwd_kernel(const T* __restri
     load8(gy + idx * 8, g);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      float s = act_eval(f[j], act);
-      float den = f[j] + 1e-10f;
-      if (sizeof(T) == 2) { s = round_bf16(s); den = round_bf16(den); }
-      float ratio = s / den;
-      if (sizeof(T) == 2) ratio = round_bf16(ratio);
-      o[j] = ratio * g[j];
+      o[j] = (act_eval(f[j], act) / (f[j] + 1e-10f)) * g[j];
     }
     store8(gx + idx * 8, o);
   }
@@ -330,7 +319,7 @@ __global__ void __launch_bounds__(256) embed_gather_kernel(const int64_t* __rest
     load8(emb + id * d + i, f);
     if (scale != 1.f) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) f[j] = round_bf16(f[j] * scale);  // HF scales the bf16 embedding in bf16
+      for (int j = 0; j < 8; ++j) f[j] = f[j] * scale;
     }
     store8(h + t * d + i, f);
   }
@@ -382,9 +371,7 @@ __global__ void __launch_bounds__(256) gxi_reduce_kernel(const T* __restrict__ x
     load8(g + row * d + i, b);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      float p = a[j] * b[j];
-      if (sizeof(T) == 2) p = round_bf16(p);  // (emb * emb.grad) is a bf16 tensor before .float().sum(-1)
-      s += p;
+      s += a[j] * b[j];
     }
   }
   s = warp_sum(s);

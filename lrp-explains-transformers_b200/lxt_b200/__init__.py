@@ -1,0 +1,24 @@
+"""lxt_b200 — B200-native AttnLRP hot path behind the `lxt` rule / patch API.
+
+Sub-modules
+  _capi     ctypes binding of liblrp_b200.so (C ABI in include/lrp_b200.h)
+  ops       torch-tensor wrappers over the C ABI (device memory + streams only)
+  engine    layer-by-layer AttnLRP executor for Llama-family decoders (headline path)
+  efficient drop-in mirror of `lxt.efficient` (monkey_patch, rules, patches, model maps)
+  explicit  drop-in mirror of `lxt.explicit.functional` / `lxt.explicit.rules`
+  dist      one-process-per-GPU batch sharding with a single NCCL gather
+"""
+__version__ = "0.1.0"
+
+from . import _capi  # noqa: F401
+
+
+def install_as_lxt() -> None:
+    """Register this package under the name `lxt` so that user scripts written against the reference
+    (`from lxt.efficient import monkey_patch`) run unchanged."""
+    import sys
+    from . import efficient, explicit
+
+    sys.modules.setdefault("lxt", sys.modules[__name__])
+    sys.modules.setdefault("lxt.efficient", efficient)
+    sys.modules.setdefault("lxt.explicit", explicit)

@@ -41,6 +41,7 @@ SIGNATURES = {
     "lrp_version": (_i, []),
     "lrp_last_error": (C.c_char_p, []),
     "lrp_check_device": (_i, []),
+    "lrp_launch_count": (_i64, []),
     "lrp_gemm_bf16": (_i, [_vp, _i64, _vp, _i64, _i, _i, _i, _i, _EP, _i, _vp]),
     "lrp_linear_fwd": (_i, [_vp, _i64, _vp, _i64, _i, _i, _i, _EP, _vp]),
     "lrp_linear_dgrad_fused": (_i, [_vp, _i64, _vp, _i64, _i, _i, _i, _EP, _vp]),

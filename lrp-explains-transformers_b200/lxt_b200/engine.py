@@ -1,0 +1,304 @@
+"""Layer-by-layer AttnLRP executor for Llama-family decoders (the headline hot path).
+
+One attribution = embed -> forward -> arg-max logit at the last position -> LRP backward in Gradient x Input
+space -> (emb * g_emb).sum(-1)   (reference workload: examples/quantized_llama.py:35-47 with
+lxt.efficient.monkey_patch(modeling_llama), lxt/efficient/models/llama.py:9-14).
+
+The engine does not use autograd: it launches the hand-written sm_100a kernels of liblrp_b200.so in the order the
+reference's autograd graph would execute its stock kernels, with the point-wise LRP rules fused into GEMM
+epilogues:
+
+  forward  per layer : rmsnorm -> [QKV GEMM] -> RoPE -> flash-attn fwd -> [O GEMM + residual]
+                       -> rmsnorm -> [gate|up GEMM] -> act*up -> [down GEMM + residual]
+  backward per layer : [down dgrad] -> (÷2, identity rule on SiLU, product rule) -> [gate|up dgrad + w*rstd +
+                       residual] -> [O dgrad] -> flash AttnLRP bwd (dQ/4,dK/4,dV/2) -> RoPE^T
+                       -> [QKV dgrad + w*rstd + residual]
+
+Data layout in HBM (T = micro_batch * S tokens, all row-major):
+  residual stream h, gradient stream g_h : fp32 [T, d]     (+ bf16 shadow of g_h = next GEMM's A operand)
+  activation store per layer (kept for the backward, nothing is recomputed when it fits — B200 has 180 GB):
+      qkv  bf16 [T, (H+2Hkv) D]  (post-RoPE q,k and v packed; attention reads strided views, no copies)
+      o    bf16 [T, H D]         lse fp32 [B, H, S]
+      gu   bf16 [T, 2 I]         (gate | up)
+      rstd1, rstd2 fp32 [T]
+  weights bf16 in nn.Linear layout [out, in]: wqkv = [wq; wk; wv], wgu = [wg; wu]; the backward consumes the
+  same storage through MN-major UMMA descriptors (no transposed copies).
+If the store for all layers does not fit, `store="sqrt"` keeps only the layer-boundary residual stream at
+segment starts (sqrt(L) segments) and recomputes the forward inside a segment before its backward.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+from typing import Dict, List, Optional
+
+import torch
+
+from . import ops
+
+
+@dataclass
+class LlamaDims:
+    d: int
+    I: int
+    H: int
+    Hkv: int
+    D: int
+    L: int
+    V: int
+    eps: float = 1e-5
+    theta: float = 10000.0
+
+    @property
+    def qkv_width(self) -> int:
+        return (self.H + 2 * self.Hkv) * self.D
+
+
+LLAMA3_8B = LlamaDims(d=4096, I=14336, H=32, Hkv=8, D=128, L=32, V=128256, eps=1e-5, theta=500000.0)
+TINYLLAMA_1B = LlamaDims(d=2048, I=5632, H=32, Hkv=4, D=64, L=22, V=32000, eps=1e-5, theta=10000.0)
+
+
+class _LayerStore:
+    __slots__ = ("qkv", "o", "lse", "gu", "rstd1", "rstd2")
+
+
+class LlamaAttnLRPEngine:
+    """B200-native AttnLRP engine.  Construct with `from_weights`, `from_hf` or `random_init`."""
+
+    def __init__(self, dims: LlamaDims, device: torch.device, weights: Dict, micro_batch: int = 8, store: str = "all"):
+        if device.type != "cuda":
+            raise RuntimeError("LlamaAttnLRPEngine runs on a CUDA (B200) device only; there is no CPU path")
+        ops._capi.require_device()
+        self.dims, self.device, self.micro_batch, self.store_policy = dims, device, micro_batch, store
+        bf = lambda t: t.to(device=device, dtype=torch.bfloat16).contiguous()
+        f32 = lambda t: t.to(device=device, dtype=torch.float32).contiguous()
+        self.emb = bf(weights["emb"])
+        self.lm_head = bf(weights["lm_head"])
+        self.norm_w = bf(weights["norm"])
+        self.layers: List[Dict[str, torch.Tensor]] = []
+        for lw in weights["layers"]:
+            wqkv = torch.cat([lw["wq"], lw["wk"], lw["wv"]], dim=0)
+            wgu = torch.cat([lw["wg"], lw["wu"]], dim=0)
+            self.layers.append(dict(wqkv=bf(wqkv), wo=bf(lw["wo"]), wgu=bf(wgu), wd=bf(lw["wd"]), ln1=bf(lw["ln1"]),
+                                    ln2=bf(lw["ln2"]), ln1_f=f32(bf(lw["ln1"])), ln2_f=f32(bf(lw["ln2"]))))
+        self._ws_key = None
+        self._ws = None
+        self._rope_key = None
+
+    # ------------------------------------------------------------------ constructors
+    @classmethod
+    def from_weights(cls, dims: LlamaDims, weights: Dict, device="cuda", **kw):
+        return cls(dims, torch.device(device), weights, **kw)
+
+    @classmethod
+    def from_hf(cls, model, device="cuda", **kw):
+        """Build from a HuggingFace LlamaForCausalLM (weights are copied to bf16 on the device)."""
+        c = model.config
+        D = getattr(c, "head_dim", None) or c.hidden_size // c.num_attention_heads
+        theta = (getattr(c, "rope_parameters", None) or {}).get("rope_theta", getattr(c, "rope_theta", 10000.0))
+        dims = LlamaDims(d=c.hidden_size, I=c.intermediate_size, H=c.num_attention_heads, Hkv=c.num_key_value_heads, D=D,
+                         L=c.num_hidden_layers, V=c.vocab_size, eps=c.rms_norm_eps, theta=theta)
+        sd = model.state_dict()
+        w = dict(emb=sd["model.embed_tokens.weight"], norm=sd["model.norm.weight"],
+                 lm_head=sd.get("lm_head.weight", sd["model.embed_tokens.weight"]), layers=[])
+        for i in range(dims.L):
+            p = f"model.layers.{i}."
+            w["layers"].append(dict(wq=sd[p + "self_attn.q_proj.weight"], wk=sd[p + "self_attn.k_proj.weight"],
+                                    wv=sd[p + "self_attn.v_proj.weight"], wo=sd[p + "self_attn.o_proj.weight"],
+                                    wg=sd[p + "mlp.gate_proj.weight"], wu=sd[p + "mlp.up_proj.weight"],
+                                    wd=sd[p + "mlp.down_proj.weight"], ln1=sd[p + "input_layernorm.weight"],
+                                    ln2=sd[p + "post_attention_layernorm.weight"]))
+        return cls(dims, torch.device(device), w, **kw)
+
+    @classmethod
+    def random_init(cls, dims: LlamaDims, device="cuda", seed: int = 0, std: float = 0.02, **kw):
+        """HF-style random init generated directly on the device (synthetic benchmark weights)."""
+        dev = torch.device(device)
+        g = torch.Generator(device=dev).manual_seed(seed)
+        rn = lambda *s: (torch.randn(*s, generator=g, device=dev, dtype=torch.float32) * std).to(torch.bfloat16)
+        ones = lambda n: torch.ones(n, device=dev, dtype=torch.bfloat16)
+        layers = []
+        for _ in range(dims.L):
+            layers.append(dict(wq=rn(dims.H * dims.D, dims.d), wk=rn(dims.Hkv * dims.D, dims.d), wv=rn(dims.Hkv * dims.D, dims.d),
+                               wo=rn(dims.d, dims.H * dims.D), wg=rn(dims.I, dims.d), wu=rn(dims.I, dims.d),
+                               wd=rn(dims.d, dims.I), ln1=ones(dims.d), ln2=ones(dims.d)))
+        w = dict(emb=rn(dims.V, dims.d), norm=ones(dims.d), lm_head=rn(dims.V, dims.d), layers=layers)
+        return cls(dims, dev, w, **kw)
+
+    # ------------------------------------------------------------------ workspace
+    def store_bytes_per_token_layer(self) -> int:
+        m = self.dims
+        return 2 * (m.qkv_width + m.H * m.D + 2 * m.I) + 4 * m.H + 8
+
+    def _workspace(self, B: int, S: int):
+        key = (B, S)
+        if self._ws_key == key:
+            return self._ws
+        self._ws = None  # release the previous workspace before allocating the new one
+        m, dev = self.dims, self.device
+        T = B * S
+        e = lambda *s, dt=torch.bfloat16: torch.empty(*s, dtype=dt, device=dev)
+        ws = {}
+        n_store = m.L if self.store_policy == "all" else self._segment_len()
+        stores = []
+        for _ in range(n_store):
+            st = _LayerStore()
+            st.qkv, st.o, st.gu = e(T, m.qkv_width), e(T, m.H * m.D), e(T, 2 * m.I)
+            st.lse = e(B, m.H, S, dt=torch.float32)
+            st.rstd1, st.rstd2 = e(T, dt=torch.float32), e(T, dt=torch.float32)
+            stores.append(st)
+        ws["stores"] = stores
+        if self.store_policy != "all":
+            ws["h_ckpt"] = [e(T, m.d, dt=torch.float32) for _ in range(math.ceil(m.L / self._segment_len()))]
+        ws["h"] = e(T, m.d, dt=torch.float32)
+        ws["g_h"] = e(T, m.d, dt=torch.float32)
+        ws["g_hb"] = e(T, m.d)
+        ws["xn"] = e(T, m.d)
+        ws["a"] = e(T, m.I)          # act(gate)*up in forward, g_a in backward
+        ws["g_gu"] = e(T, 2 * m.I)
+        ws["g_o"] = e(T, m.H * m.D)
+        ws["g_qkv"] = e(T, m.qkv_width)
+        ws["dq_acc"] = e(B, S, m.H, m.D, dt=torch.float32)
+        ws["delta"] = e(B, m.H, S, dt=torch.float32)
+        ws["logits"] = e(B, m.V, dt=torch.float32)
+        ws["last_rows"] = (torch.arange(B, device=dev, dtype=torch.int64) + 1) * S - 1
+        self._ws_key, self._ws = key, ws
+        return ws
+
+    def _segment_len(self) -> int:
+        return max(1, int(math.ceil(math.sqrt(self.dims.L))))
+
+    def _rope(self, S: int):
+        if self._rope_key != S:
+            m = self.dims
+            inv_freq = 1.0 / (m.theta ** (torch.arange(0, m.D, 2, dtype=torch.int64).float() / m.D))
+            fr = torch.outer(torch.arange(S, dtype=torch.float32), inv_freq)
+            self._cos, self._sin = fr.cos().to(self.device).contiguous(), fr.sin().to(self.device).contiguous()
+            self._rope_key = S
+        return self._cos, self._sin
+
+    # ------------------------------------------------------------------ one layer
+    def _layer_fwd(self, lw, st: _LayerStore, h, ws, B, S):
+        m = self.dims
+        T = B * S
+        cos, sin = self._rope(S)
+        scale = 1.0 / math.sqrt(m.D)
+        lib, C = ops._capi.lib(), ops._capi
+        C.check(lib.lrp_rmsnorm_fwd(h.data_ptr(), 1, lw["ln1"].data_ptr(), 0.0, m.eps, ws["xn"].data_ptr(), st.rstd1.data_ptr(),
+                                    T, m.d, ops._stream()), "rmsnorm_fwd")
+        ops.linear_fwd(ws["xn"], lw["wqkv"], st.qkv)
+        ops.rope_inplace(st.qkv, m.H + m.Hkv, m.D, cos, sin, S)
+        q, k, v = self._qkv_views(st.qkv, B, S)
+        C.check(lib.lrp_attn_fwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), m.qkv_width, m.qkv_width, m.qkv_width,
+                                 st.o.data_ptr(), st.lse.data_ptr(), B, S, m.H, m.Hkv, m.D, scale, 1, 0, ops._stream()), "attn_fwd")
+        ops.linear_fwd(st.o, lw["wo"], h, resid=h)
+        C.check(lib.lrp_rmsnorm_fwd(h.data_ptr(), 1, lw["ln2"].data_ptr(), 0.0, m.eps, ws["xn"].data_ptr(), st.rstd2.data_ptr(),
+                                    T, m.d, ops._stream()), "rmsnorm_fwd")
+        ops.linear_fwd(ws["xn"], lw["wgu"], st.gu)
+        C.check(lib.lrp_gated_act_fwd(st.gu.data_ptr(), ws["a"].data_ptr(), T, m.I, ops.ACT_SILU, ops._stream()), "gated_act_fwd")
+        ops.linear_fwd(ws["a"], lw["wd"], h, resid=h)
+
+    def _layer_bwd(self, lw, st: _LayerStore, ws, B, S):
+        m = self.dims
+        T = B * S
+        cos, sin = self._rope(S)
+        scale = 1.0 / math.sqrt(m.D)
+        lib, C = ops._capi.lib(), ops._capi
+        g_h, g_hb = ws["g_h"], ws["g_hb"]
+        # ---- gated MLP
+        ops.linear_dgrad(g_hb, lw["wd"], ws["a"])                                  # g_a [T, I]
+        C.check(lib.lrp_gated_act_bwd(ws["a"].data_ptr(), st.gu.data_ptr(), ws["g_gu"].data_ptr(), T, m.I, ops.ACT_SILU,
+                                      ops._stream()), "gated_act_bwd")
+        ops.linear_dgrad(ws["g_gu"], lw["wgu"], g_h, resid=g_h, rowscale=st.rstd2, colscale=lw["ln2_f"], shadow=g_hb)
+        # ---- attention
+        ops.linear_dgrad(g_hb, lw["wo"], ws["g_o"])                                # g_o [T, H D]
+        q, k, v = self._qkv_views(st.qkv, B, S)
+        dq, dk, dv = self._qkv_views(ws["g_qkv"], B, S)
+        C.check(lib.lrp_attn_bwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), m.qkv_width, m.qkv_width, m.qkv_width,
+                                 st.o.data_ptr(), ws["g_o"].data_ptr(), st.lse.data_ptr(), dq.data_ptr(), dk.data_ptr(),
+                                 dv.data_ptr(), m.qkv_width, m.qkv_width, m.qkv_width, ws["dq_acc"].data_ptr(),
+                                 ws["delta"].data_ptr(), B, S, m.H, m.Hkv, m.D, scale, 1, 0, 4.0, 4.0, 2.0, ops._stream()),
+                "attn_bwd")
+        ops.rope_inplace(ws["g_qkv"], m.H + m.Hkv, m.D, cos, sin, S, inverse=True)
+        ops.linear_dgrad(ws["g_qkv"], lw["wqkv"], g_h, resid=g_h, rowscale=st.rstd1, colscale=lw["ln1_f"], shadow=g_hb)
+
+    def _qkv_views(self, buf, B, S):
+        m = self.dims
+        x = buf.view(B, S, m.qkv_width)
+        q = x[:, :, : m.H * m.D]
+        k = x[:, :, m.H * m.D: (m.H + m.Hkv) * m.D]
+        v = x[:, :, (m.H + m.Hkv) * m.D:]
+        return q, k, v
+
+    # ------------------------------------------------------------------ one micro-batch, device resident
+    @torch.no_grad()
+    def attribute_device(self, ids: torch.Tensor, return_aux: bool = False):
+        """ids int64 [B,S] on the device -> relevance fp32 [B,S] on the device."""
+        m = self.dims
+        B, S = ids.shape
+        T = B * S
+        ws = self._workspace(B, S)
+        lib, C = ops._capi.lib(), ops._capi
+        h, g_h, g_hb = ws["h"], ws["g_h"], ws["g_hb"]
+        flat = ids.reshape(-1).contiguous()
+        C.check(lib.lrp_embed_gather(flat.data_ptr(), self.emb.data_ptr(), 1.0, h.data_ptr(), T, m.d, ops._stream()), "embed")
+
+        seg = self._segment_len()
+        if self.store_policy == "all":
+            for l, lw in enumerate(self.layers):
+                self._layer_fwd(lw, ws["stores"][l], h, ws, B, S)
+        else:
+            for l, lw in enumerate(self.layers):
+                if l % seg == 0:
+                    ws["h_ckpt"][l // seg].copy_(h)
+                self._layer_fwd(lw, ws["stores"][l % seg], h, ws, B, S)
+
+        # ---- head: only the last position is read (examples/quantized_llama.py:40)
+        h_last = h.index_select(0, ws["last_rows"])
+        xn_last, rstd_last = ops.rmsnorm_fwd(h_last, self.norm_w, m.eps)
+        ops.linear_fwd(xn_last, self.lm_head, ws["logits"])
+        idx, _ = ops.argmax_rows(ws["logits"])
+        # seed: d(max logit)/d(xn_last) = lm_head[idx]; through the final norm with the identity rule
+        g_xn_last = self.lm_head.index_select(0, idx.long())
+        g_last = ops.rmsnorm_bwd(g_xn_last, self.norm_w, rstd_last, out_dtype=torch.float32)
+        g_h.zero_()
+        g_h.index_copy_(0, ws["last_rows"], g_last)
+        ops.cast_bf16(g_h, g_hb)
+
+        if self.store_policy == "all":
+            for l in range(m.L - 1, -1, -1):
+                self._layer_bwd(self.layers[l], ws["stores"][l], ws, B, S)
+        else:
+            nseg = math.ceil(m.L / seg)
+            for sgi in range(nseg - 1, -1, -1):
+                lo, hi = sgi * seg, min(m.L, (sgi + 1) * seg)
+                if sgi != nseg - 1 or True:
+                    # recompute the segment's forward from its checkpoint (the last segment is still resident
+                    # only if L % seg == 0 and nothing overwrote it; recomputing keeps the logic uniform)
+                    h.copy_(ws["h_ckpt"][sgi])
+                    for l in range(lo, hi):
+                        self._layer_fwd(self.layers[l], ws["stores"][l % seg], h, ws, B, S)
+                for l in range(hi - 1, lo - 1, -1):
+                    self._layer_bwd(self.layers[l], ws["stores"][l % seg], ws, B, S)
+
+        # ---- Gradient x Input at the embedding
+        C.check(lib.lrp_embed_gather(flat.data_ptr(), self.emb.data_ptr(), 1.0, h.data_ptr(), T, m.d, ops._stream()), "embed")
+        rel = ops.gxi_reduce(h, g_h).view(B, S)
+        if return_aux:
+            return rel, {"idx": idx, "logits": ws["logits"], "g_emb": g_h.view(B, S, m.d)}
+        return rel
+
+    # ------------------------------------------------------------------ public API: host in, host out
+    @torch.no_grad()
+    def attribute(self, input_ids: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """input_ids: int64 [N,S] on the HOST (pinned memory recommended) or the device.
+        Returns token relevance fp32 [N,S] on the host.  Prompts are processed `micro_batch` at a time."""
+        N, S = input_ids.shape
+        if out is None:
+            out = torch.empty((N, S), dtype=torch.float32, pin_memory=True)
+        for i in range(0, N, self.micro_batch):
+            ids = input_ids[i:i + self.micro_batch].to(self.device, non_blocking=True)
+            rel = self.attribute_device(ids)
+            out[i:i + self.micro_batch].copy_(rel, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return out

@@ -15,6 +15,15 @@ from ._capi import Epilogue, check
 
 ACT_SILU, ACT_GELU_TANH, ACT_GELU_ERF = 0, 1, 2
 
+# Optional per-launch timing of the dominant kernel (bench.py's roofline): when set to a list, every GEMM launch
+# appends (flops, start_event, end_event) recorded on the launching stream.
+GEMM_PROFILE = None
+
+
+def launch_count() -> int:
+    """kernels enqueued by liblrp_b200.so in this process so far"""
+    return int(_capi.lib().lrp_launch_count())
+
 
 def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
@@ -76,8 +85,15 @@ def gemm(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor, *, b_layout: int, 
     if tuple(out.shape) != (M, N):
         raise _capi.LrpError(f"gemm: output shape {tuple(out.shape)} != {(M, N)}")
     e = make_epilogue(out, **epi)
+    prof = GEMM_PROFILE
+    if prof is not None:
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
     check(_capi.lib().lrp_gemm_bf16(a.data_ptr(), lda, b.data_ptr(), ldb, b_layout, M, N, K, C.byref(e), tile_n, _stream()),
           "lrp_gemm_bf16")
+    if prof is not None:
+        ev1.record()
+        prof.append((2.0 * M * N * K, ev0, ev1))
     return out
 
 

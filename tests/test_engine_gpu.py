@@ -1,0 +1,55 @@
+"""GPU parity of the engine (all CUDA kernels through the C ABI) against the golden vectors of the real
+reference and against the CPU oracle on the same seeded inputs."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import load_llama_golden, rel_l2
+
+pytestmark = pytest.mark.gpu
+
+
+def _engine(cfg, w, **kw):
+    from lxt_b200.engine import LlamaAttnLRPEngine, LlamaDims
+    dims = LlamaDims(d=cfg["d"], I=cfg["I"], H=cfg["H"], Hkv=cfg["Hkv"], D=cfg["D"], L=cfg["L"], V=cfg["V"], eps=cfg["eps"],
+                     theta=cfg["theta"])
+    return LlamaAttnLRPEngine.from_weights(dims, w, device="cuda", **kw)
+
+
+@pytest.mark.parametrize("name", ["llama_tiny_d64.npz", "llama_tiny_d128.npz"])
+@pytest.mark.parametrize("store", ["all", "sqrt"])
+def test_engine_matches_reference_golden(name, store):
+    cfg, w, ids, z = load_llama_golden(name)
+    eng = _engine(cfg, w, micro_batch=4, store=store)
+    rel, aux = eng.attribute_device(ids.cuda(), return_aux=True)
+    rel = rel.float().cpu()
+    assert np.array_equal(aux["idx"].cpu().numpy(), z["idx_fp32_sdpa"])
+    ref_gap = rel_l2(z["rel_bf16_sdpa"], z["rel_fp32_sdpa"])  # the reference's own bf16-vs-fp32 distance
+    err = rel_l2(rel, z["rel_fp32_sdpa"])
+    print(f"{name} store={store}: rel-L2 vs reference fp32 = {err:.3e} (reference bf16 vs fp32 = {ref_gap:.3e})")
+    # bf16 activation storage: a bf16 pipeline cannot reach 1e-3 against an fp32 run (one bf16 rounding alone
+    # is ~1.6e-3 rel-L2); the bar is "the same distance from the fp32 reference as the reference's own bf16
+    # run" (2.0e-3..2.4e-3 on these fixtures), stated as an absolute 4e-3.  Kernel-level tests hold 1e-3.
+    assert err < 4e-3
+    cos = torch.nn.functional.cosine_similarity(rel.flatten().double(), torch.from_numpy(z["rel_fp32_sdpa"]).flatten().double(), dim=0)
+    assert cos > 0.9999
+
+
+def test_engine_public_api_host_roundtrip():
+    cfg, w, ids, z = load_llama_golden("llama_tiny_d64.npz")
+    eng = _engine(cfg, w, micro_batch=1)
+    out = eng.attribute(ids.pin_memory())
+    assert out.shape == ids.shape and out.dtype == torch.float32 and not out.is_cuda
+    assert rel_l2(out, z["rel_fp32_sdpa"]) < 5e-3
+
+
+def test_engine_matches_oracle_on_fresh_seed():
+    from oracle import attnlrp_oracle as O
+    cfg = dict(d=512, I=1024, H=8, Hkv=2, D=64, L=3, V=1000, eps=1e-5, theta=10000.0)
+    w = O.random_llama_weights(cfg, seed=11)
+    ids = torch.randint(0, cfg["V"], (3, 200), generator=torch.Generator().manual_seed(5))
+    ref, aux = O.llama_attnlrp(w, ids, cfg, dtype=torch.float32, return_aux=True)
+    eng = _engine(cfg, w, micro_batch=3)
+    rel, a2 = eng.attribute_device(ids.cuda(), return_aux=True)
+    assert torch.equal(a2["idx"].cpu().long(), aux["idx"])
+    assert rel_l2(rel.cpu(), ref) < 5e-3
