@@ -160,6 +160,26 @@ int lrp_gxi_reduce_bf16(const void* x, const void* g, float* rel, int T, int d, 
 /* out_bf16 = bf16(in_f32), n elements */
 int lrp_cast_f32_to_bf16(const float* in, void* out, int64_t n, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Element-wise rule kernels on arbitrary tensors (the `lxt.explicit.functional` / `lxt.efficient.rules` API).
+ * All tensors of one call share a dtype: is_f32 = 1 fp32, 0 bf16; n elements, contiguous.
+ * ---------------------------------------------------------------------------------------------- */
+/* out = r / (alpha*z + eps): the `relevance_norm` step of every epsilon rule (lxt/explicit/functional.py:359,399;
+ * lxt/explicit/rules.py:215,271); `_stabilize` is a plain `+ eps` (functional.py:266-273). */
+int lrp_eps_div(const void* r, const void* z, void* out, int64_t n, float alpha, float eps, int is_f32, void* stream);
+/* out = a*b*scale: the `.mul_(inputs)` step of the epsilon rules (functional.py:361, rules.py:220). */
+int lrp_mul(const void* a, const void* b, void* out, int64_t n, float scale, int is_f32, void* stream);
+/* out = x*factor: divide_gradient backward (lxt/efficient/rules.py:125-127), mul2 uniform rule (functional.py:524-536). */
+int lrp_scale(const void* x, void* out, int64_t n, float factor, int is_f32, void* stream);
+/* gx = gy * y/(x+1e-10): identity rule in GxI space for an arbitrary y = f(x) (lxt/efficient/rules.py:88-100). */
+int lrp_identity_rule_bwd(const void* gy, const void* x, const void* y, void* gx, int64_t n, int is_f32, void* stream);
+/* Deep-Taylor softmax rule over the last dim (functional.py:308-322): out = x~*(r - p*sum(r)), -inf -> 0. */
+int lrp_softmax_dt_bwd(const void* x, const void* p, const void* r, void* out, int64_t rows, int cols, int is_f32,
+                       void* stream);
+/* epsilon rule of a+b (functional.py:439-459): ra = a*r/(a+b+eps), rb = b*r/(a+b+eps). */
+int lrp_add2_bwd(const void* a, const void* b, const void* r, void* ra, void* rb, int64_t n, float eps, int is_f32,
+                 void* stream);
+
 #ifdef __cplusplus
 }
 #endif

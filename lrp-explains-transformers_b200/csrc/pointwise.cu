@@ -387,6 +387,70 @@ __global__ void __launch_bounds__(256) cast_f32_bf16_kernel(const float* __restr
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// generic element-wise rule kernels (explicit / efficient rule API on arbitrary tensors); scalar tail handled
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float ldf(const float* p, int64_t i) { return p[i]; }
+__device__ __forceinline__ float ldf(const __nv_bfloat16* p, int64_t i) { return __bfloat162float(p[i]); }
+__device__ __forceinline__ void stf(float* p, int64_t i, float v) { p[i] = v; }
+__device__ __forceinline__ void stf(__nv_bfloat16* p, int64_t i, float v) { p[i] = __float2bfloat16_rn(v); }
+
+// out = r / (alpha * z + eps)      (_stabilize: plain "+ eps", lxt/explicit/functional.py:266-273)
+template <typename T>
+__global__ void __launch_bounds__(256) eps_div_kernel(const T* __restrict__ r, const T* __restrict__ z, T* __restrict__ out,
+                                                      int64_t n, float alpha, float eps) {
+  for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < n; i += int64_t(gridDim.x) * blockDim.x)
+    stf(out, i, ldf(r, i) / (alpha * ldf(z, i) + eps));
+}
+// out = a * b * scale
+template <typename T>
+__global__ void __launch_bounds__(256) mul_kernel(const T* __restrict__ a, const T* __restrict__ b, T* __restrict__ out,
+                                                  int64_t n, float scale) {
+  for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < n; i += int64_t(gridDim.x) * blockDim.x)
+    stf(out, i, ldf(a, i) * ldf(b, i) * scale);
+}
+// out = x * factor
+template <typename T>
+__global__ void __launch_bounds__(256) scale_kernel(const T* __restrict__ x, T* __restrict__ out, int64_t n, float factor) {
+  for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < n; i += int64_t(gridDim.x) * blockDim.x)
+    stf(out, i, ldf(x, i) * factor);
+}
+// gx = gy * (y / (x + 1e-10))     identity rule in GxI space for an arbitrary f with y = f(x)  (rules.py:88-100)
+template <typename T>
+__global__ void __launch_bounds__(256) identity_rule_bwd_kernel(const T* __restrict__ gy, const T* __restrict__ x,
+                                                                const T* __restrict__ y, T* __restrict__ gx, int64_t n) {
+  for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < n; i += int64_t(gridDim.x) * blockDim.x)
+    stf(gx, i, ldf(gy, i) * (ldf(y, i) / (ldf(x, i) + 1e-10f)));
+}
+// Deep-Taylor softmax rule (functional.py:308-322): out = x~ * (r - p * sum_row(r)), x~ = x with -inf -> 0; one warp per row
+template <typename T>
+__global__ void __launch_bounds__(256) softmax_dt_bwd_kernel(const T* __restrict__ x, const T* __restrict__ p,
+                                                             const T* __restrict__ r, T* __restrict__ out, int64_t rows, int cols) {
+  const int64_t row = blockIdx.x * int64_t(blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31;
+  float s = 0.f;
+  for (int c = lane; c < cols; c += 32) s += ldf(r, row * cols + c);
+  s = warp_sum(s);
+  for (int c = lane; c < cols; c += 32) {
+    const int64_t i = row * cols + c;
+    float xv = ldf(x, i);
+    if (xv == -INFINITY) xv = 0.f;
+    stf(out, i, xv * (ldf(r, i) - ldf(p, i) * s));
+  }
+}
+// epsilon rule for a + b (functional.py:439-459): s = r / (a + b + eps); ra = s*a; rb = s*b
+template <typename T>
+__global__ void __launch_bounds__(256) add2_bwd_kernel(const T* __restrict__ a, const T* __restrict__ b, const T* __restrict__ r,
+                                                       T* __restrict__ ra, T* __restrict__ rb, int64_t n, float eps) {
+  for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < n; i += int64_t(gridDim.x) * blockDim.x) {
+    const float av = ldf(a, i), bv = ldf(b, i);
+    const float sv = ldf(r, i) / (av + bv + eps);
+    stf(ra, i, sv * av);
+    stf(rb, i, sv * bv);
+  }
+}
+
 static inline int grid_for(int64_t work_items, int threads) {
   int64_t g = (work_items + threads - 1) / threads;
   const int64_t cap = int64_t(sm_count()) * 16;
@@ -535,6 +599,55 @@ int lrp_cast_f32_to_bf16(const float* in, void* out, int64_t n, void* stream) {
   cast_f32_bf16_kernel<<<grid_for(n / 8, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(in, (bf16*)out, n / 8);
   LRP_CHECK_LAUNCH();
   return LRP_OK;
+}
+
+}  // extern "C"
+
+template <typename F32, typename BF>
+static int ew_launch(int64_t n, int is_f32, void* stream, const char* what, F32 f32, BF bf) {
+  if (n <= 0) return set_error(LRP_ERR_ARG, what);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int g = grid_for(n, 256);
+  if (is_f32) f32(g, st); else bf(g, st);
+  LRP_CHECK_LAUNCH();
+  return LRP_OK;
+}
+
+extern "C" {
+
+int lrp_eps_div(const void* r, const void* z, void* out, int64_t n, float alpha, float eps, int is_f32, void* stream) {
+  return ew_launch(n, is_f32, stream, "eps_div: empty tensor",
+                   [&](int g, cudaStream_t st) { eps_div_kernel<float><<<g, 256, 0, st>>>((const float*)r, (const float*)z, (float*)out, n, alpha, eps); },
+                   [&](int g, cudaStream_t st) { eps_div_kernel<bf16><<<g, 256, 0, st>>>((const bf16*)r, (const bf16*)z, (bf16*)out, n, alpha, eps); });
+}
+int lrp_mul(const void* a, const void* b, void* out, int64_t n, float scale, int is_f32, void* stream) {
+  return ew_launch(n, is_f32, stream, "mul: empty tensor",
+                   [&](int g, cudaStream_t st) { mul_kernel<float><<<g, 256, 0, st>>>((const float*)a, (const float*)b, (float*)out, n, scale); },
+                   [&](int g, cudaStream_t st) { mul_kernel<bf16><<<g, 256, 0, st>>>((const bf16*)a, (const bf16*)b, (bf16*)out, n, scale); });
+}
+int lrp_scale(const void* x, void* out, int64_t n, float factor, int is_f32, void* stream) {
+  return ew_launch(n, is_f32, stream, "scale: empty tensor",
+                   [&](int g, cudaStream_t st) { scale_kernel<float><<<g, 256, 0, st>>>((const float*)x, (float*)out, n, factor); },
+                   [&](int g, cudaStream_t st) { scale_kernel<bf16><<<g, 256, 0, st>>>((const bf16*)x, (bf16*)out, n, factor); });
+}
+int lrp_identity_rule_bwd(const void* gy, const void* x, const void* y, void* gx, int64_t n, int is_f32, void* stream) {
+  return ew_launch(n, is_f32, stream, "identity_rule_bwd: empty tensor",
+                   [&](int g, cudaStream_t st) { identity_rule_bwd_kernel<float><<<g, 256, 0, st>>>((const float*)gy, (const float*)x, (const float*)y, (float*)gx, n); },
+                   [&](int g, cudaStream_t st) { identity_rule_bwd_kernel<bf16><<<g, 256, 0, st>>>((const bf16*)gy, (const bf16*)x, (const bf16*)y, (bf16*)gx, n); });
+}
+int lrp_softmax_dt_bwd(const void* x, const void* p, const void* r, void* out, int64_t rows, int cols, int is_f32, void* stream) {
+  if (rows <= 0 || cols <= 0) return set_error(LRP_ERR_ARG, "softmax_dt_bwd: empty tensor");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const unsigned g = unsigned((rows + 7) / 8);
+  if (is_f32) softmax_dt_bwd_kernel<float><<<g, 256, 0, st>>>((const float*)x, (const float*)p, (const float*)r, (float*)out, rows, cols);
+  else softmax_dt_bwd_kernel<bf16><<<g, 256, 0, st>>>((const bf16*)x, (const bf16*)p, (const bf16*)r, (bf16*)out, rows, cols);
+  LRP_CHECK_LAUNCH();
+  return LRP_OK;
+}
+int lrp_add2_bwd(const void* a, const void* b, const void* r, void* ra, void* rb, int64_t n, float eps, int is_f32, void* stream) {
+  return ew_launch(n, is_f32, stream, "add2_bwd: empty tensor",
+                   [&](int g, cudaStream_t st) { add2_bwd_kernel<float><<<g, 256, 0, st>>>((const float*)a, (const float*)b, (const float*)r, (float*)ra, (float*)rb, n, eps); },
+                   [&](int g, cudaStream_t st) { add2_bwd_kernel<bf16><<<g, 256, 0, st>>>((const bf16*)a, (const bf16*)b, (const bf16*)r, (bf16*)ra, (bf16*)rb, n, eps); });
 }
 
 }  // extern "C"

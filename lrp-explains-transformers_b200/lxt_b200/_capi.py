@@ -67,6 +67,12 @@ SIGNATURES = {
     "lrp_gxi_reduce": (_i, [_vp, _vp, _vp, _i, _i, _vp]),
     "lrp_gxi_reduce_bf16": (_i, [_vp, _vp, _vp, _i, _i, _vp]),
     "lrp_cast_f32_to_bf16": (_i, [_vp, _vp, _i64, _vp]),
+    "lrp_eps_div": (_i, [_vp, _vp, _vp, _i64, _f, _f, _i, _vp]),
+    "lrp_mul": (_i, [_vp, _vp, _vp, _i64, _f, _i, _vp]),
+    "lrp_scale": (_i, [_vp, _vp, _i64, _f, _i, _vp]),
+    "lrp_identity_rule_bwd": (_i, [_vp, _vp, _vp, _vp, _i64, _i, _vp]),
+    "lrp_softmax_dt_bwd": (_i, [_vp, _vp, _vp, _vp, _i64, _i, _i, _vp]),
+    "lrp_add2_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _i64, _f, _i, _vp]),
 }
 
 _lib = None

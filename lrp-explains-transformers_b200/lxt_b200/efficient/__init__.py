@@ -1,1 +1,3 @@
-"""mirror of lxt.efficient (filled in below)"""
+"""Drop-in for `lxt.efficient`: `from lxt_b200.efficient import monkey_patch`."""
+from .core import monkey_patch  # noqa: F401
+from . import rules, patches, models  # noqa: F401

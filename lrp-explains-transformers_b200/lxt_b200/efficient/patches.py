@@ -1,0 +1,381 @@
+"""Forward replacements and patch plumbing — drop-in for `lxt.efficient.patches`
+(reference: lxt/efficient/patches.py:22-280).  Same names, same signatures, same return conventions; the
+arithmetic runs in the sm_100a kernels of liblrp_b200.so through `torch.autograd.Function`s, so a patched
+HuggingFace model keeps running unchanged Python (`loss.backward()`, `x * x.grad`).
+
+Tensors must be CUDA bf16 (fp32 where noted): there is no CPU or eager fallback — unsupported inputs raise.
+"""
+from __future__ import annotations
+
+import math
+from warnings import warn
+
+import torch
+from torch.autograd import Function
+
+from .. import ops
+from .._capi import LrpError
+from .rules import _act_code, divide_gradient, identity_rule_implicit, stop_gradient  # noqa: F401
+
+# ---------------------------------------------------------------------------------------------------------
+# patch plumbing (host logic; reference lxt/efficient/patches.py:22-104)
+# ---------------------------------------------------------------------------------------------------------
+
+
+def check_already_patched(target_fn, new_fn):
+    """True (with a warning) when `target_fn` already lives in the module `new_fn` comes from — the reference's
+    re-patch guard is a `__module__` string comparison (patches.py:40), kept bug-compatible."""
+    if getattr(target_fn, "__module__", None) != getattr(new_fn, "__module__", object()):
+        return False
+    warn(f"{getattr(target_fn, '__name__', target_fn)} already patched.")
+    return True
+
+
+def patch_method(fn, module, method_name="forward", keep_original=False):
+    """Replace `module.<method_name>` by `fn` (class-level, process-global).  Returns True when patched."""
+    current = getattr(module, method_name)
+    if check_already_patched(current, fn):
+        return False
+    if keep_original:
+        setattr(module, f"original_{method_name}", current)
+    setattr(module, method_name, fn)
+    return True
+
+
+def replace_module(patched_module, original_module):
+    """Copy every public attribute of `patched_module` onto `original_module`."""
+    if original_module == patched_module:
+        return False
+    for name in dir(patched_module):
+        if name.startswith("__"):
+            continue
+        setattr(original_module, name, getattr(patched_module, name))
+    return True
+
+
+# ---------------------------------------------------------------------------------------------------------
+# autograd bridges over the C-ABI kernels
+# ---------------------------------------------------------------------------------------------------------
+
+
+def _as_2d(x: torch.Tensor) -> torch.Tensor:
+    x2 = x.reshape(-1, x.shape[-1])
+    return x2 if x2.is_contiguous() else x2.contiguous()
+
+
+def _need_bf16_cuda(x: torch.Tensor, what: str) -> None:
+    if not (x.is_cuda and x.dtype == torch.bfloat16):
+        raise LrpError(f"{what}: the B200 path takes CUDA bfloat16 tensors (got {x.device}, {x.dtype}); no fallback exists")
+
+
+class _RMSNormIdentityFn(Function):
+    """y = (x * rsqrt(mean(x^2)+eps)) * (w + w_offset); backward with the variance detached (identity rule)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, eps, w_offset):
+        _need_bf16_cuda(x, "rms_norm_forward")
+        x2 = _as_2d(x)
+        w = weight.detach().to(torch.bfloat16).contiguous()
+        y, rstd = ops.rmsnorm_fwd(x2, w, eps, w_offset=w_offset)
+        ctx.save_for_backward(w, rstd)
+        ctx.w_offset = w_offset
+        return y.view(x.shape)
+
+    @staticmethod
+    def backward(ctx, gy):
+        w, rstd = ctx.saved_tensors
+        gx = ops.rmsnorm_bwd(_as_2d(gy), w, rstd, w_offset=ctx.w_offset)
+        return gx.view(gy.shape), None, None, None
+
+
+class _LayerNormIdentityFn(Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias, eps):
+        if not x.is_cuda or x.dtype not in (torch.bfloat16, torch.float32):
+            raise LrpError("layer_norm_forward: CUDA bf16/fp32 tensors only")
+        x2 = _as_2d(x)
+        w = None if weight is None else weight.detach().to(x.dtype).contiguous()
+        b = None if bias is None else bias.detach().to(x.dtype).contiguous()
+        y, _, rstd = ops.layernorm_fwd(x2, w, b, eps)
+        ctx.w = w
+        ctx.save_for_backward(rstd)
+        return y.view(x.shape)
+
+    @staticmethod
+    def backward(ctx, gy):
+        (rstd,) = ctx.saved_tensors
+        return ops.layernorm_bwd(_as_2d(gy), ctx.w, rstd).view(gy.shape), None, None, None
+
+
+class _LinearFn(Function):
+    """y = x W^T + b on the tcgen05 GEMM; backward g_x = g_y W (weights are frozen on this path)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        x2 = _as_2d(x)
+        w = weight.detach()
+        w = w if w.is_contiguous() else w.contiguous()
+        y = torch.empty((x2.shape[0], w.shape[0]), dtype=torch.bfloat16, device=x.device)
+        ops.linear_fwd(x2, w, y, bias=None if bias is None else bias.detach().float().contiguous())
+        ctx.save_for_backward(w)
+        return y.view(*x.shape[:-1], w.shape[0])
+
+    @staticmethod
+    def backward(ctx, gy):
+        (w,) = ctx.saved_tensors
+        g2 = _as_2d(gy)
+        gx = torch.empty((g2.shape[0], w.shape[1]), dtype=torch.bfloat16, device=gy.device)
+        ops.linear_dgrad(g2, w, gx)
+        return gx.view(*gy.shape[:-1], w.shape[1]), None, None
+
+
+def _linear_ok(x: torch.Tensor, weight: torch.Tensor) -> bool:
+    return (x.is_cuda and x.dtype == torch.bfloat16 and weight.dtype == torch.bfloat16 and weight.shape[0] % 8 == 0
+            and weight.shape[1] % 8 == 0)
+
+
+def _linear(mod, x):
+    """run an nn.Linear through the B200 GEMM"""
+    if not _linear_ok(x, mod.weight):
+        raise LrpError(f"linear: needs CUDA bf16 with in/out features multiples of 8 (got {x.dtype}, {tuple(mod.weight.shape)})")
+    return _LinearFn.apply(x, mod.weight, mod.bias)
+
+
+class _GatedMLPFn(Function):
+    """down( divide_gradient_2( identity_rule(act)(gate(x)) * up(x) ) ) as five launches forward, five backward."""
+
+    @staticmethod
+    def forward(ctx, x, wg, wu, wd, bg, bu, bd, act):
+        _need_bf16_cuda(x, "gated_mlp_forward")
+        x2 = _as_2d(x)
+        T, I = x2.shape[0], wg.shape[0]
+        wg, wu, wd = (w.detach().contiguous() for w in (wg, wu, wd))
+        f32 = lambda b: None if b is None else b.detach().float().contiguous()
+        gu = torch.empty((T, 2 * I), dtype=torch.bfloat16, device=x.device)
+        ops.linear_fwd(x2, wg, gu[:, :I], bias=f32(bg))
+        ops.linear_fwd(x2, wu, gu[:, I:], bias=f32(bu))
+        a = ops.gated_act_fwd(gu, act)
+        y = torch.empty((T, wd.shape[0]), dtype=torch.bfloat16, device=x.device)
+        ops.linear_fwd(a, wd, y, bias=f32(bd))
+        ctx.save_for_backward(gu, wg, wu, wd)
+        ctx.act = act
+        return y.view(*x.shape[:-1], wd.shape[0])
+
+    @staticmethod
+    def backward(ctx, gy):
+        gu, wg, wu, wd = ctx.saved_tensors
+        T, I = gu.shape[0], wg.shape[0]
+        g2 = _as_2d(gy)
+        ga = torch.empty((T, I), dtype=torch.bfloat16, device=gy.device)
+        ops.linear_dgrad(g2, wd, ga)
+        ggu = ops.gated_act_bwd(ga, gu, ctx.act)
+        acc = torch.empty((T, wg.shape[1]), dtype=torch.float32, device=gy.device)
+        ops.linear_dgrad(ggu[:, :I], wg, acc)
+        gx = torch.empty((T, wg.shape[1]), dtype=torch.bfloat16, device=gy.device)
+        ops.linear_dgrad(ggu[:, I:], wu, acc, resid=acc, shadow=gx)
+        return gx.view(*gy.shape[:-1], wg.shape[1]), None, None, None, None, None, None, None
+
+
+class _FlashAttnLRPFn(Function):
+    """soft-max attention with the AttnLRP backward (dQ/q_div, dK/k_div, dV/v_div); q,k,v in HF layout [B,H,S,D]."""
+
+    @staticmethod
+    def forward(ctx, q, k, v, scale, causal, window, q_div, k_div, v_div):
+        for t, n in ((q, "query"), (k, "key"), (v, "value")):
+            _need_bf16_cuda(t, f"attention {n}")
+        qs, ks, vs = (t.transpose(1, 2).contiguous() for t in (q, k, v))  # [B,S,H,D]; no copy if already so in memory
+        o, lse = ops.attn_fwd(qs, ks, vs, scale, causal=causal, window=window)
+        ctx.save_for_backward(qs, ks, vs, o, lse)
+        ctx.cfg = (scale, causal, window, q_div, k_div, v_div)
+        return o  # [B,S,H,D] — what HF attention functions return after their transpose(1,2).contiguous()
+
+    @staticmethod
+    def backward(ctx, d_o):
+        qs, ks, vs, o, lse = ctx.saved_tensors
+        scale, causal, window, q_div, k_div, v_div = ctx.cfg
+        dq, dk, dv = ops.attn_bwd(qs, ks, vs, o, d_o.contiguous(), lse, scale, causal=causal, window=window, q_div=q_div,
+                                  k_div=k_div, v_div=v_div)
+        return dq.transpose(1, 2), dk.transpose(1, 2), dv.transpose(1, 2), None, None, None, None, None, None
+
+
+def _check_mask_is_causal(mask, S, window):
+    """Only plain (optionally sliding-window) causal attention exists on the B200 path; padding masks raise."""
+    if mask is None:
+        return
+    if mask.dim() != 4 or mask.shape[-1] != S or mask.shape[-2] != S:
+        raise LrpError(f"attention_mask of shape {tuple(mask.shape)} is not supported (causal self-attention only)")
+    i = torch.arange(S, device=mask.device)
+    allowed = i[None, :] <= i[:, None]
+    if window:
+        allowed &= (i[:, None] - i[None, :]) < window
+    got = mask if mask.dtype == torch.bool else (mask == 0)
+    if not bool((got == allowed).all()):
+        raise LrpError("attention_mask is not a plain causal mask (padding / custom masks are not supported)")
+
+
+def _lrp_attention(module, query, key, value, args, kwargs, q_div, k_div, v_div):
+    mask = args[0] if len(args) > 0 else kwargs.get("attention_mask")
+    scaling = kwargs.get("scaling")
+    if scaling is None:
+        scaling = args[2] if len(args) > 2 else 1.0 / math.sqrt(query.shape[-1])
+    if kwargs.get("softcap") is not None:
+        raise LrpError("attention softcap is not supported by the B200 AttnLRP kernel")
+    window = kwargs.get("sliding_window") or 0
+    is_causal = kwargs.get("is_causal")
+    if is_causal is None:
+        is_causal = getattr(module, "is_causal", True)
+    S = query.shape[2]
+    if key.shape[2] != S:
+        raise LrpError("AttnLRP needs full-sequence self-attention (use_cache=False)")
+    if is_causal or mask is not None:
+        _check_mask_is_causal(mask, S, window)
+        causal = True
+    else:
+        causal = False
+    out = _FlashAttnLRPFn.apply(query, key, value, float(scaling), bool(causal), int(window), q_div, k_div, v_div)
+    return out, None
+
+
+# ---------------------------------------------------------------------------------------------------------
+# AttnLRP patches (reference lxt/efficient/patches.py:111-220)
+# ---------------------------------------------------------------------------------------------------------
+
+
+def rms_norm_forward(self, hidden_states):
+    """identity rule on RMSNorm: variance path detached (reference patches.py:111-123)."""
+    return _RMSNormIdentityFn.apply(hidden_states, self.weight, float(getattr(self, "variance_epsilon", getattr(self, "eps", 1e-6))), 0.0)
+
+
+def gemma_rms_norm_forward(self, x):
+    """Gemma-style RMSNorm `(1 + w) * x_hat` with the identity rule (reference lxt/efficient/models/gemma3.py:11-12)."""
+    return _RMSNormIdentityFn.apply(x, self.weight, float(self.eps), 1.0)
+
+
+def layer_norm_forward(self, x):
+    """identity rule on LayerNorm: std detached (reference patches.py:126-142)."""
+    return _LayerNormIdentityFn.apply(x, self.weight, self.bias, float(self.eps))
+
+
+def gated_mlp_forward(self, x):
+    """identity rule on the activation, uniform rule on the product (reference patches.py:145-157)."""
+    act = _act_code(self.act_fn)
+    if act is None:
+        raise LrpError(f"gated_mlp_forward: unsupported activation {type(self.act_fn).__name__}")
+    return _GatedMLPFn.apply(x, self.gate_proj.weight, self.up_proj.weight, self.down_proj.weight, self.gate_proj.bias,
+                             self.up_proj.bias, self.down_proj.bias, act)
+
+
+def _find(mod, *names):
+    for n in names:
+        if hasattr(mod, n):
+            return getattr(mod, n)
+    raise AttributeError(f"{type(mod).__name__} has none of {names}")
+
+
+def mlp_forward(self, x):
+    """identity rule on the activation of a plain 2-layer MLP (reference patches.py:159-169)."""
+    up, down = _find(self, "up_proj", "c_fc", "fc1"), _find(self, "down_proj", "c_proj", "fc2")
+    act = _find(self, "act_fn", "act", "activation_fn")
+    if isinstance(up, torch.nn.Linear):
+        h = _linear(up, x)
+    else:
+        h = up(x)
+    h = identity_rule_implicit(act, h)
+    return _linear(down, h) if isinstance(down, torch.nn.Linear) else down(h)
+
+
+def linear_forward(self, x):
+    """nn.Linear on the tcgen05 GEMM (forward + LRP dgrad).  Not part of the reference's patch map — it leaves
+    nn.Linear to cuBLAS — added so that a patched model runs every FLOP of the path on the B200 kernels.
+    Inputs the kernel does not take (fp32, CPU, odd widths) go through the original forward unchanged."""
+    if _linear_ok(x, self.weight):
+        return _LinearFn.apply(x, self.weight, self.bias)
+    return self.original_forward(x)
+
+
+def wrap_attention_forward(forward_fn):
+    """AttnLRP attention: uniform rule on both matmuls = dQ/4, dK/4, dV/2 (reference patches.py:193-203).
+    `forward_fn` (the HF attention implementation being replaced) is kept only for introspection."""
+
+    def attention_forward(module, query, key, value, *args, **kwargs):
+        return _lrp_attention(module, query, key, value, args, kwargs, 4.0, 4.0, 2.0)
+
+    attention_forward.wrapped = forward_fn
+    return attention_forward
+
+
+def _patch_attention_registry(module, wrapper):
+    new_forward = wrapper(module.eager_attention_forward)
+    if check_already_patched(module.eager_attention_forward, new_forward):
+        return False
+    module.eager_attention_forward = new_forward
+    for key, value in list(module.ALL_ATTENTION_FUNCTIONS.items()):
+        new_forward = wrapper(value)
+        if check_already_patched(value, new_forward):
+            return False  # registry shared with an already patched family (reference behaviour, patches.py:184-189)
+        module.ALL_ATTENTION_FUNCTIONS[key] = new_forward
+    return True
+
+
+def patch_attention(module):
+    """Patch `module.eager_attention_forward` and every entry of the shared `ALL_ATTENTION_FUNCTIONS` registry
+    (reference patches.py:171-190)."""
+    return _patch_attention_registry(module, wrap_attention_forward)
+
+
+def non_linear_forward(self, x):
+    """identity rule on an element-wise activation module (reference patches.py:206-211)."""
+    code = _act_code(self)
+    return identity_rule_implicit(self if code is not None else self.original_forward, x)
+
+
+def dropout_forward(self, x):
+    """Dropout is the identity on this path (reference patches.py:214-220: lets HF checkpointing run in train())."""
+    return x
+
+
+# ---------------------------------------------------------------------------------------------------------
+# CP-LRP patches (reference lxt/efficient/patches.py:228-280)
+# ---------------------------------------------------------------------------------------------------------
+
+
+def cp_wrap_attention_forward(forward_fn):
+    """CP-LRP: no relevance through the softmax (q, k detached), plain gradient through v."""
+
+    def cp_attention_forward(module, query, key, value, *args, **kwargs):
+        return _lrp_attention(module, query, key, value, args, kwargs, 0.0, 0.0, 1.0)
+
+    cp_attention_forward.wrapped = forward_fn
+    return cp_attention_forward
+
+
+def patch_cp_attention(module):
+    return _patch_attention_registry(module, cp_wrap_attention_forward)
+
+
+def cp_multi_head_attention_forward(self, query, key, value, *args, **kwargs):
+    """CP-LRP for torch.nn.MultiheadAttention: q, k detached (reference patches.py:261-269)."""
+    return self.original_forward(stop_gradient(query), stop_gradient(key), value, *args, **kwargs)
+
+
+def cp_gated_mlp_forward(self, x):
+    """CP-LRP: no relevance through the gate (reference patches.py:272-280)."""
+    gate = stop_gradient(_linear(self.gate_proj, x))
+    act = _act_code(self.act_fn)
+    gate = ops.act_identity_fwd(gate.contiguous(), act) if act is not None else self.act_fn(gate)
+    weighted = _MulConstFn.apply(_linear(self.up_proj, x), gate)
+    return _linear(self.down_proj, weighted)
+
+
+class _MulConstFn(Function):
+    """y = x * c with c constant (detached): g_x = g_y * c"""
+
+    @staticmethod
+    def forward(ctx, x, c):
+        ctx.save_for_backward(c)
+        return ops.mul(x, c)
+
+    @staticmethod
+    def backward(ctx, gy):
+        (c,) = ctx.saved_tensors
+        return ops.mul(gy, c), None

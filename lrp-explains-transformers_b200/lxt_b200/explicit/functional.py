@@ -1,0 +1,195 @@
+"""Relevance-space rules — drop-in for `lxt.explicit.functional` (reference lxt/explicit/functional.py:44-158,
+276-536).  Same names / argument order / defaults.  Users seed with `y.backward(relevance)` and read `x.grad`.
+
+All arithmetic of the backward rules runs in liblrp_b200.so kernels:
+  linear_epsilon   one fused tcgen05 launch  (z, R/(z+eps), contraction with W, * x)
+  matmul           eps+uniform rule: eps_div kernel + two tcgen05 GEMMs per batch slice + mul kernel
+  softmax          Deep-Taylor rule kernel;  add2 / mul2 / rms_norm_identity element-wise kernels
+CUDA tensors only (bf16 or fp32; GEMM operands are consumed as bf16).
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn.functional as F
+from torch.autograd import Function
+
+from .. import ops
+from .._capi import LrpError
+
+
+def _stabilize(input, epsilon=1e-6, inplace=False):
+    """`z + eps` — no sign handling, exactly like the reference (functional.py:266-273)."""
+    return input.add_(epsilon) if inplace else input + epsilon
+
+
+def _fwd_linear(x2, w, b):
+    """forward of linear on the tcgen05 GEMM; returns fp32 or bf16 following x (odd widths are zero-padded)"""
+    N0 = w.shape[0]
+    xb = ops.pad_to8(x2.to(torch.bfloat16), [1]).contiguous()
+    wb = ops.pad_to8(w.to(torch.bfloat16), [0, 1]).contiguous()
+    out = torch.empty((x2.shape[0], wb.shape[0]), dtype=x2.dtype if x2.dtype == torch.bfloat16 else torch.float32, device=x2.device)
+    ops.linear_fwd(xb, wb, out, bias=None if b is None else ops.pad_to8(b.float(), [0]).contiguous())
+    return out[:, :N0] if wb.shape[0] != N0 else out
+
+
+class linear_epsilon_fn(Function):
+    @staticmethod
+    def forward(ctx, inputs, weight, bias=None, epsilon=1e-6):
+        if not inputs.is_cuda:
+            raise LrpError("linear_epsilon: CUDA tensors only (no CPU fallback)")
+        x2 = inputs.reshape(-1, inputs.shape[-1])
+        out = _fwd_linear(x2, weight, bias).to(inputs.dtype)
+        ctx.save_for_backward(inputs, weight, bias if bias is not None else torch.empty(0, device=inputs.device))
+        ctx.has_bias, ctx.epsilon = bias is not None, epsilon
+        return out.view(*inputs.shape[:-1], weight.shape[0])
+
+    @staticmethod
+    def backward(ctx, *out_relevance):
+        inputs, weight, bias = ctx.saved_tensors
+        R = out_relevance[0].reshape(-1, weight.shape[0])
+        if R.dtype not in (torch.float32, torch.bfloat16):
+            R = R.float()
+        r_in = ops.linear_eps_bwd(inputs.reshape(-1, inputs.shape[-1]), weight, bias if ctx.has_bias else None, R, ctx.epsilon)
+        return r_in.to(inputs.dtype).view(inputs.shape), None, None, None
+
+
+def _bmm_kernel(a3, b3, b_layout, mul=None):
+    """per-slice tcgen05 GEMMs over the leading batch dim; a3 [G,M,K]; b3 [G,N,K] (layout 0) or [G,K,N] (layout 1)"""
+    G, M0, _ = a3.shape
+    N0 = b3.shape[1] if b_layout == 0 else b3.shape[2]
+    ab = ops.pad_to8(a3.to(torch.bfloat16), [1, 2]).contiguous()   # zero padding leaves the products unchanged
+    bb = ops.pad_to8(b3.to(torch.bfloat16), [1, 2]).contiguous()
+    M = ab.shape[1]
+    N = bb.shape[1] if b_layout == 0 else bb.shape[2]
+    out = torch.empty((G, M, N), dtype=torch.float32, device=a3.device)
+    for g in range(G):
+        ops.gemm(ab[g], bb[g], out[g], b_layout=b_layout)
+    return out[:, :M0, :N0] if (M, N) != (M0, N0) else out
+
+
+class matmul_fn(Function):
+    @staticmethod
+    def forward(ctx, input_a, input_b, inplace=False, epsilon=1e-6):
+        if not input_a.is_cuda:
+            raise LrpError("matmul: CUDA tensors only (no CPU fallback)")
+        M, K = input_a.shape[-2:]
+        N = input_b.shape[-1]
+        a3 = input_a.reshape(-1, M, K)
+        b3 = input_b.expand(*input_a.shape[:-2], K, N).reshape(-1, K, N)
+        out = _bmm_kernel(a3, b3, 1).to(input_a.dtype).view(*input_a.shape[:-2], M, N)
+        ctx.save_for_backward(input_a, input_b, out)
+        ctx.epsilon = epsilon
+        return out
+
+    @staticmethod
+    def backward(ctx, *out_relevance):
+        a, b, out = ctx.saved_tensors
+        M, K = a.shape[-2:]
+        N = b.shape[-1]
+        s = ops.eps_div(out_relevance[0].to(out.dtype), out, ctx.epsilon, alpha=2.0)        # R / (2 O + eps)
+        s3 = s.reshape(-1, M, N)
+        a3 = a.reshape(-1, M, K)
+        b3 = b.expand(*a.shape[:-2], K, N).reshape(-1, K, N)
+        ra = ops.mul(_bmm_kernel(s3, b3, 0).to(a.dtype).view(a.shape), a)                   # (s b^T) * a
+        rb = _bmm_kernel(a3.transpose(1, 2).contiguous(), s3, 1).to(b.dtype)                # (a^T s)
+        rb = ops.mul(rb.view(*a.shape[:-2], K, N), b.expand(*a.shape[:-2], K, N))
+        if rb.shape != b.shape:
+            rb = rb.sum_to_size(b.shape)
+        return ra, rb, None, None
+
+
+class softmax_fn(Function):
+    @staticmethod
+    def forward(ctx, inputs, dim, dtype=None, temperature=1.0, inplace=False):
+        if dtype is not None:
+            inputs = inputs.to(dtype)
+        inputs = inputs / temperature
+        outputs = F.softmax(inputs, dim=dim, dtype=dtype)
+        ctx.save_for_backward(inputs, outputs)
+        ctx.dim = dim
+        return outputs
+
+    @staticmethod
+    def backward(ctx, *out_relevance):
+        inputs, outputs = ctx.saved_tensors
+        dim = ctx.dim if ctx.dim >= 0 else inputs.dim() + ctx.dim
+        R = out_relevance[0].to(inputs.dtype)
+        if dim != inputs.dim() - 1:
+            x, p, r = (t.transpose(dim, -1).contiguous() for t in (inputs, outputs, R))
+            return ops.softmax_dt_bwd(x, p, r).transpose(dim, -1), None, None, None, None
+        return ops.softmax_dt_bwd(inputs, outputs, R), None, None, None, None
+
+
+class add2_tensors_fn(Function):
+    @staticmethod
+    def forward(ctx, input_a, input_b, inplace=False, epsilon=1e-6):
+        outputs = input_a + input_b
+        if input_a.requires_grad or input_b.requires_grad:
+            ctx.save_for_backward(input_a, input_b)
+            ctx.epsilon = epsilon
+        return outputs
+
+    @staticmethod
+    def backward(ctx, *out_relevance):
+        a, b = ctx.saved_tensors
+        shape = torch.broadcast_shapes(a.shape, b.shape)
+        ra, rb = ops.add2_bwd(a.expand(shape), b.expand(shape), out_relevance[0].to(a.dtype), ctx.epsilon)
+        return ra.sum_to_size(a.shape), rb.sum_to_size(b.shape), None, None
+
+
+class rms_norm_identity_fn(Function):
+    @staticmethod
+    def forward(ctx, hidden_states, weight, variance_epsilon):
+        if hidden_states.is_cuda and hidden_states.dtype == torch.bfloat16:
+            y, _ = ops.rmsnorm_fwd(hidden_states.reshape(-1, hidden_states.shape[-1]).contiguous(),
+                                   weight.to(torch.bfloat16).contiguous(), variance_epsilon, want_rstd=False)
+            return y.view(hidden_states.shape)
+        hs = hidden_states.to(torch.float32)
+        hs = hs * torch.rsqrt(hs.pow(2).mean(-1, keepdim=True) + variance_epsilon)
+        return weight * hs.to(hidden_states.dtype)
+
+    @staticmethod
+    def backward(ctx, *out_relevance):
+        return out_relevance + (None, None)
+
+
+class mul2_fn(Function):
+    @staticmethod
+    def forward(ctx, input_a, input_b, inplace=False):
+        ctx.requires_grads = [i for i, t in enumerate((input_a, input_b)) if isinstance(t, torch.Tensor) and t.requires_grad]
+        return input_a * input_b
+
+    @staticmethod
+    def backward(ctx, *out_relevance):
+        r = ops.scale(out_relevance[0], 1.0 / len(ctx.requires_grads))
+        return tuple(r if i in ctx.requires_grads else None for i in range(2)) + (None,)
+
+
+def add2(input_a, input_b, inplace=False, epsilon=1e-8):
+    """epsilon-LRP for a + b (AttnLRP Eq. 8)."""
+    return add2_tensors_fn.apply(input_a, input_b, inplace, epsilon)
+
+
+def softmax(input, dim, dtype=None, temperature=1.0, inplace=False):
+    """Deep-Taylor-with-bias rule for softmax (AttnLRP Prop. 3.1)."""
+    return softmax_fn.apply(input, dim, dtype, temperature, inplace)
+
+
+def linear_epsilon(input, weight, bias=None, epsilon=1e-6):
+    """epsilon-LRP for nn.functional.linear (AttnLRP Eq. 8) — the fused single-launch sm_100a kernel."""
+    return linear_epsilon_fn.apply(input, weight, bias, epsilon)
+
+
+def matmul(input_a, input_b, inplace=False, epsilon=1e-8):
+    """epsilon + uniform rule for torch.matmul (AttnLRP Prop. 3.3)."""
+    return matmul_fn.apply(input_a, input_b, inplace, epsilon)
+
+
+def rms_norm_identity(hidden_states, weight, variance_epsilon):
+    """identity rule for RMSNorm (AttnLRP Prop. 3.4)."""
+    return rms_norm_identity_fn.apply(hidden_states, weight, variance_epsilon)
+
+
+def mul2(input_a, input_b, inplace=False):
+    """uniform rule for a * b (AttnLRP Prop. 3.2)."""
+    return mul2_fn.apply(input_a, input_b, inplace)

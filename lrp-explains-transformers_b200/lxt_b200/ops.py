@@ -300,3 +300,105 @@ def cast_bf16(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tens
         out = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
     check(_capi.lib().lrp_cast_f32_to_bf16(x.data_ptr(), out.data_ptr(), x.numel(), _stream()), "lrp_cast_f32_to_bf16")
     return out
+
+
+# ---------------------------------------------------------------------------------------------------------
+# generic element-wise rule kernels (any shape; tensors of one call share dtype bf16 or fp32)
+# ---------------------------------------------------------------------------------------------------------
+def _ew_prepare(*ts: torch.Tensor):
+    t0 = ts[0]
+    if not t0.is_cuda:
+        raise _capi.LrpError("lxt_b200 rules run on CUDA tensors only (no CPU fallback)")
+    if t0.dtype not in (torch.float32, torch.bfloat16):
+        raise _capi.LrpError(f"lxt_b200 rules support bf16 and fp32 tensors, got {t0.dtype}")
+    out = []
+    for t in ts:
+        if t.dtype != t0.dtype or t.shape != t0.shape or t.device != t0.device:
+            t = t.to(device=t0.device, dtype=t0.dtype).expand(t0.shape)
+        out.append(t.contiguous())
+    return out, int(t0.dtype == torch.float32)
+
+
+def eps_div(r: torch.Tensor, z: torch.Tensor, eps: float, alpha: float = 1.0) -> torch.Tensor:
+    """r / (alpha*z + eps)"""
+    (r, z), f32 = _ew_prepare(r, z)
+    out = torch.empty_like(r)
+    check(_capi.lib().lrp_eps_div(r.data_ptr(), z.data_ptr(), out.data_ptr(), r.numel(), alpha, eps, f32, _stream()), "lrp_eps_div")
+    return out
+
+
+def mul(a: torch.Tensor, b: torch.Tensor, scale: float = 1.0) -> torch.Tensor:
+    (a, b), f32 = _ew_prepare(a, b)
+    out = torch.empty_like(a)
+    check(_capi.lib().lrp_mul(a.data_ptr(), b.data_ptr(), out.data_ptr(), a.numel(), scale, f32, _stream()), "lrp_mul")
+    return out
+
+
+def scale(x: torch.Tensor, factor: float) -> torch.Tensor:
+    (x,), f32 = _ew_prepare(x)
+    out = torch.empty_like(x)
+    check(_capi.lib().lrp_scale(x.data_ptr(), out.data_ptr(), x.numel(), factor, f32, _stream()), "lrp_scale")
+    return out
+
+
+def identity_rule_bwd(gy: torch.Tensor, x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
+    (gy, x, y), f32 = _ew_prepare(gy, x, y)
+    gx = torch.empty_like(x)
+    check(_capi.lib().lrp_identity_rule_bwd(gy.data_ptr(), x.data_ptr(), y.data_ptr(), gx.data_ptr(), x.numel(), f32, _stream()),
+          "lrp_identity_rule_bwd")
+    return gx
+
+
+def softmax_dt_bwd(x: torch.Tensor, p: torch.Tensor, r: torch.Tensor) -> torch.Tensor:
+    """Deep-Taylor softmax relevance over the LAST dimension"""
+    (x, p, r), f32 = _ew_prepare(x, p, r)
+    cols = x.shape[-1]
+    out = torch.empty_like(x)
+    check(_capi.lib().lrp_softmax_dt_bwd(x.data_ptr(), p.data_ptr(), r.data_ptr(), out.data_ptr(), x.numel() // cols, cols, f32,
+                                         _stream()), "lrp_softmax_dt_bwd")
+    return out
+
+
+def add2_bwd(a: torch.Tensor, b: torch.Tensor, r: torch.Tensor, eps: float):
+    (a, b, r), f32 = _ew_prepare(a, b, r)
+    ra, rb = torch.empty_like(a), torch.empty_like(a)
+    check(_capi.lib().lrp_add2_bwd(a.data_ptr(), b.data_ptr(), r.data_ptr(), ra.data_ptr(), rb.data_ptr(), a.numel(), eps, f32,
+                                   _stream()), "lrp_add2_bwd")
+    return ra, rb
+
+
+def pad_to8(t: torch.Tensor, dims) -> torch.Tensor:
+    """zero-pad the given dims of `t` up to multiples of 8 (tensor-core tiles need 16-byte rows)"""
+    pads = [0, 0] * t.dim()
+    need = False
+    for d in dims:
+        d = d % t.dim()
+        extra = (-t.shape[d]) % 8
+        if extra:
+            need = True
+            pads[2 * (t.dim() - 1 - d) + 1] = extra
+    return torch.nn.functional.pad(t, pads) if need else t
+
+
+def linear_eps_bwd(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], r_out: torch.Tensor, eps: float) -> torch.Tensor:
+    """Fused relevance-space epsilon rule of nn.Linear in one launch: R_in = x * ((R_out/(x W^T + b + eps)) W).
+    x [T,K], w [N,K] are consumed as bf16 (fp32 inputs are rounded once); R_out / R_in keep R_out's dtype.
+    Feature counts that are not multiples of 8 are zero-padded (padded outputs have R = 0, z = 0 -> s = 0)."""
+    if not x.is_cuda:
+        raise _capi.LrpError("linear_eps_bwd: CUDA tensors only")
+    T, K0 = x.shape
+    N0 = w.shape[0]
+    xb = pad_to8(x.to(torch.bfloat16), [1]).contiguous()
+    wb = pad_to8(w.to(torch.bfloat16), [0, 1]).contiguous()
+    N, K = wb.shape
+    r = pad_to8(r_out, [1]).contiguous()
+    if r.dtype not in (torch.float32, torch.bfloat16):
+        raise _capi.LrpError("linear_eps_bwd: relevance must be bf16 or fp32")
+    bf = None if bias is None else pad_to8(bias.to(torch.float32), [0]).contiguous()
+    r_in = torch.empty((T, K), dtype=r.dtype, device=x.device)
+    s_ws = torch.empty((T, N), dtype=torch.bfloat16, device=x.device)
+    flags = torch.zeros((int(_capi.lib().lrp_linear_eps_flags_count(T)),), dtype=torch.int32, device=x.device)
+    check(_capi.lib().lrp_linear_eps_bwd(xb.data_ptr(), wb.data_ptr(), _p(bf), r.data_ptr(), int(r.dtype == torch.float32),
+                                         r_in.data_ptr(), s_ws.data_ptr(), flags.data_ptr(), T, N, K, eps, _stream()),
+          "lrp_linear_eps_bwd")
+    return r_in[:, :K0] if K != K0 else r_in

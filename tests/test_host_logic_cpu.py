@@ -1,0 +1,102 @@
+"""CPU: host-side logic of the drop-in API (patch plumbing, registries, sharding) and the loud-failure contract
+(no CPU fallback: rules / ops raise on CPU tensors instead of silently computing elsewhere)."""
+import types
+import warnings
+
+import pytest
+import torch
+
+from lxt_b200 import _capi, ops
+from lxt_b200.efficient import monkey_patch
+from lxt_b200.efficient import patches as P
+from lxt_b200.efficient import rules as R
+from lxt_b200.efficient.models import DEFAULT_MAP, get_default_map
+
+
+def test_patch_method_and_keep_original():
+    class A(torch.nn.Identity):  # forward lives in torch.nn.modules.linear, i.e. "not yet patched"
+        pass
+
+    def fwd(self, x):
+        return x * 2
+
+    orig = A.forward
+    assert P.patch_method(fwd, A, keep_original=True) is True
+    assert A.forward is fwd and A.original_forward is orig
+    assert A().forward(3) == 6
+
+
+def test_already_patched_guard_is_module_string_equality():
+    # reference lxt/efficient/patches.py:40: functions from the same module count as "already patched"
+    class B:
+        forward = P.dropout_forward
+
+    with pytest.warns(UserWarning):
+        assert P.patch_method(P.rms_norm_forward, B) is False
+
+
+def test_replace_module_copies_public_attributes():
+    src, dst = types.ModuleType("src"), types.ModuleType("dst")
+    src.a, src._b = 1, 2
+    assert P.replace_module(src, dst) is True and dst.a == 1 and dst._b == 2
+    assert P.replace_module(src, src) is False
+
+
+def test_default_map_and_unknown_module():
+    from transformers.models.llama import modeling_llama
+    assert modeling_llama in DEFAULT_MAP and "attnLRP" in dir(__import__("lxt_b200.efficient.models.llama", fromlist=["x"]))
+    with pytest.raises(ValueError, match="not yet supported"):
+        get_default_map(types)
+
+
+def test_monkey_patch_reports_failed_patchers():
+    calls = []
+
+    class T1:
+        pass
+
+    class T2:
+        pass
+
+    pm = {T1: lambda t: calls.append(t) or True, T2: lambda t: calls.append(t) or False}
+    with pytest.warns(UserWarning, match="Failed to patch T2"):
+        monkey_patch(types, patch_map=pm)
+    assert calls == [T1, T2]
+
+
+def test_attention_wrapper_shape_of_api():
+    w = P.wrap_attention_forward(lambda *a, **k: None)
+    assert w.__name__ == "attention_forward" and w.__module__ == P.__name__
+    cp = P.cp_wrap_attention_forward(lambda *a, **k: None)
+    assert cp.__name__ == "cp_attention_forward"
+
+
+def test_rules_fail_loudly_on_cpu_tensors():
+    x = torch.randn(4, 8, requires_grad=True)
+    assert R.stop_gradient(x).requires_grad is False
+    y = R.divide_gradient(x, 4)  # forward is the identity and launches nothing
+    with pytest.raises(_capi.LrpError):
+        y.sum().backward()
+    with pytest.raises(_capi.LrpError):
+        R.identity_rule_implicit(torch.nn.functional.silu, x).sum().backward()
+    with pytest.raises(_capi.LrpError):
+        ops.eps_div(x.detach(), x.detach(), 1e-6)
+    with pytest.raises(_capi.LrpError):
+        ops.gemm(torch.zeros(8, 8, dtype=torch.bfloat16), torch.zeros(8, 8, dtype=torch.bfloat16), torch.zeros(8, 8), b_layout=0)
+
+
+def test_engine_refuses_cpu():
+    from lxt_b200.engine import LlamaAttnLRPEngine, LlamaDims
+    with pytest.raises(RuntimeError):
+        LlamaAttnLRPEngine(LlamaDims(d=64, I=128, H=1, Hkv=1, D=64, L=1, V=16), torch.device("cpu"), {})
+
+
+def test_shard_range_is_balanced_and_contiguous():
+    from lxt_b200.dist import shard_range
+    for n in (1, 7, 32, 33):
+        for w in (1, 2, 3, 8):
+            spans = [shard_range(n, r, w) for r in range(w)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(spans[i][1] == spans[i + 1][0] for i in range(w - 1))
+            sizes = [b - a for a, b in spans]
+            assert max(sizes) - min(sizes) <= 1

@@ -1,0 +1,176 @@
+"""GPU: every C-ABI kernel against a plain PyTorch fp32 reference of the same op on the same bf16 inputs.
+Tolerances (rel-L2): fp32-output kernels 1e-5; bf16-output kernels 3e-3 (one bf16 rounding is 1.6e-3 rel-L2)."""
+import math
+
+import pytest
+import torch
+
+from helpers import rel_l2
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from lxt_b200 import ops as o
+    return o
+
+
+def rnd(*shape, scale=1.0, dtype=torch.bfloat16, seed=0):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    return (torch.randn(*shape, generator=g, device="cuda") * scale).to(dtype)
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (300, 520, 200), (1000, 1024, 4096), (64, 2048, 512), (4224, 768, 384)])
+@pytest.mark.parametrize("layout", [0, 1])
+def test_gemm_plain_and_fused_epilogue(ops, M, N, K, layout):
+    a = rnd(M, K, seed=1)
+    b = rnd(N, K, seed=2) if layout == 0 else rnd(K, N, seed=2)
+    ref = a.float() @ (b.float().T if layout == 0 else b.float())
+    out = torch.empty(M, N, dtype=torch.bfloat16, device="cuda")
+    ops.gemm(a, b, out, b_layout=layout)
+    assert rel_l2(out.float(), ref) < 3e-3
+    # fp32 out + residual + row/col scale + bias + bf16 shadow
+    res, rs, cs, bias = rnd(M, N, dtype=torch.float32, seed=3), rnd(M, dtype=torch.float32, seed=4), rnd(N, dtype=torch.float32, seed=5), rnd(N, dtype=torch.float32, seed=6)
+    out32 = torch.empty(M, N, dtype=torch.float32, device="cuda")
+    sh = torch.empty(M, N, dtype=torch.bfloat16, device="cuda")
+    ops.gemm(a, b, out32, b_layout=layout, resid=res, rowscale=rs, colscale=cs, bias=bias, shadow=sh, alpha=0.5)
+    ref2 = res + 0.5 * ref * rs[:, None] * cs[None, :] + bias[None, :]
+    assert rel_l2(out32, ref2) < 1e-5
+    assert rel_l2(sh.float(), ref2) < 3e-3
+
+
+def test_gemm_strided_views_and_inplace_accumulate(ops):
+    T, I, d = 384, 256, 128
+    gu = rnd(T, 2 * I, seed=7)
+    w = rnd(I, d, seed=8)
+    acc = rnd(T, d, dtype=torch.float32, seed=9)
+    ref = acc + gu[:, I:].float() @ w.float()
+    ops.linear_dgrad(gu[:, I:], w, acc, resid=acc)  # A is a strided view, output accumulates in place
+    assert rel_l2(acc, ref) < 1e-5
+
+
+def test_gemm_argument_errors_are_loud(ops):
+    from lxt_b200._capi import LrpError
+    a, b = rnd(16, 12), rnd(16, 12)
+    with pytest.raises(LrpError):
+        ops.gemm(a, b, torch.empty(16, 16, dtype=torch.bfloat16, device="cuda"), b_layout=0)  # K % 8 != 0
+    with pytest.raises(LrpError):
+        ops.gemm(rnd(16, 16), rnd(16, 8), torch.empty(16, 16, dtype=torch.bfloat16, device="cuda"), b_layout=0)
+
+
+def _attn_ref(q, k, v, d_o, scale, causal, window):
+    """fp32 torch reference; q [B,S,H,D], k/v [B,S,Hkv,D]"""
+    B, S, H, D = q.shape
+    G = H // k.shape[2]
+    qf, kf, vf = (t.float().transpose(1, 2).requires_grad_() for t in (q, k, v))
+    kr, vr = kf.repeat_interleave(G, 1), vf.repeat_interleave(G, 1)
+    sc = qf @ kr.transpose(-1, -2) * scale
+    i = torch.arange(S, device=q.device)
+    m = torch.zeros(S, S, dtype=torch.bool, device=q.device)
+    if causal:
+        m |= i[None, :] > i[:, None]
+    if window:
+        m |= (i[:, None] - i[None, :]) >= window
+    sc = sc.masked_fill(m, float("-inf"))
+    p = sc.softmax(-1)
+    o = (p @ vr).transpose(1, 2)
+    o.backward(d_o.float())
+    return o.detach(), torch.logsumexp(sc, -1).detach(), qf.grad.transpose(1, 2), kf.grad.transpose(1, 2), vf.grad.transpose(1, 2)
+
+
+@pytest.mark.parametrize("B,S,H,Hkv,D,causal,window", [(1, 128, 1, 1, 128, True, 0), (2, 300, 4, 2, 128, True, 0),
+                                                       (2, 300, 4, 2, 64, True, 0), (2, 197, 4, 4, 64, False, 0),
+                                                       (1, 520, 4, 1, 128, True, 200), (1, 1024, 8, 2, 128, True, 0)])
+def test_flash_attnlrp_fwd_bwd(ops, B, S, H, Hkv, D, causal, window):
+    qkv = rnd(B, S, (H + 2 * Hkv) * D, scale=1.0, seed=11)  # packed buffer: kernels read strided views, no copies
+    q = qkv[:, :, : H * D].view(B, S, H, D)
+    k = qkv[:, :, H * D: (H + Hkv) * D].view(B, S, Hkv, D)
+    v = qkv[:, :, (H + Hkv) * D:].view(B, S, Hkv, D)
+    d_o = rnd(B, S, H, D, seed=12)
+    scale = 1 / math.sqrt(D)
+    o, lse = ops.attn_fwd(q, k, v, scale, causal=causal, window=window)
+    dq, dk, dv = ops.attn_bwd(q, k, v, o, d_o, lse, scale, causal=causal, window=window)
+    ro, rlse, rdq, rdk, rdv = _attn_ref(q, k, v, d_o, scale, causal, window)
+    assert rel_l2(o.float(), ro) < 5e-3
+    assert rel_l2(lse, rlse) < 1e-5
+    # AttnLRP: uniform rule = dQ/4, dK/4, dV/2 (lxt/efficient/patches.py:193-203)
+    assert rel_l2(dq.float(), rdq / 4) < 8e-3
+    assert rel_l2(dk.float(), rdk / 4) < 8e-3
+    assert rel_l2(dv.float(), rdv / 2) < 8e-3
+    # CP-LRP: q,k detached
+    dq0, dk0, dv1 = ops.attn_bwd(q, k, v, o, d_o, lse, scale, causal=causal, window=window, q_div=0.0, k_div=0.0, v_div=1.0)
+    assert float(dq0.abs().max()) == 0.0 and float(dk0.abs().max()) == 0.0
+    assert rel_l2(dv1.float(), rdv) < 8e-3
+
+
+def test_rmsnorm_fwd_bwd(ops):
+    T, d = 777, 1024
+    for xdt in (torch.float32, torch.bfloat16):
+        x, w, g = rnd(T, d, dtype=xdt, seed=21), (1 + 0.1 * rnd(d, dtype=torch.float32, seed=22)).bfloat16(), rnd(T, d, seed=23)
+        for w_off in (0.0, 1.0):
+            y, rstd = ops.rmsnorm_fwd(x, w, 1e-5, w_offset=w_off)
+            xf = x.float()
+            r = torch.rsqrt(xf.pow(2).mean(-1, keepdim=True) + 1e-5)
+            assert rel_l2(rstd, r.squeeze(-1)) < 1e-6
+            assert rel_l2(y.float(), xf * r * (w.float() + w_off)) < 3e-3
+            gx = ops.rmsnorm_bwd(g, w, rstd, w_offset=w_off, out_dtype=torch.float32)
+            assert rel_l2(gx, g.float() * (w.float() + w_off) * r) < 1e-6
+
+
+def test_layernorm_detached_std(ops):
+    T, d = 394, 1024
+    for dt, tol in ((torch.float32, 1e-5), (torch.bfloat16, 4e-3)):
+        x, w, b, g = rnd(T, d, dtype=dt, seed=31), rnd(d, dtype=dt, seed=32), rnd(d, dtype=dt, seed=33), rnd(T, d, dtype=dt, seed=34)
+        y, mean, rstd = ops.layernorm_fwd(x, w, b, 1e-6)
+        xf = x.float().requires_grad_()
+        mu = xf.mean(-1, keepdim=True)
+        std = ((xf - mu) ** 2).mean(-1, keepdim=True).add(1e-6).sqrt()
+        yr = (xf - mu) / std.detach() * w.float() + b.float()  # lxt/efficient/patches.py:126-142
+        yr.backward(g.float())
+        assert rel_l2(y.float(), yr.detach()) < tol
+        assert rel_l2(ops.layernorm_bwd(g, w, rstd).float(), xf.grad) < tol
+
+
+def test_rope_forward_and_transpose(ops):
+    from oracle.attnlrp_oracle import rope_tables, _rotate_half, _rotate_half_T
+    B, S, Hn, D = 2, 200, 6, 128
+    x = rnd(B * S, Hn * D + 256, seed=41)
+    cos, sin = rope_tables(S, D, 10000.0)
+    c, s = cos[:, : D // 2].cuda().contiguous(), sin[:, : D // 2].cuda().contiguous()
+    ref_in = x[:, : Hn * D].float().view(B, S, Hn, D).transpose(1, 2)
+    ref = ref_in * cos.cuda() + _rotate_half(ref_in) * sin.cuda()
+    y = x.clone()
+    ops.rope_inplace(y, Hn, D, c, s, S)
+    assert rel_l2(y[:, : Hn * D].float().view(B, S, Hn, D).transpose(1, 2), ref) < 3e-3
+    assert torch.equal(y[:, Hn * D:], x[:, Hn * D:])  # columns beyond the rotated heads are untouched
+    g = x.clone()
+    ops.rope_inplace(g, Hn, D, c, s, S, inverse=True)
+    refT = ref_in * cos.cuda() + _rotate_half_T(ref_in * sin.cuda())
+    assert rel_l2(g[:, : Hn * D].float().view(B, S, Hn, D).transpose(1, 2), refT) < 3e-3
+
+
+def test_gated_act_rules(ops):
+    T, I = 500, 1536
+    gu, ga = rnd(T, 2 * I, scale=2.0, seed=51), rnd(T, I, seed=52)
+    gate, up = gu[:, :I].float(), gu[:, I:].float()
+    s = torch.nn.functional.silu(gate)
+    assert rel_l2(ops.gated_act_fwd(gu).float(), s * up) < 3e-3
+    ggu = ops.gated_act_bwd(ga, gu).float()
+    gh = ga.float() / 2                                   # divide_gradient (rules.py:125-127)
+    assert rel_l2(ggu[:, I:], gh * s) < 3e-3              # product rule, up branch
+    assert rel_l2(ggu[:, :I], gh * up * (s / (gate + 1e-10))) < 3e-3   # identity rule on SiLU (rules.py:88-100)
+
+
+def test_path_ends(ops):
+    V, d, T = 1000, 512, 300
+    emb = rnd(V, d, seed=61)
+    ids = torch.randint(0, V, (T,), device="cuda")
+    h = ops.embed_gather(ids, emb)
+    assert torch.equal(h, emb[ids].float())
+    logits = rnd(7, 5003, dtype=torch.float32, seed=62)
+    idx, val = ops.argmax_rows(logits)
+    assert torch.equal(idx.long(), logits.argmax(-1)) and torch.equal(val, logits.max(-1).values)
+    g = rnd(T, d, dtype=torch.float32, seed=63)
+    assert rel_l2(ops.gxi_reduce(h, g), (h * g).sum(-1)) < 1e-6
+    assert torch.equal(ops.cast_bf16(g), g.bfloat16())

@@ -1,0 +1,120 @@
+"""GPU: the drop-in rule API (`lxt_b200.explicit.functional`, `.explicit.rules`, `.efficient.rules`) against the
+CPU oracle on the reference's own test shapes (tests/test_rules.py, tests/test_functional.py) and the BASELINE
+"2-layer 128-d MLP".  Inputs are the golden inputs rounded to bf16 (the tensor-core operands are bf16), the oracle
+is evaluated in fp32 on exactly those values.  Tolerances: element-wise fp32 kernels 1e-5; rules whose
+normalised relevance s = R/(z+eps) is a bf16 GEMM operand 2.5e-3 rel-L2 (bound of one bf16 rounding)."""
+import functools
+
+import pytest
+import torch
+
+from helpers import load_npz, rel_l2
+from oracle import attnlrp_oracle as O
+
+pytestmark = pytest.mark.gpu
+T = torch.from_numpy
+
+
+def q(t):
+    """bf16-representable fp32"""
+    return t.bfloat16().float()
+
+
+@pytest.fixture(scope="module")
+def G():
+    return {k: T(v) for k, v in load_npz("rules.npz").items()}
+
+
+def _grad(fn, *xs, seed):
+    xs = [x.cuda().requires_grad_() for x in xs]
+    y = fn(*xs)
+    y.backward(seed.cuda().to(y.dtype))
+    return y.detach().cpu(), [x.grad.float().cpu() for x in xs]
+
+
+def test_linear_epsilon_reference_test_shapes(G):
+    import lxt_b200.explicit.functional as lf
+    import lxt_b200.explicit.rules as rules
+    for x, W, b, R, eps in ((G["le_x"], G["le_W"], G["le_b"], G["le_R"], 1e-6), (G["lin_x"], G["lin_W"], None, G["lin_R"], 1e-9)):
+        x, W, R = q(x), q(W), q(R)
+        b = None if b is None else q(b)
+        exp = O.linear_epsilon_relevance(x, W, b, R, eps)
+        Wc, bc = W.cuda(), None if b is None else b.cuda()
+        y, (got,) = _grad(lambda t: lf.linear_epsilon(t, Wc, bc, eps), x, seed=R)
+        assert rel_l2(y, torch.nn.functional.linear(x, W, b)) < 1e-5
+        assert rel_l2(got, exp) < 2.5e-3
+        # tests/test_rules.py:9-24 — EpsilonRule(F.linear partial) == linear_epsilon
+        rule = rules.EpsilonRule(functools.partial(torch.nn.functional.linear, weight=Wc, bias=bc), epsilon=eps)
+        _, (got2,) = _grad(rule, x, seed=R)
+        assert rel_l2(got2, exp) < 1e-4       # generic VJP path: fp32 element-wise kernels + autograd.grad
+        lin = torch.nn.Linear(W.shape[1], W.shape[0], bias=b is not None).cuda()
+        lin.weight.data.copy_(Wc)
+        if b is not None:
+            lin.bias.data.copy_(bc)
+
+
+def test_two_layer_128d_mlp_epsilon_rule(G):
+    # BASELINE.json configs[0]
+    import lxt_b200.explicit.functional as lf
+    x, W1, b1, W2, b2, R = (q(G[k]) for k in ("mlp_x", "mlp_W1", "mlp_b1", "mlp_W2", "mlp_b2", "mlp_R"))
+    h1 = q(torch.nn.functional.linear(x, W1, b1))  # the kernel's layer-2 input is the bf16-rounded layer-1 output
+    R1 = O.linear_epsilon_relevance(h1, W2, b2, R, 1e-6)
+    exp = O.linear_epsilon_relevance(x, W1, b1, R1, 1e-6)
+    W1c, b1c, W2c, b2c = W1.cuda(), b1.cuda(), W2.cuda(), b2.cuda()
+    _, (got,) = _grad(lambda t: lf.linear_epsilon(lf.linear_epsilon(t, W1c, b1c, 1e-6), W2c, b2c, 1e-6), x, seed=R)
+    assert rel_l2(got, exp) < 5e-3   # two chained bf16-operand rules
+
+
+def test_fused_linear_eps_kernel_large(G):
+    from lxt_b200 import ops
+    g = torch.Generator().manual_seed(3)
+    Tn, N, K = 1500, 1024, 768
+    x = q(torch.rand(Tn, K, generator=g) + 0.5)
+    W = q(torch.rand(N, K, generator=g) + 0.5)
+    b = torch.rand(N, generator=g)
+    R = torch.randn(Tn, N, generator=g)
+    exp = O.linear_epsilon_relevance(x, W, b, R, 1e-6)
+    got = ops.linear_eps_bwd(x.cuda(), W.cuda(), b.cuda(), R.cuda(), 1e-6).cpu()
+    assert rel_l2(got, exp) < 2.5e-3
+
+
+def test_matmul_softmax_add_mul_rms(G):
+    import lxt_b200.explicit.functional as lf
+    import lxt_b200.explicit.rules as rules
+    a, b, R = q(G["mm_a"]), q(G["mm_b"]), q(G["mm_R"])
+    ea, eb = O.matmul_relevance(a, b, R, 1e-9)
+    _, (ga, gb) = _grad(lambda p, r: lf.matmul(p, r, False, 1e-9), a, b, seed=R)
+    assert rel_l2(ga, ea) < 2.5e-3 and rel_l2(gb, eb) < 2.5e-3
+    x, R = G["sm_x"], G["sm_R"]
+    _, (gs,) = _grad(lambda t: lf.softmax(t, -1), x, seed=R)
+    assert rel_l2(gs, O.softmax_relevance(x, R)) < 1e-5
+    a, b, R = G["add_a"], G["add_b"], G["add_R"]
+    _, (ra, rb) = _grad(lambda p, r: lf.add2(p, r, False, 1e-8), a, b, seed=R)
+    ea, eb = O.add2_relevance(a, b, R, 1e-8)
+    assert rel_l2(ra, ea) < 1e-5 and rel_l2(rb, eb) < 1e-5
+    _, (ma, mb) = _grad(lf.mul2, a, b, seed=R)
+    assert torch.allclose(ma, R / 2) and torch.allclose(mb, R / 2)
+    x, w, R = G["rms_x"], G["rms_w"], G["rms_R"]
+    y, (gx,) = _grad(lambda t: lf.rms_norm_identity(t, w.cuda(), 1e-6), x, seed=R)
+    assert torch.allclose(y, G["rms_y"], atol=1e-5) and torch.equal(gx, R)
+
+    class MM(torch.nn.Module):
+        def forward(self, p, r):
+            return torch.matmul(p, r)
+
+    a, b, R = G["ue_a"], G["ue_b"], G["ue_R"]
+    _, (ua, ub) = _grad(rules.UniformEpsilonRule(MM(), epsilon=1e-6), a, b, seed=R)
+    ea, eb = O.uniform_epsilon_matmul_relevance(a, b, R, 1e-6)
+    assert rel_l2(ua, ea) < 1e-4 and rel_l2(ub, eb) < 1e-4
+
+
+def test_efficient_rules(G):
+    from lxt_b200.efficient import rules as R
+    F = torch.nn.functional
+    x, g = G["id_x"], G["id_gout"]
+    for name, fn in (("silu", F.silu), ("gelu", torch.nn.GELU()), ("gelu_tanh", torch.nn.GELU(approximate="tanh")),
+                     ("silu", lambda t: F.silu(t))):  # last: generic-callable path
+        y, (gx,) = _grad(lambda t: R.identity_rule_implicit(fn, t), x, seed=g)
+        assert rel_l2(gx, G[f"id_{name}_g"]) < 1e-5
+    _, (gd,) = _grad(lambda t: R.divide_gradient(t * 1.0, 4), x, seed=g)
+    assert torch.allclose(gd, G["div4_g"])
