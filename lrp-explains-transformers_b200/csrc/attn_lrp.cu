@@ -48,6 +48,60 @@ __device__ __forceinline__ bool is_masked(int qpos, int kpos, int S, int causal,
   return false;
 }
 
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// Per-row column window [lo, hi] (tile-relative) of keys that are NOT masked:
+//   key (kbase + c) is visible iff lo <= c <= hi.
+__device__ __forceinline__ void row_window(int qpos, int kbase, int S, int causal, int window, int& lo, int& hi) {
+  hi = S - 1 - kbase;
+  if (causal) hi = min(hi, qpos - kbase);
+  lo = window > 0 ? qpos - window + 1 - kbase : 0;
+}
+
+template <bool MASK>
+__device__ __forceinline__ float chunk_max(const uint32_t (&v)[32], int c0, int lo, int hi) {
+  float mx = -INFINITY;
+#pragma unroll
+  for (int i = 0; i < 32; ++i) {
+    float t = __uint_as_float(v[i]);
+    if (MASK) t = (c0 + i > hi || c0 + i < lo) ? -INFINITY : t;
+    mx = fmaxf(mx, t);
+  }
+  return mx;
+}
+
+// f[i] = 2^(s*scale_log2 - msub) (0 where masked); returns the chunk's sum
+template <bool MASK>
+__device__ __forceinline__ float chunk_exp(const uint32_t (&v)[32], float (&f)[32], float scale_log2, float msub, int c0,
+                                           int lo, int hi) {
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < 32; ++i) {
+    float pe = ex2_approx(fmaf(__uint_as_float(v[i]), scale_log2, -msub));
+    if (MASK) pe = (c0 + i > hi || c0 + i < lo) ? 0.f : pe;
+    f[i] = pe;
+    sum += pe;
+  }
+  return sum;
+}
+
+// backward: P = 2^(s*scale_log2 - lse2), dS = P * (dP*scale - delta*scale)
+template <bool MASK>
+__device__ __forceinline__ void chunk_p_ds(const uint32_t (&vs)[32], const uint32_t (&vd)[32], float (&fp)[32], float (&fd)[32],
+                                           float scale_log2, float lse2, float scale, float delta_s, int c0, int lo, int hi) {
+#pragma unroll
+  for (int i = 0; i < 32; ++i) {
+    float pe = ex2_approx(fmaf(__uint_as_float(vs[i]), scale_log2, -lse2));
+    if (MASK) pe = (c0 + i > hi || c0 + i < lo) ? 0.f : pe;
+    fp[i] = pe;
+    fd[i] = pe * fmaf(__uint_as_float(vd[i]), scale, -delta_s);
+  }
+}
+
 // write 32 consecutive bf16 columns [c*32, c*32+32) of row r into a [128][128] tile stored as two
 // [128 rows][64 cols] 128B-swizzled blocks
 __device__ __forceinline__ void store_row_chunk_sw128(uint8_t* tile, int r, int c, const float (&f)[32]) {
@@ -192,21 +246,18 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__
                              (p.window > 0 && q0 + ATT_TILE - 1 - kbase >= p.window);
       mbar_wait(s_full, jj & 1);
       tc_fence_after();
-      // pass 1: row maximum
+      int lo, hi;
+      row_window(qpos, kbase, p.S, p.causal, p.window, lo, hi);
+      // pass 1: row maximum of the raw scores (scale > 0, so the order is preserved)
       float mx = -INFINITY;
 #pragma unroll 1
       for (int c = 0; c < 4; ++c) {
         uint32_t v[32];
         tmem_ld32(tmem_S + lane_base + c * 32, v);
         tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          float t = __uint_as_float(v[i]) * p.scale_log2;
-          if (need_mask && is_masked(qpos, kbase + c * 32 + i, p.S, p.causal, p.window)) t = -INFINITY;
-          mx = fmaxf(mx, t);
-        }
+        mx = fmaxf(mx, need_mask ? chunk_max<true>(v, c * 32, lo, hi) : chunk_max<false>(v, c * 32, lo, hi));
       }
-      const float m_new = fmaxf(m_used, mx);
+      const float m_new = fmaxf(m_used, mx * p.scale_log2);
       float alpha = 1.f;
       if (jj == 0) {
         m_used = m_new;
@@ -216,7 +267,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__
         const bool want = m_new > m_used + 8.f;   // lazy rescale: only when the max moved by > 2^8
         if (__any_sync(0xffffffffu, want)) {
           if (want) {
-            alpha = (m_used == -INFINITY) ? 0.f : exp2f(m_used - m_new);
+            alpha = (m_used == -INFINITY) ? 0.f : ex2_approx(m_used - m_new);
             m_used = m_new;
           }
 #pragma unroll 1
@@ -240,13 +291,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__
         float f[32];
         tmem_ld32(tmem_S + lane_base + c * 32, v);
         tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          float pe = exp2f(__uint_as_float(v[i]) * p.scale_log2 - msub);
-          if (need_mask && is_masked(qpos, kbase + c * 32 + i, p.S, p.causal, p.window)) pe = 0.f;
-          f[i] = pe;
-          lsum += pe;
-        }
+        lsum += need_mask ? chunk_exp<true>(v, f, p.scale_log2, msub, c * 32, lo, hi)
+                          : chunk_exp<false>(v, f, p.scale_log2, msub, c * 32, lo, hi);
         store_row_chunk_sw128(sP, r, c, f);
       }
       l = l * alpha + lsum;
@@ -377,10 +423,16 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__
         delta = p.delta[(int64_t(b) * p.H + h) * p.S + qpos];
       }
       const bool row_ok = valid && lse2 != -INFINITY;
+      if (!row_ok) lse2 = 0.f;
       const bool need_mask = (p.causal && k0 + ATT_TILE - 1 > i * ATT_TILE) || (k0 + ATT_TILE > p.S) ||
                              (p.window > 0 && i * ATT_TILE + ATT_TILE - 1 - k0 >= p.window);
       mbar_wait(s_full, it & 1);
       tc_fence_after();
+      int lo, hi;
+      row_window(qpos, k0, p.S, p.causal, p.window, lo, hi);
+      if (!row_ok) { lo = 1; hi = 0; }  // padded / fully masked query row: everything is masked
+      const bool mask_tile = need_mask || !__all_sync(0xffffffffu, row_ok);
+      const float delta_s = delta * p.scale;
 #pragma unroll 1
       for (int c = 0; c < 4; ++c) {
         uint32_t vs[32], vd[32];
@@ -388,14 +440,10 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__
         tmem_ld32(tmem_S + lane_base + c * 32, vs);
         tmem_ld32(tmem_dP + lane_base + c * 32, vd);
         tmem_ld_wait();
-#pragma unroll
-        for (int x = 0; x < 32; ++x) {
-          float pe = 0.f;
-          if (row_ok && !(need_mask && is_masked(qpos, k0 + c * 32 + x, p.S, p.causal, p.window)))
-            pe = exp2f(__uint_as_float(vs[x]) * p.scale_log2 - lse2);
-          fp[x] = pe;
-          fd[x] = pe * (__uint_as_float(vd[x]) - delta) * p.scale;
-        }
+        if (mask_tile)
+          chunk_p_ds<true>(vs, vd, fp, fd, p.scale_log2, lse2, p.scale, delta_s, c * 32, lo, hi);
+        else
+          chunk_p_ds<false>(vs, vd, fp, fd, p.scale_log2, lse2, p.scale, delta_s, c * 32, lo, hi);
         store_row_chunk_sw128(sP, r, c, fp);
         store_row_chunk_sw128(sdS, r, c, fd);
       }
