@@ -118,9 +118,10 @@ int lrp_rope_inplace(void* qk, int64_t ld, int n_heads_total, int D, const float
  * (lxt/efficient/patches.py:145-157 `gated_mlp_forward`, lxt/efficient/rules.py:69-127).
  *   fwd: a = act(gate) * up                          gu = [T, 2I] bf16 (gate | up), a = [T, I] bf16
  *   bwd: g_up = (g_a/2) * act(gate);  g_gate = (g_a/2) * up * act(gate)/(gate + 1e-10)
- *        (fp32 arithmetic on the bf16 inputs, one rounding per output) */
+ *        (fp32 arithmetic on the bf16 inputs, one rounding per output)
+ *   cp_variant = 1 is CP-LRP (`cp_gated_mlp_forward`, patches.py:272-280): g_gate = 0, g_up = g_a * act(gate). */
 int lrp_gated_act_fwd(const void* gu, void* a, int T, int I, int act, void* stream);
-int lrp_gated_act_bwd(const void* ga, const void* gu, void* ggu, int T, int I, int act, void* stream);
+int lrp_gated_act_bwd(const void* ga, const void* gu, void* ggu, int T, int I, int act, int cp_variant, void* stream);
 
 /* Identity rule on a plain element-wise non-linearity (lxt/efficient/rules.py:88-100,
  * lxt/efficient/patches.py:159-169 `mlp_forward`, :206-211 `non_linear_forward`):

@@ -257,7 +257,8 @@ __global__ void __launch_bounds__(256) gated_act_fwd_kernel(const __nv_bfloat16*
 // fp32 arithmetic on the bf16 inputs, one rounding on each output.
 __global__ void __launch_bounds__(256) gated_act_bwd_kernel(const __nv_bfloat16* __restrict__ ga,
                                                             const __nv_bfloat16* __restrict__ gu,
-                                                            __nv_bfloat16* __restrict__ ggu, int64_t T, int I, int act) {
+                                                            __nv_bfloat16* __restrict__ ggu, int64_t T, int I, int act,
+                                                            int cp_variant) {
   const int chunks = I >> 3;
   const int64_t total = T * chunks;
   for (int64_t idx = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; idx < total;
@@ -271,9 +272,14 @@ __global__ void __launch_bounds__(256) gated_act_bwd_kernel(const __nv_bfloat16*
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const float s = act_eval(g[j], act);
-      const float gh = d[j] * 0.5f;
-      ou[j] = gh * s;
-      og[j] = (s / (g[j] + 1e-10f)) * (gh * u[j]);
+      if (cp_variant) {  // CP-LRP (patches.py:272-280): gate detached, no uniform split
+        ou[j] = d[j] * s;
+        og[j] = 0.f;
+      } else {
+        const float gh = d[j] * 0.5f;
+        ou[j] = gh * s;
+        og[j] = (s / (g[j] + 1e-10f)) * (gh * u[j]);
+      }
     }
     store8(ggu + t * 2 * I + c, og);
     store8(ggu + t * 2 * I + I + c, ou);
@@ -532,12 +538,12 @@ int lrp_gated_act_fwd(const void* gu, void* a, int T, int I, int act, void* stre
   return LRP_OK;
 }
 
-int lrp_gated_act_bwd(const void* ga, const void* gu, void* ggu, int T, int I, int act, void* stream) {
+int lrp_gated_act_bwd(const void* ga, const void* gu, void* ggu, int T, int I, int act, int cp_variant, void* stream) {
   if (T <= 0 || I <= 0 || (I % 8) != 0) return set_error(LRP_ERR_ARG, "gated_act_bwd: I must be a positive multiple of 8");
   if (act < 0 || act > 2) return set_error(LRP_ERR_ARG, "gated_act_bwd: unknown activation");
   const int64_t total = int64_t(T) * (I / 8);
   gated_act_bwd_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>((const bf16*)ga, (const bf16*)gu,
-                                                                                          (bf16*)ggu, T, I, act);
+                                                                                          (bf16*)ggu, T, I, act, cp_variant);
   LRP_CHECK_LAUNCH();
   return LRP_OK;
 }

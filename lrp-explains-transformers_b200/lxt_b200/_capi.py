@@ -53,7 +53,7 @@ SIGNATURES = {
     "lrp_layernorm_bwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
     "lrp_rope_inplace": (_i, [_vp, _i64, _i, _i, _vp, _vp, _i, _i, _i, _vp]),
     "lrp_gated_act_fwd": (_i, [_vp, _vp, _i, _i, _i, _vp]),
-    "lrp_gated_act_bwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp]),
+    "lrp_gated_act_bwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "lrp_act_identity_fwd": (_i, [_vp, _vp, _i64, _i, _i, _vp]),
     "lrp_act_identity_bwd": (_i, [_vp, _vp, _vp, _i64, _i, _i, _vp]),
     "lrp_attn_fwd": (_i, [_vp, _vp, _vp, _i64, _i64, _i64, _vp, _vp, _i, _i, _i, _i, _i, _f, _i, _i, _vp]),

@@ -145,7 +145,7 @@ class _GatedMLPFn(Function):
     """down( divide_gradient_2( identity_rule(act)(gate(x)) * up(x) ) ) as five launches forward, five backward."""
 
     @staticmethod
-    def forward(ctx, x, wg, wu, wd, bg, bu, bd, act):
+    def forward(ctx, x, wg, wu, wd, bg, bu, bd, act, cp=False):
         _need_bf16_cuda(x, "gated_mlp_forward")
         x2 = _as_2d(x)
         T, I = x2.shape[0], wg.shape[0]
@@ -158,7 +158,7 @@ class _GatedMLPFn(Function):
         y = torch.empty((T, wd.shape[0]), dtype=torch.bfloat16, device=x.device)
         ops.linear_fwd(a, wd, y, bias=f32(bd))
         ctx.save_for_backward(gu, wg, wu, wd)
-        ctx.act = act
+        ctx.act, ctx.cp = act, cp
         return y.view(*x.shape[:-1], wd.shape[0])
 
     @staticmethod
@@ -168,12 +168,12 @@ class _GatedMLPFn(Function):
         g2 = _as_2d(gy)
         ga = torch.empty((T, I), dtype=torch.bfloat16, device=gy.device)
         ops.linear_dgrad(g2, wd, ga)
-        ggu = ops.gated_act_bwd(ga, gu, ctx.act)
+        ggu = ops.gated_act_bwd(ga, gu, ctx.act, cp=ctx.cp)
         acc = torch.empty((T, wg.shape[1]), dtype=torch.float32, device=gy.device)
         ops.linear_dgrad(ggu[:, :I], wg, acc)
         gx = torch.empty((T, wg.shape[1]), dtype=torch.bfloat16, device=gy.device)
         ops.linear_dgrad(ggu[:, I:], wu, acc, resid=acc, shadow=gx)
-        return gx.view(*gy.shape[:-1], wg.shape[1]), None, None, None, None, None, None, None
+        return gx.view(*gy.shape[:-1], wg.shape[1]), None, None, None, None, None, None, None, None
 
 
 class _FlashAttnLRPFn(Function):
@@ -359,12 +359,12 @@ def cp_multi_head_attention_forward(self, query, key, value, *args, **kwargs):
 
 
 def cp_gated_mlp_forward(self, x):
-    """CP-LRP: no relevance through the gate (reference patches.py:272-280)."""
-    gate = stop_gradient(_linear(self.gate_proj, x))
+    """CP-LRP: no relevance through the gate, no uniform split (reference patches.py:272-280)."""
     act = _act_code(self.act_fn)
-    gate = ops.act_identity_fwd(gate.contiguous(), act) if act is not None else self.act_fn(gate)
-    weighted = _MulConstFn.apply(_linear(self.up_proj, x), gate)
-    return _linear(self.down_proj, weighted)
+    if act is None:
+        raise LrpError(f"cp_gated_mlp_forward: unsupported activation {type(self.act_fn).__name__}")
+    return _GatedMLPFn.apply(x, self.gate_proj.weight, self.up_proj.weight, self.down_proj.weight, self.gate_proj.bias,
+                             self.up_proj.bias, self.down_proj.bias, act, True)
 
 
 class _MulConstFn(Function):

@@ -65,11 +65,15 @@ class _LayerStore:
 class LlamaAttnLRPEngine:
     """B200-native AttnLRP engine.  Construct with `from_weights`, `from_hf` or `random_init`."""
 
-    def __init__(self, dims: LlamaDims, device: torch.device, weights: Dict, micro_batch: int = 8, store: str = "all"):
+    def __init__(self, dims: LlamaDims, device: torch.device, weights: Dict, micro_batch: int = 8, store: str = "all",
+                 rule: str = "attnlrp"):
         if device.type != "cuda":
             raise RuntimeError("LlamaAttnLRPEngine runs on a CUDA (B200) device only; there is no CPU path")
         ops._capi.require_device()
         self.dims, self.device, self.micro_batch, self.store_policy = dims, device, micro_batch, store
+        if rule not in ("attnlrp", "cp"):
+            raise ValueError("rule must be 'attnlrp' (lxt attnLRP map) or 'cp' (lxt cp_LRP map)")
+        self.cp = rule == "cp"  # CP-LRP: q,k and the MLP gate detached (lxt/efficient/models/llama.py:16-21)
         bf = lambda t: t.to(device=device, dtype=torch.bfloat16).contiguous()
         f32 = lambda t: t.to(device=device, dtype=torch.float32).contiguous()
         self.emb = bf(weights["emb"])
@@ -208,7 +212,7 @@ class LlamaAttnLRPEngine:
         # ---- gated MLP
         ops.linear_dgrad(g_hb, lw["wd"], ws["a"])                                  # g_a [T, I]
         C.check(lib.lrp_gated_act_bwd(ws["a"].data_ptr(), st.gu.data_ptr(), ws["g_gu"].data_ptr(), T, m.I, ops.ACT_SILU,
-                                      ops._stream()), "gated_act_bwd")
+                                      int(self.cp), ops._stream()), "gated_act_bwd")
         ops.linear_dgrad(ws["g_gu"], lw["wgu"], g_h, resid=g_h, rowscale=st.rstd2, colscale=lw["ln2_f"], shadow=g_hb)
         # ---- attention
         ops.linear_dgrad(g_hb, lw["wo"], ws["g_o"])                                # g_o [T, H D]
@@ -217,7 +221,8 @@ class LlamaAttnLRPEngine:
         C.check(lib.lrp_attn_bwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), m.qkv_width, m.qkv_width, m.qkv_width,
                                  st.o.data_ptr(), ws["g_o"].data_ptr(), st.lse.data_ptr(), dq.data_ptr(), dk.data_ptr(),
                                  dv.data_ptr(), m.qkv_width, m.qkv_width, m.qkv_width, ws["dq_acc"].data_ptr(),
-                                 ws["delta"].data_ptr(), B, S, m.H, m.Hkv, m.D, scale, 1, 0, 4.0, 4.0, 2.0, ops._stream()),
+                                 ws["delta"].data_ptr(), B, S, m.H, m.Hkv, m.D, scale, 1, 0, *((0.0, 0.0, 1.0) if self.cp else (4.0, 4.0, 2.0)),
+                                 ops._stream()),
                 "attn_bwd")
         ops.rope_inplace(ws["g_qkv"], m.H + m.Hkv, m.D, cos, sin, S, inverse=True)
         ops.linear_dgrad(ws["g_qkv"], lw["wqkv"], g_h, resid=g_h, rowscale=st.rstd1, colscale=lw["ln1_f"], shadow=g_hb)

@@ -181,7 +181,7 @@ def gated_act_fwd(gu: torch.Tensor, act: int = ACT_SILU) -> torch.Tensor:
     return a
 
 
-def gated_act_bwd(ga: torch.Tensor, gu: torch.Tensor, act: int = ACT_SILU, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+def gated_act_bwd(ga: torch.Tensor, gu: torch.Tensor, act: int = ACT_SILU, out: Optional[torch.Tensor] = None, cp: bool = False) -> torch.Tensor:
     _need(ga, torch.bfloat16, "ga")
     _need(gu, torch.bfloat16, "gu")
     T, I2 = gu.shape
@@ -189,7 +189,7 @@ def gated_act_bwd(ga: torch.Tensor, gu: torch.Tensor, act: int = ACT_SILU, out: 
         raise _capi.LrpError("gated_act_bwd: inputs must be contiguous")
     if out is None:
         out = torch.empty_like(gu)
-    check(_capi.lib().lrp_gated_act_bwd(ga.data_ptr(), gu.data_ptr(), out.data_ptr(), T, I2 // 2, act, _stream()),
+    check(_capi.lib().lrp_gated_act_bwd(ga.data_ptr(), gu.data_ptr(), out.data_ptr(), T, I2 // 2, act, int(cp), _stream()),
           "lrp_gated_act_bwd")
     return out
 

@@ -140,12 +140,16 @@ def _rmsnorm_bwd(g, w, rstd):
     return ((g * w).to(torch.float32) * rstd).to(dt)
 
 
-def llama_attnlrp(weights: Dict, ids: torch.Tensor, cfg: Dict, dtype=torch.float32, return_aux: bool = False):
+def llama_attnlrp(weights: Dict, ids: torch.Tensor, cfg: Dict, dtype=torch.float32, return_aux: bool = False,
+                  rule: str = "attnlrp"):
     """One AttnLRP attribution per prompt, entirely with explicit formulas (no autograd).
 
     weights: {'emb','norm','lm_head', 'layers':[{'wq','wk','wv','wo','wg','wu','wd','ln1','ln2'}]} (any float dtype)
     ids: int64 [B,S].  cfg: d, H, Hkv, D, eps, theta.  Returns relevance fp32 [B,S] (and aux dict).
+    rule="cp" restates the CP-LRP map (lxt/efficient/models/llama.py:16-21; patches.py:228-280): q,k detached
+    before attention, MLP gate detached and no uniform split on the product.
     """
+    cp = rule == "cp"
     H, Hkv, D, eps = cfg["H"], cfg["Hkv"], cfg["D"], cfg["eps"]
     G = H // Hkv
     B, S = ids.shape
@@ -189,11 +193,14 @@ def llama_attnlrp(weights: Dict, ids: torch.Tensor, cfg: Dict, dtype=torch.float
     g_h[:, -1, :] = _rmsnorm_bwd(g_hN_last, W(weights["norm"]), rstdN[:, -1, :])
     for lw, st in zip(reversed(weights["layers"]), reversed(stash)):
         # gated MLP: uniform rule on the product, identity rule on SiLU (patches.py:145-157, rules.py:88-127)
-        g_a = divide_gradient_grad(g_h @ W(lw["wd"]), 2)
-        g_s = g_a * st["up"]
-        g_up = g_a * st["s"]
-        g_gate = identity_rule_implicit_grad(st["s"], st["gate"], g_s)
-        g_xn2 = g_gate @ W(lw["wg"]) + g_up @ W(lw["wu"])
+        if cp:
+            g_xn2 = ((g_h @ W(lw["wd"])) * st["s"]) @ W(lw["wu"])
+        else:
+            g_a = divide_gradient_grad(g_h @ W(lw["wd"]), 2)
+            g_s = g_a * st["up"]
+            g_up = g_a * st["s"]
+            g_gate = identity_rule_implicit_grad(st["s"], st["gate"], g_s)
+            g_xn2 = g_gate @ W(lw["wg"]) + g_up @ W(lw["wu"])
         g_h = g_h + _rmsnorm_bwd(g_xn2, W(lw["ln2"]), st["rstd2"])
         # attention: ordinary softmax-attention backward, then dQ/4, dK/4, dV/2 (patches.py:193-203)
         g_o = (g_h @ W(lw["wo"])).view(B, S, H, D).transpose(1, 2)
@@ -206,7 +213,7 @@ def llama_attnlrp(weights: Dict, ids: torch.Tensor, cfg: Dict, dtype=torch.float
         dK = dS.transpose(-1, -2) @ q
         dK = dK.view(B, Hkv, G, S, D).sum(2)
         dV = dV.view(B, Hkv, G, S, D).sum(2)
-        dQ, dK, dV = dQ / 4, dK / 4, dV / 2
+        dQ, dK, dV = (dQ * 0, dK * 0, dV) if cp else (dQ / 4, dK / 4, dV / 2)
         dQ = dQ * cos + _rotate_half_T(dQ * sin)
         dK = dK * cos + _rotate_half_T(dK * sin)
         g_xn = (dQ.transpose(1, 2).reshape(B, S, H * D) @ W(lw["wq"])

@@ -177,8 +177,71 @@ def gen_llama(name, cfg, B, S, seed):
     np.savez_compressed(os.path.join(HERE, f"{name}.npz"), **save)
 
 
+def gen_vit():
+    """torchvision ViT, lxt.efficient.monkey_patch(vision_transformer) (cp_LRP map), examples/vit_torch.py:84-91."""
+    from torchvision.models import vision_transformer
+    monkey_patch(vision_transformer, verbose=True)
+    torch.manual_seed(5)
+    model = vision_transformer.VisionTransformer(image_size=64, patch_size=16, num_layers=2, num_heads=2, hidden_dim=128,
+                                                 mlp_dim=256, num_classes=16).eval()
+    torch.nn.init.normal_(model.heads.head.weight, std=0.02)  # torchvision zero-fills the head (all-zero relevance)
+    for p_ in model.parameters():
+        p_.requires_grad_(False)
+    x = torch.randn(2, 3, 64, 64, generator=torch.Generator().manual_seed(6)).requires_grad_()
+    y = model(x)
+    cls = y.argmax(-1)
+    y[torch.arange(2), cls].sum().backward()
+    heat = (x * x.grad).sum(1)
+    save = {"x": x.detach().numpy(), "heat": heat.detach().numpy(), "cls": cls.numpy(), "logits": y.detach().numpy()}
+    for k, v in model.state_dict().items():
+        save["sd_" + k] = v.numpy()
+    np.savez_compressed(os.path.join(HERE, "vit_tiny.npz"), **save)
+    print("vit_tiny.npz heat norm", float(heat.norm()))
+
+
+def gen_llama_cp():
+    """CP-LRP variant (lxt/efficient/models/llama.py:16-21) — run in a fresh process: patches are process-global."""
+    from lxt.efficient.models.llama import cp_LRP
+    monkey_patch(modeling_llama, cp_LRP, verbose=True)
+    cfg = dict(d=256, I=512, H=4, Hkv=2, D=64, L=2, V=256, eps=1e-5, theta=10000.0)
+    w = random_llama_weights(cfg, seed=0, std=0.02, dtype=torch.bfloat16)
+    ids = torch.randint(0, cfg["V"], (2, 160), generator=torch.Generator().manual_seed(1))
+    hf_cfg = LlamaConfig(hidden_size=cfg["d"], intermediate_size=cfg["I"], num_hidden_layers=cfg["L"],
+                         num_attention_heads=cfg["H"], num_key_value_heads=cfg["Hkv"], head_dim=cfg["D"],
+                         vocab_size=cfg["V"], rms_norm_eps=cfg["eps"],
+                         rope_parameters={"rope_type": "default", "rope_theta": cfg["theta"]},
+                         max_position_embeddings=512, attention_bias=False, tie_word_embeddings=False)
+    hf_cfg._attn_implementation = "sdpa"
+    model = LlamaForCausalLM(hf_cfg).float().eval()
+    sd = {"model.embed_tokens.weight": w["emb"], "model.norm.weight": w["norm"], "lm_head.weight": w["lm_head"]}
+    for i, lw in enumerate(w["layers"]):
+        p = f"model.layers.{i}."
+        sd.update({p + "self_attn.q_proj.weight": lw["wq"], p + "self_attn.k_proj.weight": lw["wk"],
+                   p + "self_attn.v_proj.weight": lw["wv"], p + "self_attn.o_proj.weight": lw["wo"],
+                   p + "mlp.gate_proj.weight": lw["wg"], p + "mlp.up_proj.weight": lw["wu"],
+                   p + "mlp.down_proj.weight": lw["wd"], p + "input_layernorm.weight": lw["ln1"],
+                   p + "post_attention_layernorm.weight": lw["ln2"]})
+    model.load_state_dict({k: v.float() for k, v in sd.items()}, strict=True)
+    for p_ in model.parameters():
+        p_.requires_grad_(False)
+    emb = model.get_input_embeddings()(ids).detach().requires_grad_()
+    logits = model(inputs_embeds=emb, use_cache=False).logits
+    max_logits, max_idx = torch.max(logits[:, -1, :], dim=-1)
+    max_logits.sum().backward()
+    rel = (emb * emb.grad).float().sum(-1)
+    np.savez_compressed(os.path.join(HERE, "llama_tiny_cp.npz"), ids=ids.numpy(), rel_fp32=rel.detach().numpy(),
+                        idx=max_idx.numpy(), seed=np.array([0]))
+    print("llama_tiny_cp.npz rel norm", float(rel.norm()))
+
+
 if __name__ == "__main__":
     torch.manual_seed(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "--cp":
+        gen_llama_cp()
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "--vit":
+        gen_vit()
+        sys.exit(0)
     gen_rules()
     gen_llama("llama_tiny_d64", dict(d=256, I=512, H=4, Hkv=2, D=64, L=2, V=256, eps=1e-5, theta=10000.0), B=2, S=160, seed=0)
     gen_llama("llama_tiny_d128", dict(d=256, I=384, H=2, Hkv=1, D=128, L=2, V=320, eps=1e-5, theta=500000.0), B=1, S=130, seed=7)

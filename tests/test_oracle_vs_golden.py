@@ -72,3 +72,13 @@ def test_llama_attnlrp_bf16_close_to_reference_bf16(name):
     # two bf16 runs differ by rounding order (the reference's own bf16-vs-fp32 gap is ~2e-3 here); the
     # bf16 mode of the oracle is informational (CPU baseline timing), the fp32 mode above is the pin.
     assert rel_l2(rel, z["rel_fp32_sdpa"]) < 2e-2
+
+
+def test_llama_cp_lrp_matches_reference():
+    """CP-LRP map of the reference (lxt/efficient/models/llama.py:16-21), golden from a separate reference process."""
+    z = load_npz("llama_tiny_cp.npz")
+    cfg = dict(d=256, I=512, H=4, Hkv=2, D=64, L=2, V=256, eps=1e-5, theta=10000.0)
+    w = O.random_llama_weights(cfg, seed=0)
+    rel, aux = O.llama_attnlrp(w, T(z["ids"]), cfg, dtype=torch.float32, return_aux=True, rule="cp")
+    assert np.array_equal(aux["idx"].numpy(), z["idx"])
+    assert rel_l2(rel, z["rel_fp32"]) < 1e-4

@@ -1,0 +1,35 @@
+"""GPU: BASELINE configs[3] — torchvision ViT pixel relevance through `lxt_b200.efficient.monkey_patch` (the cp_LRP
+map of lxt/efficient/models/vit_torch.py:7-11), same user code as examples/vit_torch.py:84-91, against the golden
+heat-map of the real reference.  fp32 model: LayerNorm / GELU rules run in the fp32 kernels."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import load_npz, rel_l2
+
+pytestmark = pytest.mark.gpu
+
+
+def test_vit_pixel_relevance_matches_reference():
+    from torchvision.models import vision_transformer
+    from lxt_b200.efficient import monkey_patch
+    from lxt_b200 import ops
+    z = load_npz("vit_tiny.npz")
+    monkey_patch(vision_transformer, verbose=True)
+    model = vision_transformer.VisionTransformer(image_size=64, patch_size=16, num_layers=2, num_heads=2, hidden_dim=128,
+                                                 mlp_dim=256, num_classes=16)
+    model.load_state_dict({k[3:]: torch.from_numpy(v) for k, v in z.items() if k.startswith("sd_")})
+    model = model.cuda().eval()
+    for p in model.parameters():
+        p.requires_grad_(False)
+    n0 = ops.launch_count()
+    x = torch.from_numpy(z["x"]).cuda().requires_grad_()
+    y = model(x)
+    cls = y.argmax(-1)
+    assert np.array_equal(cls.cpu().numpy(), z["cls"])
+    y[torch.arange(2), cls].sum().backward()
+    heat = (x * x.grad).sum(1).detach().cpu()
+    assert ops.launch_count() - n0 >= 2 * (2 * 2 + 1 + 2), "LayerNorm / GELU rule kernels did not run"
+    err = rel_l2(heat, z["heat"])
+    print(f"ViT heat-map rel-L2 vs reference = {err:.3e}")
+    assert err < 1e-3
