@@ -117,22 +117,27 @@ __device__ __forceinline__ void store_row_chunk_sw128(uint8_t* tile, int r, int 
 
 // ---- UMMA issue helpers (single thread) -------------------------------------------------------
 // C[128 x N] (+)= A_kmajor[128 x K] * B_kmajor[N x K]^T, K = KB*64, tiles as [rows][64]-blocks of 16 KiB
+//   a_blk / b_blk = byte distance between consecutive 64-column blocks of the A / B tile (= rows * 128 B)
 template <int N>
-__device__ __forceinline__ void mma_kk(uint32_t tmem_d, uint32_t a_base, uint32_t b_base, int ktot, bool acc_first) {
+__device__ __forceinline__ void mma_kk(uint32_t tmem_d, uint32_t a_base, uint32_t b_base, int ktot, bool acc_first,
+                                       uint32_t a_blk = 16384, uint32_t b_blk = 16384) {
   constexpr uint32_t idesc = make_idesc_bf16(128, N, 0, 0);
   for (int kk = 0; kk < ktot / 16; ++kk) {
-    const uint32_t off = (kk >> 2) * 16384 + (kk & 3) * 32;
-    tc_mma_ss(tmem_d, make_sdesc_sw128(a_base + off, 16, 1024), make_sdesc_sw128(b_base + off, 16, 1024), idesc,
+    const uint32_t aoff = (kk >> 2) * a_blk + (kk & 3) * 32;
+    const uint32_t boff = (kk >> 2) * b_blk + (kk & 3) * 32;
+    tc_mma_ss(tmem_d, make_sdesc_sw128(a_base + aoff, 16, 1024), make_sdesc_sw128(b_base + boff, 16, 1024), idesc,
               (acc_first || kk > 0) ? 1u : 0u);
   }
 }
 // C[128 x N] (+)= A_kmajor[128 x 128] * B_mnmajor[128(k) x N]
+//   ktot = contraction length (rows of B); b_lbo = byte distance between 64-column blocks of B (= ktot * 128 B)
 template <int N>
-__device__ __forceinline__ void mma_kmn(uint32_t tmem_d, uint32_t a_base, uint32_t b_base, bool acc_first) {
+__device__ __forceinline__ void mma_kmn(uint32_t tmem_d, uint32_t a_base, uint32_t b_base, bool acc_first, int ktot = 128,
+                                        uint32_t b_lbo = 16384) {
   constexpr uint32_t idesc = make_idesc_bf16(128, N, 0, 1);
-  for (int kk = 0; kk < 8; ++kk) {
+  for (int kk = 0; kk < ktot / 16; ++kk) {
     const uint32_t aoff = (kk >> 2) * 16384 + (kk & 3) * 32;
-    tc_mma_ss(tmem_d, make_sdesc_sw128(a_base + aoff, 16, 1024), make_sdesc_sw128(b_base + kk * 2048, 16384, 1024),
+    tc_mma_ss(tmem_d, make_sdesc_sw128(a_base + aoff, 16, 1024), make_sdesc_sw128(b_base + kk * 2048, b_lbo, 1024),
               idesc, (acc_first || kk > 0) ? 1u : 0u);
   }
 }
@@ -146,27 +151,30 @@ __device__ __forceinline__ void mma_mnmn(uint32_t tmem_d, uint32_t a_base, uint3
   }
 }
 
-template <int D>
+template <int D, int ROWS = 128>
 __device__ __forceinline__ void load_tile(uint8_t* dst, const CUtensorMap* tm, uint64_t* bar, int col0, int row0, int b) {
 #pragma unroll
-  for (int kb = 0; kb < D / 64; ++kb) tma_load_3d(dst + kb * 16384, tm, bar, col0 + kb * 64, row0, b);
+  for (int kb = 0; kb < D / 64; ++kb) tma_load_3d(dst + kb * (ROWS * 128), tm, bar, col0 + kb * 64, row0, b);
 }
 
 // =================================================================================================
 // forward
 // =================================================================================================
-template <int D>
-__global__ void __launch_bounds__(ATT_THREADS, 1)
+template <int D, int BN>
+__global__ void __launch_bounds__(ATT_THREADS, 2)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__ CUtensorMap tmk,
                 const __grid_constant__ CUtensorMap tmv, const AttnParams p) {
-  constexpr int TILE_BYTES = ATT_TILE * D * 2;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // Two CTAs are resident per SM (<= 113 KiB smem, 256 TMEM columns each): while one CTA's soft-max warps work,
+  // the other CTA's S / P.V MMAs occupy the tensor pipe.
+  constexpr int Q_BYTES = ATT_TILE * D * 2;
+  constexpr int KV_BYTES = BN * D * 2;
+  constexpr int P_BYTES = ATT_TILE * BN * 2;
+  extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sQ = smem;
-  uint8_t* sK = sQ + TILE_BYTES;       // 2 stages
-  uint8_t* sV = sK + 2 * TILE_BYTES;   // 2 stages
-  uint8_t* sP = sV + 2 * TILE_BYTES;   // 32 KiB
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 32768);
+  uint8_t* sK = sQ + Q_BYTES;        // 2 stages
+  uint8_t* sV = sK + 2 * KV_BYTES;   // 2 stages
+  uint8_t* sP = sV + 2 * KV_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + P_BYTES);
   uint64_t* q_full = bars;
   uint64_t* k_full = bars + 1;    // [2]
   uint64_t* v_full = bars + 3;    // [2]
@@ -181,9 +189,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__
   const int h = blockIdx.y, b = blockIdx.z;
   const int hk = h / (p.H / p.Hkv);
   const int q0 = qt * ATT_TILE;
-  const int nkv = (p.S + ATT_TILE - 1) / ATT_TILE;
-  const int j_hi = p.causal ? min(qt, nkv - 1) : nkv - 1;
-  const int j_lo = p.window > 0 ? max(0, q0 - p.window + 1) / ATT_TILE : 0;
+  const int nkv = (p.S + BN - 1) / BN;
+  const int j_hi = p.causal ? min((q0 + ATT_TILE - 1) / BN, nkv - 1) : nkv - 1;
+  const int j_lo = p.window > 0 ? max(0, q0 - p.window + 1) / BN : 0;
   const int n = j_hi - j_lo + 1;
 
   if (warp == 4 && lane == 0) {
@@ -204,31 +212,31 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__
 
   if (warp == 4) {
     if (lane == 0) {
-      mbar_expect_tx(q_full, TILE_BYTES);
+      mbar_expect_tx(q_full, Q_BYTES);
       load_tile<D>(sQ, &tmq, q_full, h * D, q0, b);
-      mbar_expect_tx(&k_full[0], TILE_BYTES);
-      load_tile<D>(sK, &tmk, &k_full[0], hk * D, j_lo * ATT_TILE, b);
-      mbar_expect_tx(&v_full[0], TILE_BYTES);
-      load_tile<D>(sV, &tmv, &v_full[0], hk * D, j_lo * ATT_TILE, b);
+      mbar_expect_tx(&k_full[0], KV_BYTES);
+      load_tile<D, BN>(sK, &tmk, &k_full[0], hk * D, j_lo * BN, b);
+      mbar_expect_tx(&v_full[0], KV_BYTES);
+      load_tile<D, BN>(sV, &tmv, &v_full[0], hk * D, j_lo * BN, b);
       for (int jj = 0; jj < n; ++jj) {
         const int st = jj & 1;
         if (jj + 1 < n) {
           const int ns = st ^ 1;
           if (jj >= 1) mbar_wait(&kv_empty[ns], ((jj - 1) >> 1) & 1);
-          mbar_expect_tx(&k_full[ns], TILE_BYTES);
-          load_tile<D>(sK + ns * TILE_BYTES, &tmk, &k_full[ns], hk * D, (j_lo + jj + 1) * ATT_TILE, b);
-          mbar_expect_tx(&v_full[ns], TILE_BYTES);
-          load_tile<D>(sV + ns * TILE_BYTES, &tmv, &v_full[ns], hk * D, (j_lo + jj + 1) * ATT_TILE, b);
+          mbar_expect_tx(&k_full[ns], KV_BYTES);
+          load_tile<D, BN>(sK + ns * KV_BYTES, &tmk, &k_full[ns], hk * D, (j_lo + jj + 1) * BN, b);
+          mbar_expect_tx(&v_full[ns], KV_BYTES);
+          load_tile<D, BN>(sV + ns * KV_BYTES, &tmv, &v_full[ns], hk * D, (j_lo + jj + 1) * BN, b);
         }
         if (jj == 0) mbar_wait(q_full, 0);
         mbar_wait(&k_full[st], (jj >> 1) & 1);
         tc_fence_after();
-        mma_kk<128>(tmem_S, smem_u32(sQ), smem_u32(sK + st * TILE_BYTES), D, false);
+        mma_kk<BN>(tmem_S, smem_u32(sQ), smem_u32(sK + st * KV_BYTES), D, false, 16384, BN * 128);   // S = Q K^T
         tc_commit(s_full);
         mbar_wait(p_full, jj & 1);
         mbar_wait(&v_full[st], (jj >> 1) & 1);
         tc_fence_after();
-        mma_kmn<D>(tmem_O, smem_u32(sP), smem_u32(sV + st * TILE_BYTES), jj > 0);
+        mma_kmn<D>(tmem_O, smem_u32(sP), smem_u32(sV + st * KV_BYTES), jj > 0, BN, BN * 128);        // O += P V
         tc_commit(&kv_empty[st]);
         tc_commit(o_full);
       }
@@ -241,8 +249,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__
     float m_used = -INFINITY, l = 0.f;
     for (int jj = 0; jj < n; ++jj) {
       const int j = j_lo + jj;
-      const int kbase = j * ATT_TILE;
-      const bool need_mask = (p.causal && kbase + ATT_TILE - 1 > q0) || (kbase + ATT_TILE > p.S) ||
+      const int kbase = j * BN;
+      const bool need_mask = (p.causal && kbase + BN - 1 > q0) || (kbase + BN > p.S) ||
                              (p.window > 0 && q0 + ATT_TILE - 1 - kbase >= p.window);
       mbar_wait(s_full, jj & 1);
       tc_fence_after();
@@ -251,7 +259,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__
       // pass 1: row maximum of the raw scores (scale > 0, so the order is preserved)
       float mx = -INFINITY;
 #pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
+      for (int c = 0; c < BN / 32; ++c) {
         uint32_t v[32];
         tmem_ld32(tmem_S + lane_base + c * 32, v);
         tmem_ld_wait();
@@ -286,7 +294,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__
       float lsum = 0.f;
       const float msub = (m_used == -INFINITY) ? 0.f : m_used;
 #pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
+      for (int c = 0; c < BN / 32; ++c) {
         uint32_t v[32];
         float f[32];
         tmem_ld32(tmem_S + lane_base + c * 32, v);
@@ -458,7 +466,11 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__
         uint32_t v[32];
         tmem_ld32(tmem_S + lane_base + c * 32, v);
         tmem_ld_wait();
+#ifndef LRP_EXPERIMENT_NO_DQ_ATOMICS
         if (valid) {
+#else
+        if (valid && __uint_as_float(v[0]) == 123456.789f) {
+#endif
 #pragma unroll
           for (int q = 0; q < 8; ++q)
             red_add_v4(dqrow + c * 32 + q * 4, __uint_as_float(v[q * 4]), __uint_as_float(v[q * 4 + 1]),
@@ -547,8 +559,8 @@ __global__ void __launch_bounds__(256) attn_dq_finish_kernel(const float* __rest
   }
 }
 
-template <int D>
-static int fwd_smem_bytes() { return 5 * ATT_TILE * D * 2 + 32768 + 1024 + 256; }
+template <int D, int BN>
+static int fwd_smem_bytes() { return ATT_TILE * D * 2 + 4 * BN * D * 2 + ATT_TILE * BN * 2 + 128; }
 template <int D>
 static int bwd_smem_bytes() { return 4 * ATT_TILE * D * 2 + 65536 + 1024 + 256; }
 
@@ -563,18 +575,18 @@ static int check_common(const void* q, const void* k, const void* v, int64_t ldq
   return LRP_OK;
 }
 
-template <int D>
+template <int D, int BN>
 static int launch_fwd(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnParams& p,
                       cudaStream_t st) {
-  auto kern = attn_fwd_kernel<D>;
+  auto kern = attn_fwd_kernel<D, BN>;
   static bool done = false;
   if (!done) {
-    cudaError_t ce = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, fwd_smem_bytes<D>());
+    cudaError_t ce = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, fwd_smem_bytes<D, BN>());
     if (ce != cudaSuccess) return set_error(LRP_ERR_CUDA, cudaGetErrorString(ce));
     done = true;
   }
   dim3 grid((p.S + ATT_TILE - 1) / ATT_TILE, p.H, p.B);
-  kern<<<grid, ATT_THREADS, fwd_smem_bytes<D>(), st>>>(tq, tk, tv, p);
+  kern<<<grid, ATT_THREADS, fwd_smem_bytes<D, BN>(), st>>>(tq, tk, tv, p);
   LRP_CHECK_LAUNCH();
   return LRP_OK;
 }
@@ -605,10 +617,12 @@ int lrp_attn_fwd(const void* q, const void* k, const void* v, int64_t ldq, int64
                  int B, int S, int H, int Hkv, int D, float scale, int causal, int window, void* stream) {
   if (int e = check_common(q, k, v, ldq, ldk, ldv, B, S, H, Hkv, D)) return e;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  // key tile: 64 keys for D=128, 128 keys for D=64 -> 112 KiB of smem per CTA either way (2 CTAs per SM)
+  const int BN = D == 128 ? 64 : 128;
   CUtensorMap tq, tk, tv;
   if (int e = make_tmap_3d_bf16(&tq, q, uint64_t(H) * D, S, B, ldq, uint64_t(S) * ldq, 64, ATT_TILE)) return e;
-  if (int e = make_tmap_3d_bf16(&tk, k, uint64_t(Hkv) * D, S, B, ldk, uint64_t(S) * ldk, 64, ATT_TILE)) return e;
-  if (int e = make_tmap_3d_bf16(&tv, v, uint64_t(Hkv) * D, S, B, ldv, uint64_t(S) * ldv, 64, ATT_TILE)) return e;
+  if (int e = make_tmap_3d_bf16(&tk, k, uint64_t(Hkv) * D, S, B, ldk, uint64_t(S) * ldk, 64, BN)) return e;
+  if (int e = make_tmap_3d_bf16(&tv, v, uint64_t(Hkv) * D, S, B, ldv, uint64_t(S) * ldv, 64, BN)) return e;
   AttnParams p;
   memset(&p, 0, sizeof(p));
   p.B = B; p.S = S; p.H = H; p.Hkv = Hkv; p.D = D;
@@ -616,7 +630,7 @@ int lrp_attn_fwd(const void* q, const void* k, const void* v, int64_t ldq, int64
   p.causal = causal; p.window = window;
   p.o = reinterpret_cast<__nv_bfloat16*>(o);
   p.lse = lse;
-  return D == 128 ? launch_fwd<128>(tq, tk, tv, p, st) : launch_fwd<64>(tq, tk, tv, p, st);
+  return D == 128 ? launch_fwd<128, 64>(tq, tk, tv, p, st) : launch_fwd<64, 128>(tq, tk, tv, p, st);
 }
 
 int lrp_attn_bwd(const void* q, const void* k, const void* v, int64_t ldq, int64_t ldk, int64_t ldv, const void* o,
