@@ -18,6 +18,7 @@
 //                                 tcgen05.commit releases smem stages / publishes accumulators)
 //   warps 2..5  : epilogue       (tcgen05.ld TMEM -> registers -> fused epilogue -> global)
 //   TMEM holds two accumulator stages so the epilogue of tile i overlaps the mainloop of tile i+1.
+#include <stdlib.h>
 #include "ptx_sm100.cuh"
 #include "lrp_internal.h"
 
@@ -27,7 +28,6 @@ constexpr int BM = 128;
 constexpr int BK = 64;  // 64 bf16 = 128 B = one swizzle row
 constexpr int UMMA_K = 16;
 constexpr int GEMM_THREADS = 192;
-constexpr int GROUP_M = 16;  // rasterisation: 16 m-blocks share each streamed B panel through L2
 
 template <int BN>
 struct GemmCfg {
@@ -51,13 +51,14 @@ struct GemmParams {
   float alpha;
   int64_t ldc;
   int out_is_f32;
+  int group_m;  // rasterisation: `group_m` m-blocks share each streamed B panel through L2
 };
 
-__device__ __forceinline__ void tile_coords(int t, int num_m, int num_n, int& m_blk, int& n_blk) {
-  const int tiles_per_group = GROUP_M * num_n;
+__device__ __forceinline__ void tile_coords(int t, int num_m, int num_n, int group_m, int& m_blk, int& n_blk) {
+  const int tiles_per_group = group_m * num_n;
   const int group = t / tiles_per_group;
-  const int first_m = group * GROUP_M;
-  const int gsize = min(GROUP_M, num_m - first_m);
+  const int first_m = group * group_m;
+  const int gsize = min(group_m, num_m - first_m);
   const int in_group = t - group * tiles_per_group;
   m_blk = first_m + in_group % gsize;
   n_blk = in_group / gsize;
@@ -116,7 +117,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
       uint32_t phase = 0;
       for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
         int m_blk, n_blk;
-        tile_coords(t, num_m, num_n, m_blk, n_blk);
+        tile_coords(t, num_m, num_n, p.group_m, m_blk, n_blk);
         for (int kb = 0; kb < num_k; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
@@ -174,7 +175,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     uint32_t acc_phase = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
       int m_blk, n_blk;
-      tile_coords(t, num_m, num_n, m_blk, n_blk);
+      tile_coords(t, num_m, num_n, p.group_m, m_blk, n_blk);
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
       const int m = m_blk * BM + q * 32 + lane;
@@ -295,6 +296,18 @@ int gemm_bf16(const void* A, int64_t lda, const void* B, int64_t ldb, int b_layo
   p.alpha = epi->alpha;
   p.ldc = epi->ldc;
   p.out_is_f32 = epi->out_is_f32;
+  {
+    // A panels of one group (group_m x 128 rows x K) should stay L2-resident (~40 MB of the 126 MB) while the B
+    // panels stream past them: fewer re-reads of B from HBM for short K, no A thrashing for long K.
+    static const int forced = getenv("LRP_GROUP_M") ? atoi(getenv("LRP_GROUP_M")) : 0;
+    int g = forced;
+    if (g <= 0) {
+      const int64_t panel = int64_t(BM) * K * 2;
+      g = 64;
+      while (g > 4 && g * panel > (int64_t(40) << 20)) g >>= 1;
+    }
+    p.group_m = g;
+  }
   int bn = force_bn;
   if (bn == 0) {
     // 256-wide tiles when they still fill the machine; otherwise 128-wide for more parallelism
