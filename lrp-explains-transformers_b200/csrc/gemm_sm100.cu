@@ -297,15 +297,10 @@ int gemm_bf16(const void* A, int64_t lda, const void* B, int64_t ldb, int b_layo
   p.ldc = epi->ldc;
   p.out_is_f32 = epi->out_is_f32;
   {
-    // A panels of one group (group_m x 128 rows x K) should stay L2-resident (~40 MB of the 126 MB) while the B
-    // panels stream past them: fewer re-reads of B from HBM for short K, no A thrashing for long K.
+    // 16 m-blocks per group measured best on B200 across the Llama shapes (sweep 8/16/32/64 in
+    // profiles/r01_gemm_group_m_sweep.txt): A panels of a group stay L2-resident while B panels stream past them.
     static const int forced = getenv("LRP_GROUP_M") ? atoi(getenv("LRP_GROUP_M")) : 0;
-    int g = forced;
-    if (g <= 0) {
-      const int64_t panel = int64_t(BM) * K * 2;
-      g = 64;
-      while (g > 4 && g * panel > (int64_t(40) << 20)) g >>= 1;
-    }
+    const int g = forced > 0 ? forced : 16;
     p.group_m = g;
   }
   int bn = force_bn;
