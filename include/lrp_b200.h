@@ -57,6 +57,14 @@ typedef struct lrp_epilogue {
   const float* bias;      /* [N] fp32 */
   float alpha;
   int64_t ldc;            /* leading dimension of out / shadow / resid, in elements */
+  /* Optional fused gated-MLP LRP backward (replaces `out`, which may then be NULL): the accumulator is g_a, the
+   * gradient w.r.t. act(gate)*up, and the epilogue applies divide_gradient(2) + the identity rule on the activation +
+   * the product rule (lxt/efficient/patches.py:145-157, rules.py:88-127) exactly like lrp_gated_act_bwd:
+   *   gated_out[m, n] = g_gate,  gated_out[m, I+n] = g_up,  reading gate/up from gated_gu[m, n] / [m, I+n]. */
+  const void* gated_gu;   /* bf16 [M, 2I] (gate | up), I = N of this GEMM */
+  void* gated_out;        /* bf16 [M, 2I] */
+  int32_t gated_act;      /* LRP_ACT_* */
+  int32_t gated_cp;       /* 1 = CP-LRP variant */
 } lrp_epilogue_t;
 
 /* Generic tcgen05 GEMM, A [M,K] bf16.  b_layout 0: B is [N,K] (NT);  b_layout 1: B is [K,N] (NN).

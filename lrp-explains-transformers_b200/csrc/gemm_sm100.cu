@@ -51,8 +51,20 @@ struct GemmParams {
   float alpha;
   int64_t ldc;
   int out_is_f32;
+  const __nv_bfloat16* gated_gu;
+  __nv_bfloat16* gated_out;
+  int gated_act, gated_cp;
   int group_m;  // rasterisation: `group_m` m-blocks share each streamed B panel through L2
 };
+
+__device__ __forceinline__ float gemm_act_eval(float x, int act) {
+  if (act == LRP_ACT_SILU) return x / (1.f + __expf(-x));
+  if (act == LRP_ACT_GELU_TANH) {
+    const float k = 0.7978845608028654f;
+    return 0.5f * x * (1.f + tanhf(k * (x + 0.044715f * x * x * x)));
+  }
+  return 0.5f * x * (1.f + erff(x * 0.7071067811865476f));
+}
 
 __device__ __forceinline__ void tile_coords(int t, int num_m, int num_n, int group_m, int& m_blk, int& n_blk) {
   const int tiles_per_group = group_m * num_n;
@@ -215,7 +227,33 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
                 f[0] += r0.x; f[1] += r0.y; f[2] += r0.z; f[3] += r0.w;
                 f[4] += r1.x; f[5] += r1.y; f[6] += r1.z; f[7] += r1.w;
               }
-              if (p.out_is_f32) {
+              if (p.gated_gu != nullptr) {
+                // fused gated-MLP LRP backward: f[] = g_a
+                const int64_t goff = int64_t(m) * (2 * int64_t(p.N));
+                const uint4 ug = *reinterpret_cast<const uint4*>(p.gated_gu + goff + n);
+                const uint4 uu = *reinterpret_cast<const uint4*>(p.gated_gu + goff + p.N + n);
+                const float gt[8] = {bf16_lo(ug.x), bf16_hi(ug.x), bf16_lo(ug.y), bf16_hi(ug.y),
+                                     bf16_lo(ug.z), bf16_hi(ug.z), bf16_lo(ug.w), bf16_hi(ug.w)};
+                const float up[8] = {bf16_lo(uu.x), bf16_hi(uu.x), bf16_lo(uu.y), bf16_hi(uu.y),
+                                     bf16_lo(uu.z), bf16_hi(uu.z), bf16_lo(uu.w), bf16_hi(uu.w)};
+                float og[8], ou[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                  const float sv = gemm_act_eval(gt[j], p.gated_act);
+                  if (p.gated_cp) {
+                    ou[j] = f[j] * sv;
+                    og[j] = 0.f;
+                  } else {
+                    const float gh = f[j] * 0.5f;
+                    ou[j] = gh * sv;
+                    og[j] = (sv / (gt[j] + 1e-10f)) * (gh * up[j]);
+                  }
+                }
+                *reinterpret_cast<uint4*>(p.gated_out + goff + n) =
+                    make_uint4(pack_bf16x2(og[0], og[1]), pack_bf16x2(og[2], og[3]), pack_bf16x2(og[4], og[5]), pack_bf16x2(og[6], og[7]));
+                *reinterpret_cast<uint4*>(p.gated_out + goff + p.N + n) =
+                    make_uint4(pack_bf16x2(ou[0], ou[1]), pack_bf16x2(ou[2], ou[3]), pack_bf16x2(ou[4], ou[5]), pack_bf16x2(ou[6], ou[7]));
+              } else if (p.out_is_f32) {
                 float* o = reinterpret_cast<float*>(p.out) + row_off + n;
                 *reinterpret_cast<float4*>(o) = make_float4(f[0], f[1], f[2], f[3]);
                 *reinterpret_cast<float4*>(o + 4) = make_float4(f[4], f[5], f[6], f[7]);
@@ -283,7 +321,9 @@ int gemm_bf16(const void* A, int64_t lda, const void* B, int64_t ldb, int b_layo
   if ((lda % 8) != 0 || (ldb % 8) != 0) return set_error(LRP_ERR_ARG, "gemm: lda/ldb must be multiples of 8");
   if ((reinterpret_cast<uintptr_t>(A) & 15) || (reinterpret_cast<uintptr_t>(B) & 15))
     return set_error(LRP_ERR_ARG, "gemm: A/B must be 16-byte aligned");
-  if (epi == nullptr || epi->out == nullptr) return set_error(LRP_ERR_ARG, "gemm: missing output");
+  if (epi == nullptr || (epi->out == nullptr && epi->gated_gu == nullptr)) return set_error(LRP_ERR_ARG, "gemm: missing output");
+  if (epi->gated_gu != nullptr && (epi->gated_out == nullptr || epi->gated_act < 0 || epi->gated_act > 2))
+    return set_error(LRP_ERR_ARG, "gemm: fused gated backward needs gated_out and a valid activation");
   if ((epi->ldc % 8) != 0) return set_error(LRP_ERR_ARG, "gemm: ldc must be a multiple of 8");
   GemmParams p;
   p.M = M; p.N = N; p.K = K;
@@ -296,6 +336,10 @@ int gemm_bf16(const void* A, int64_t lda, const void* B, int64_t ldb, int b_layo
   p.alpha = epi->alpha;
   p.ldc = epi->ldc;
   p.out_is_f32 = epi->out_is_f32;
+  p.gated_gu = reinterpret_cast<const __nv_bfloat16*>(epi->gated_gu);
+  p.gated_out = reinterpret_cast<__nv_bfloat16*>(epi->gated_out);
+  p.gated_act = epi->gated_act;
+  p.gated_cp = epi->gated_cp;
   {
     // 16 m-blocks per group measured best on B200 across the Llama shapes (sweep 8/16/32/64 in
     // profiles/r01_gemm_group_m_sweep.txt): A panels of a group stay L2-resident while B panels stream past them.

@@ -30,6 +30,10 @@ class Epilogue(C.Structure):
         ("bias", C.c_void_p),
         ("alpha", C.c_float),
         ("ldc", C.c_int64),
+        ("gated_gu", C.c_void_p),
+        ("gated_out", C.c_void_p),
+        ("gated_act", C.c_int32),
+        ("gated_cp", C.c_int32),
     ]
 
 

@@ -74,6 +74,10 @@ class LlamaAttnLRPEngine:
         if rule not in ("attnlrp", "cp"):
             raise ValueError("rule must be 'attnlrp' (lxt attnLRP map) or 'cp' (lxt cp_LRP map)")
         self.cp = rule == "cp"  # CP-LRP: q,k and the MLP gate detached (lxt/efficient/models/llama.py:16-21)
+        import os
+        # fusing the gated-MLP backward rules into the down-dgrad epilogue was measured SLOWER on B200 (16.2 vs 16.9
+        # attributions/s: the exp/div epilogue outlasts the K=4096 mainloop), so it is opt-in
+        self.fuse_gated = os.environ.get("LRP_FUSE_GATED", "0") == "1"
         bf = lambda t: t.to(device=device, dtype=torch.bfloat16).contiguous()
         f32 = lambda t: t.to(device=device, dtype=torch.float32).contiguous()
         self.emb = bf(weights["emb"])
@@ -210,9 +214,13 @@ class LlamaAttnLRPEngine:
         lib, C = ops._capi.lib(), ops._capi
         g_h, g_hb = ws["g_h"], ws["g_hb"]
         # ---- gated MLP
-        ops.linear_dgrad(g_hb, lw["wd"], ws["a"])                                  # g_a [T, I]
-        C.check(lib.lrp_gated_act_bwd(ws["a"].data_ptr(), st.gu.data_ptr(), ws["g_gu"].data_ptr(), T, m.I, ops.ACT_SILU,
-                                      int(self.cp), ops._stream()), "gated_act_bwd")
+        if self.fuse_gated:
+            # down dgrad with (÷2, identity rule on SiLU, product rule) fused into its epilogue: g_a never touches HBM
+            ops.linear_dgrad_gated_bwd(g_hb, lw["wd"], st.gu, ws["g_gu"], ops.ACT_SILU, self.cp)
+        else:
+            ops.linear_dgrad(g_hb, lw["wd"], ws["a"])                              # g_a [T, I]
+            C.check(lib.lrp_gated_act_bwd(ws["a"].data_ptr(), st.gu.data_ptr(), ws["g_gu"].data_ptr(), T, m.I, ops.ACT_SILU,
+                                          int(self.cp), ops._stream()), "gated_act_bwd")
         ops.linear_dgrad(ws["g_gu"], lw["wgu"], g_h, resid=g_h, rowscale=st.rstd2, colscale=lw["ln2_f"], shadow=g_hb)
         # ---- attention
         ops.linear_dgrad(g_hb, lw["wo"], ws["g_o"])                                # g_o [T, H D]

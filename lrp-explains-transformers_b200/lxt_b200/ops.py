@@ -97,6 +97,35 @@ def gemm(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor, *, b_layout: int, 
     return out
 
 
+def linear_dgrad_gated_bwd(gy: torch.Tensor, w: torch.Tensor, gu: torch.Tensor, ggu: torch.Tensor, act: int = ACT_SILU,
+                           cp: bool = False) -> torch.Tensor:
+    """Down-projection LRP dgrad with the gated-MLP point-wise rules fused into the epilogue:
+    g_a = gy @ w  (never written);  ggu = [g_gate | g_up] as `gated_act_bwd(g_a, gu)` would produce.
+    gy [T,d] bf16, w [d,I] bf16 (nn.Linear layout of down_proj), gu/ggu [T,2I] bf16 contiguous."""
+    _need(gy, torch.bfloat16, "gy")
+    _need(w, torch.bfloat16, "w")
+    _need(gu, torch.bfloat16, "gu")
+    _need(ggu, torch.bfloat16, "ggu")
+    T, K = gy.shape
+    I = w.shape[1]
+    if w.shape[0] != K or tuple(gu.shape) != (T, 2 * I) or tuple(ggu.shape) != (T, 2 * I) or not (gu.is_contiguous() and ggu.is_contiguous()):
+        raise _capi.LrpError("linear_dgrad_gated_bwd: shape mismatch")
+    e = Epilogue()
+    e.alpha = 1.0
+    e.ldc = I
+    e.gated_gu, e.gated_out, e.gated_act, e.gated_cp = gu.data_ptr(), ggu.data_ptr(), act, int(cp)
+    prof = GEMM_PROFILE
+    if prof is not None:
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+    check(_capi.lib().lrp_gemm_bf16(gy.data_ptr(), _rowmajor2d(gy, "gy"), w.data_ptr(), _rowmajor2d(w, "w"), 1, T, I, K,
+                                    C.byref(e), 0, _stream()), "lrp_gemm_bf16(gated)")
+    if prof is not None:
+        ev1.record()
+        prof.append((2.0 * T * I * K, ev0, ev1))
+    return ggu
+
+
 def linear_fwd(x: torch.Tensor, w: torch.Tensor, out: torch.Tensor, **epi) -> torch.Tensor:
     """y = x W^T (+ fused epilogue).  x [T,K] bf16, w [N,K] bf16."""
     return gemm(x, w, out, b_layout=0, **epi)

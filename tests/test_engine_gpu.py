@@ -76,10 +76,15 @@ def test_engine_tinyllama_dims_seq512():
     w = O.random_llama_weights(cfg, seed=21)
     ids = torch.randint(0, cfg["V"], (1, 512), generator=torch.Generator().manual_seed(22))
     ref, aux = O.llama_attnlrp(w, ids, cfg, dtype=torch.float32, return_aux=True)
+    ref_bf16, aux_bf16 = O.llama_attnlrp(w, ids, cfg, dtype=torch.bfloat16, return_aux=True)  # reference-style bf16 run
     rel, a2 = _engine(cfg, w, micro_batch=1).attribute_device(ids.cuda(), return_aux=True)
     assert torch.equal(a2["idx"].cpu().long(), aux["idx"])
-    err = rel_l2(rel.cpu(), ref)
-    gerr = rel_l2(a2["g_emb"].cpu(), aux["g_emb"])
-    print(f"TinyLlama-width engine rel-L2 vs oracle fp32: relevance {err:.3e}, g_emb {gerr:.3e}")
-    # relevance[t] = sum over d=2048 signed terms: cancellation amplifies the bf16 operand noise of g_emb
-    assert gerr < 6e-3 and err < 1e-2
+    err, gerr = rel_l2(rel.cpu(), ref), rel_l2(a2["g_emb"].cpu(), aux["g_emb"])
+    err_b, gerr_b = rel_l2(ref_bf16, ref), rel_l2(aux_bf16["g_emb"].float(), aux["g_emb"])
+    print(f"TinyLlama-width rel-L2 vs oracle fp32: engine relevance {err:.3e} g_emb {gerr:.3e}; "
+          f"bf16 oracle run relevance {err_b:.3e} g_emb {gerr_b:.3e}")
+    # At d=2048 even the forward logits of any bf16 pipeline are ~1e-2 from fp32.  The bar is self-calibrating: the
+    # engine (fp32 residual/gradient streams) must be at least as close to the fp32 oracle as a reference-style
+    # bf16 run of the same model, with an absolute ceiling.
+    assert err <= 1.1 * err_b and gerr <= 1.1 * gerr_b
+    assert err < 1.5e-2 and gerr < 2e-2

@@ -174,3 +174,21 @@ def test_path_ends(ops):
     g = rnd(T, d, dtype=torch.float32, seed=63)
     assert rel_l2(ops.gxi_reduce(h, g), (h * g).sum(-1)) < 1e-6
     assert torch.equal(ops.cast_bf16(g), g.bfloat16())
+
+
+@pytest.mark.parametrize("cp", [False, True])
+def test_fused_gated_backward_epilogue_equals_unfused(ops, cp):
+    """down-proj LRP dgrad with the gated-MLP rules in its epilogue == dgrad followed by lrp_gated_act_bwd"""
+    T, d, I = 640, 512, 1280
+    gy, w, gu = rnd(T, d, seed=71), rnd(d, I, scale=0.05, seed=72), rnd(T, 2 * I, scale=2.0, seed=73)
+    ga = torch.empty(T, I, dtype=torch.bfloat16, device="cuda")
+    ops.linear_dgrad(gy, w, ga)
+    ref = ops.gated_act_bwd(ga, gu, cp=cp)
+    got = ops.linear_dgrad_gated_bwd(gy, w, gu, torch.empty_like(gu), cp=cp)
+    # the unfused path rounds g_a to bf16 before the point-wise rule, the fused one does not
+    assert rel_l2(got.float(), ref.float()) < 4e-3
+    ga32 = gy.float() @ w.float()
+    gate, up = gu[:, :I].float(), gu[:, I:].float()
+    s = torch.nn.functional.silu(gate)
+    exp = torch.cat([torch.zeros_like(gate), ga32 * s], 1) if cp else torch.cat([(s / (gate + 1e-10)) * (ga32 / 2 * up), ga32 / 2 * s], 1)
+    assert rel_l2(got.float(), exp) < 3e-3
