@@ -245,8 +245,13 @@ class LlamaAttnLRPEngine:
 
     # ------------------------------------------------------------------ one micro-batch, device resident
     @torch.no_grad()
-    def attribute_device(self, ids: torch.Tensor, return_aux: bool = False):
-        """ids int64 [B,S] on the device -> relevance fp32 [B,S] on the device."""
+    def attribute_device(self, ids: torch.Tensor, return_aux: bool = False, trace: bool = False):
+        """ids int64 [B,S] on the device -> relevance fp32 [B,S] on the device.
+        trace=True additionally returns the latent relevance of every decoder layer's output, `[L,B,S]`
+        (= `output * output.grad` summed over features, what docs/source/latent-feature-attribution-efficient.rst
+        :49-90 obtains with forward hooks + retain_grad), emitted here as one reduction kernel per layer."""
+        if trace and self.store_policy != "all":
+            raise ValueError("trace=True needs store='all'")
         m = self.dims
         B, S = ids.shape
         T = B * S
@@ -258,8 +263,11 @@ class LlamaAttnLRPEngine:
 
         seg = self._segment_len()
         if self.store_policy == "all":
+            h_outs = [] if trace else None
             for l, lw in enumerate(self.layers):
                 self._layer_fwd(lw, ws["stores"][l], h, ws, B, S)
+                if trace:
+                    h_outs.append(h.clone())
         else:
             for l, lw in enumerate(self.layers):
                 if l % seg == 0:
@@ -279,7 +287,11 @@ class LlamaAttnLRPEngine:
         ops.cast_bf16(g_h, g_hb)
 
         if self.store_policy == "all":
+            layer_rel = [None] * m.L
             for l in range(m.L - 1, -1, -1):
+                if trace:
+                    layer_rel[l] = ops.gxi_reduce(h_outs[l], g_h).view(B, S)
+                    h_outs[l] = None
                 self._layer_bwd(self.layers[l], ws["stores"][l], ws, B, S)
         else:
             nseg = math.ceil(m.L / seg)
@@ -297,8 +309,11 @@ class LlamaAttnLRPEngine:
         # ---- Gradient x Input at the embedding
         C.check(lib.lrp_embed_gather(flat.data_ptr(), self.emb.data_ptr(), 1.0, h.data_ptr(), T, m.d, ops._stream()), "embed")
         rel = ops.gxi_reduce(h, g_h).view(B, S)
-        if return_aux:
-            return rel, {"idx": idx, "logits": ws["logits"], "g_emb": g_h.view(B, S, m.d)}
+        if return_aux or trace:
+            aux = {"idx": idx, "logits": ws["logits"], "g_emb": g_h.view(B, S, m.d)}
+            if trace:
+                aux["layer_relevance"] = torch.stack(layer_rel)
+            return rel, aux
         return rel
 
     # ------------------------------------------------------------------ public API: host in, host out

@@ -182,6 +182,7 @@ def llama_attnlrp(weights: Dict, ids: torch.Tensor, cfg: Dict, dtype=torch.float
         s = F.silu(gate)
         st.update(gate=gate, up=up, s=s)
         h = h + (s * up) @ W(lw["wd"]).T  # lxt/efficient/patches.py:145-157 (`gated_mlp_forward`)
+        st["h_out"] = h
         stash.append(st)
     hN, rstdN = _rmsnorm_fwd(h, W(weights["norm"]), eps)
     logits = hN[:, -1, :] @ W(weights["lm_head"]).T  # only the last position is read (quantized_llama.py:40)
@@ -191,7 +192,10 @@ def llama_attnlrp(weights: Dict, ids: torch.Tensor, cfg: Dict, dtype=torch.float
     g_h = torch.zeros_like(h)
     g_hN_last = W(weights["lm_head"])[idx]  # d(logit_max)/d(hN_last)
     g_h[:, -1, :] = _rmsnorm_bwd(g_hN_last, W(weights["norm"]), rstdN[:, -1, :])
+    trace = []
     for lw, st in zip(reversed(weights["layers"]), reversed(stash)):
+        # latent relevance of this layer's output: output * grad (docs/source/latent-feature-attribution-efficient.rst:49-90)
+        trace.append((st["h_out"] * g_h).float().sum(-1))
         # gated MLP: uniform rule on the product, identity rule on SiLU (patches.py:145-157, rules.py:88-127)
         if cp:
             g_xn2 = ((g_h @ W(lw["wd"])) * st["s"]) @ W(lw["wu"])
@@ -222,7 +226,7 @@ def llama_attnlrp(weights: Dict, ids: torch.Tensor, cfg: Dict, dtype=torch.float
         g_h = g_h + _rmsnorm_bwd(g_xn, W(lw["ln1"]), st["rstd1"])
     rel = (emb * g_h).float().sum(-1)  # quantized_llama.py:47
     if return_aux:
-        return rel, {"idx": idx, "logits": logits.float(), "g_emb": g_h}
+        return rel, {"idx": idx, "logits": logits.float(), "g_emb": g_h, "layer_relevance": torch.stack(trace[::-1])}
     return rel
 
 

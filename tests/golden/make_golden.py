@@ -158,10 +158,24 @@ def gen_llama(name, cfg, B, S, seed):
             # examples/quantized_llama.py:35-47
             emb = model.get_input_embeddings()(ids)
             emb = emb.detach().requires_grad_()
+            # latent relevance trace exactly as docs/source/latent-feature-attribution-efficient.rst:49-90 does it:
+            # forward hooks keep each decoder layer's output and retain its grad; relevance = output * output.grad
+            kept, hooks = [], []
+
+            def keep(mod, inp, out):
+                t = out[0] if isinstance(out, tuple) else out
+                t.retain_grad()
+                kept.append(t)
+
+            for layer in model.model.layers:
+                hooks.append(layer.register_forward_hook(keep))
             logits = model(inputs_embeds=emb, use_cache=False).logits
             max_logits, max_idx = torch.max(logits[:, -1, :], dim=-1)
             max_logits.sum().backward()
+            for hk in hooks:
+                hk.remove()
             rel = (emb * emb.grad).float().sum(-1)
+            res[f"trace_{tag}_{impl}"] = torch.stack([(t * t.grad).float().sum(-1) for t in kept]).detach().numpy()
             res[f"rel_{tag}_{impl}"] = rel.detach().numpy()
             res[f"idx_{tag}_{impl}"] = max_idx.numpy()
             res[f"gemb_{tag}_{impl}"] = emb.grad.float().numpy()

@@ -88,3 +88,14 @@ def test_engine_tinyllama_dims_seq512():
     # bf16 run of the same model, with an absolute ceiling.
     assert err <= 1.1 * err_b and gerr <= 1.1 * gerr_b
     assert err < 1.5e-2 and gerr < 2e-2
+
+
+def test_engine_latent_relevance_trace():
+    """per-layer latent relevance as a by-product of the backward sweep, vs the reference's hooks"""
+    cfg, w, ids, z = load_llama_golden("llama_tiny_d128.npz")
+    rel, aux = _engine(cfg, w, micro_batch=1).attribute_device(ids.cuda(), trace=True)
+    tr = aux["layer_relevance"].cpu()
+    assert tuple(tr.shape) == (cfg["L"],) + tuple(ids.shape)
+    err = rel_l2(tr, z["trace_fp32_sdpa"])
+    print(f"latent trace rel-L2 vs reference hooks = {err:.3e}")
+    assert err < 6e-3

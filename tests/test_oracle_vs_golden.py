@@ -82,3 +82,11 @@ def test_llama_cp_lrp_matches_reference():
     rel, aux = O.llama_attnlrp(w, T(z["ids"]), cfg, dtype=torch.float32, return_aux=True, rule="cp")
     assert np.array_equal(aux["idx"].numpy(), z["idx"])
     assert rel_l2(rel, z["rel_fp32"]) < 1e-4
+
+
+@pytest.mark.parametrize("name", ["llama_tiny_d64.npz", "llama_tiny_d128.npz"])
+def test_latent_relevance_trace_matches_reference_hooks(name):
+    """per-layer `output * output.grad` (docs/source/latent-feature-attribution-efficient.rst:49-90)"""
+    cfg, w, ids, z = load_llama_golden(name)
+    _, aux = O.llama_attnlrp(w, ids, cfg, dtype=torch.float32, return_aux=True)
+    assert rel_l2(aux["layer_relevance"], z["trace_fp32_sdpa"]) < 1e-4
