@@ -198,6 +198,34 @@ class _FlashAttnLRPFn(Function):
         return dq.transpose(1, 2), dk.transpose(1, 2), dv.transpose(1, 2), None, None, None, None, None, None
 
 
+class _PackedSelfAttnFn(Function):
+    """self-attention on a packed projection `qkv [B,S,3*H*D]` (q | k | v): the flash kernels read and write strided
+    views of the packed buffers, so the in-projection GEMM output and its gradient are never split or copied."""
+
+    @staticmethod
+    def forward(ctx, qkv, H, D, scale, causal, q_div, k_div, v_div):
+        _need_bf16_cuda(qkv, "packed self-attention")
+        B, S, W = qkv.shape
+        qkv = qkv.contiguous()
+        q, k, v = (qkv[:, :, i * H * D:(i + 1) * H * D].view(B, S, H, D) for i in range(3))
+        o, lse = ops.attn_fwd(q, k, v, scale, causal=causal, window=0)
+        ctx.save_for_backward(qkv, o, lse)
+        ctx.cfg = (H, D, scale, causal, q_div, k_div, v_div)
+        return o.view(B, S, H * D)
+
+    @staticmethod
+    def backward(ctx, d_o):
+        qkv, o, lse = ctx.saved_tensors
+        H, D, scale, causal, q_div, k_div, v_div = ctx.cfg
+        B, S, _ = qkv.shape
+        q, k, v = (qkv[:, :, i * H * D:(i + 1) * H * D].view(B, S, H, D) for i in range(3))
+        g = torch.empty_like(qkv)
+        dq, dk, dv = (g[:, :, i * H * D:(i + 1) * H * D].view(B, S, H, D) for i in range(3))
+        ops.attn_bwd(q, k, v, o, d_o.contiguous().view(B, S, H, D), lse, scale, causal=causal, window=0, q_div=q_div,
+                     k_div=k_div, v_div=v_div, dq=dq, dk=dk, dv=dv)
+        return g, None, None, None, None, None, None, None
+
+
 def _check_mask_is_causal(mask, S, window):
     """Only plain (optionally sliding-window) causal attention exists on the B200 path; padding masks raise."""
     if mask is None:
@@ -356,6 +384,25 @@ def patch_cp_attention(module):
 def cp_multi_head_attention_forward(self, query, key, value, *args, **kwargs):
     """CP-LRP for torch.nn.MultiheadAttention: q, k detached (reference patches.py:261-269)."""
     return self.original_forward(stop_gradient(query), stop_gradient(key), value, *args, **kwargs)
+
+
+def b200_cp_multi_head_attention_forward(self, query, key, value, *args, **kwargs):
+    """CP-LRP `nn.MultiheadAttention` entirely on the B200 kernels: packed in-projection GEMM -> flash attention with
+    q,k detached (dQ = dK = 0, plain dV) -> out-projection GEMM.  Same rule as `cp_multi_head_attention_forward`
+    (reference patches.py:261-269); calls that the kernels do not cover (cross-attention, masks, fp32, seq-first
+    layout, exotic head sizes) take that reference-equivalent route instead."""
+    E, H = self.embed_dim, self.num_heads
+    D = E // H
+    plain = (query is key and key is value and query.dim() == 3 and self.batch_first and self._qkv_same_embed_dim
+             and self.in_proj_weight is not None and query.is_cuda and query.dtype == torch.bfloat16 and D in (64, 128)
+             and kwargs.get("attn_mask") is None and kwargs.get("key_padding_mask") is None and not kwargs.get("is_causal", False)
+             and len(args) == 0 and self.bias_k is None and not self.add_zero_attn and (self.dropout == 0.0 or not self.training))
+    if not plain:
+        return cp_multi_head_attention_forward(self, query, key, value, *args, **kwargs)
+    qkv = _LinearFn.apply(query, self.in_proj_weight, self.in_proj_bias)
+    o = _PackedSelfAttnFn.apply(qkv, H, D, 1.0 / math.sqrt(D), False, 0.0, 0.0, 1.0)
+    out = _LinearFn.apply(o, self.out_proj.weight, self.out_proj.bias)
+    return out, None
 
 
 def cp_gated_mlp_forward(self, x):

@@ -10,18 +10,50 @@ from helpers import load_npz, rel_l2
 pytestmark = pytest.mark.gpu
 
 
+def _tiny_vit(z):
+    from torchvision.models import vision_transformer
+    model = vision_transformer.VisionTransformer(image_size=64, patch_size=16, num_layers=2, num_heads=2, hidden_dim=128,
+                                                 mlp_dim=256, num_classes=16)
+    model.load_state_dict({k[3:]: torch.from_numpy(v) for k, v in z.items() if k.startswith("sd_")})
+    for p in model.parameters():
+        p.requires_grad_(False)
+    return model.cuda().eval()
+
+
+def test_vit_bf16_runs_whole_block_on_b200_kernels():
+    """bf16 ViT: projections + attention + MLP on the tcgen05 kernels (non-causal flash attention, S = 17 tokens)"""
+    from torchvision.models import vision_transformer
+    from lxt_b200.efficient import monkey_patch
+    from lxt_b200 import ops
+    import warnings
+    z = load_npz("vit_tiny.npz")
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        monkey_patch(vision_transformer)
+    model = _tiny_vit(z).to(torch.bfloat16)
+    n0 = ops.launch_count()
+    x = torch.from_numpy(z["x"]).cuda().to(torch.bfloat16).requires_grad_()
+    y = model(x)
+    cls = torch.from_numpy(z["cls"]).cuda()
+    y[torch.arange(2), cls].sum().backward()
+    heat = (x * x.grad).float().sum(1).detach().cpu()
+    assert ops.launch_count() - n0 > 2 * 20, "the block did not run on the B200 kernels"
+    err = rel_l2(heat, z["heat"])
+    cos = torch.nn.functional.cosine_similarity(heat.flatten(), torch.from_numpy(z["heat"]).flatten(), dim=0)
+    print(f"bf16 ViT heat-map vs fp32 reference: rel-L2 {err:.3e}, cos {cos:.5f}")
+    assert err < 3e-2 and cos > 0.999
+
+
 def test_vit_pixel_relevance_matches_reference():
     from torchvision.models import vision_transformer
     from lxt_b200.efficient import monkey_patch
     from lxt_b200 import ops
     z = load_npz("vit_tiny.npz")
-    monkey_patch(vision_transformer, verbose=True)
-    model = vision_transformer.VisionTransformer(image_size=64, patch_size=16, num_layers=2, num_heads=2, hidden_dim=128,
-                                                 mlp_dim=256, num_classes=16)
-    model.load_state_dict({k[3:]: torch.from_numpy(v) for k, v in z.items() if k.startswith("sd_")})
-    model = model.cuda().eval()
-    for p in model.parameters():
-        p.requires_grad_(False)
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        monkey_patch(vision_transformer, verbose=True)
+    model = _tiny_vit(z)
     n0 = ops.launch_count()
     x = torch.from_numpy(z["x"]).cuda().requires_grad_()
     y = model(x)
