@@ -66,7 +66,7 @@ class LlamaAttnLRPEngine:
     """B200-native AttnLRP engine.  Construct with `from_weights`, `from_hf` or `random_init`."""
 
     def __init__(self, dims: LlamaDims, device: torch.device, weights: Dict, micro_batch: int = 8, store: str = "all",
-                 rule: str = "attnlrp"):
+                 rule: str = "attnlrp", cuda_graph: bool = False):
         if device.type != "cuda":
             raise RuntimeError("LlamaAttnLRPEngine runs on a CUDA (B200) device only; there is no CPU path")
         ops._capi.require_device()
@@ -92,6 +92,10 @@ class LlamaAttnLRPEngine:
         self._ws_key = None
         self._ws = None
         self._rope_key = None
+        # cuda_graph=True captures the whole attribution (≈20 launches per layer) of a given [B,S] once and replays it:
+        # small / latency-bound shapes (e.g. TinyLlama, B=1, S=512) stop being bound by host launch overhead.
+        self.cuda_graph = cuda_graph
+        self._graphs = {}
 
     # ------------------------------------------------------------------ constructors
     @classmethod
@@ -316,6 +320,31 @@ class LlamaAttnLRPEngine:
             return rel, aux
         return rel
 
+    @torch.no_grad()
+    def attribute_device_graphed(self, ids: torch.Tensor) -> torch.Tensor:
+        """Same as `attribute_device(ids)` but replayed from a CUDA graph captured on first use of this [B,S]
+        (static input/output buffers; the returned tensor is overwritten by the next call of the same shape)."""
+        key = tuple(ids.shape)
+        ent = self._graphs.get(key)
+        if ent is None:
+            if self._graphs:
+                raise RuntimeError("one graphed [B,S] shape per engine (the workspace is shared); build another engine")
+            static_ids = ids.clone()
+            side = torch.cuda.Stream(device=self.device)
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for _ in range(2):  # warm-up outside capture: lazy attribute setup, workspace allocation, rope tables
+                    self.attribute_device(static_ids)
+            torch.cuda.current_stream().wait_stream(side)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                static_out = self.attribute_device(static_ids)
+            ent = self._graphs[key] = (g, static_ids, static_out)
+        g, static_ids, static_out = ent
+        static_ids.copy_(ids, non_blocking=True)
+        g.replay()
+        return static_out
+
     # ------------------------------------------------------------------ public API: host in, host out
     @torch.no_grad()
     def attribute(self, input_ids: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
@@ -326,7 +355,8 @@ class LlamaAttnLRPEngine:
             out = torch.empty((N, S), dtype=torch.float32, pin_memory=True)
         for i in range(0, N, self.micro_batch):
             ids = input_ids[i:i + self.micro_batch].to(self.device, non_blocking=True)
-            rel = self.attribute_device(ids)
+            full = ids.shape[0] == self.micro_batch
+            rel = self.attribute_device_graphed(ids) if (self.cuda_graph and full) else self.attribute_device(ids)
             out[i:i + self.micro_batch].copy_(rel, non_blocking=True)
         torch.cuda.current_stream().synchronize()
         return out

@@ -99,3 +99,14 @@ def test_engine_latent_relevance_trace():
     err = rel_l2(tr, z["trace_fp32_sdpa"])
     print(f"latent trace rel-L2 vs reference hooks = {err:.3e}")
     assert err < 6e-3
+
+
+def test_engine_cuda_graph_replay_matches_eager():
+    cfg, w, ids, z = load_llama_golden("llama_tiny_d64.npz")
+    eager = _engine(cfg, w, micro_batch=2).attribute(ids.pin_memory()).clone()
+    eng = _engine(cfg, w, micro_batch=2, cuda_graph=True)
+    for _ in range(3):  # first call captures, the next ones replay
+        got = eng.attribute(ids.pin_memory()).clone()
+        assert rel_l2(got, eager) < 1e-5   # dQ uses fp32 atomics: order-dependent in the last bits only
+    ids2 = torch.roll(ids, 1, 0)           # different content, same shape: replay must pick up the new ids
+    assert rel_l2(eng.attribute(ids2.pin_memory()), torch.roll(eager, 1, 0)) < 1e-5
