@@ -13,149 +13,10 @@
 //
 // Thread roles (160 threads): warps 0-3 own one query row each (row r <-> TMEM lane r, so soft-max needs no
 // shuffles); warp 4 lane 0 issues all TMA loads and all tcgen05.mma.
-#include <math.h>
-#include <string.h>
-#include "ptx_sm100.cuh"
-#include "lrp_internal.h"
+#include <stdlib.h>
+#include "attn_common.cuh"
 
 namespace lrp {
-
-constexpr int ATT_TILE = 128;       // query rows per CTA tile == keys per tile
-constexpr int ATT_THREADS = 160;
-constexpr float LOG2E = 1.4426950408889634f;
-constexpr float LN2 = 0.6931471805599453f;
-
-struct AttnParams {
-  int B, S, H, Hkv, D;
-  float scale, scale_log2;
-  int causal, window;
-  // forward
-  __nv_bfloat16* o;   // [B,S,H,D]
-  float* lse;         // [B,H,S]
-  // backward
-  const float* delta; // [B,H,S]
-  float* dq_acc;      // [B,S,H,D] fp32
-  __nv_bfloat16* dk;  // [B,S,Hkv,D] strided by lddk
-  __nv_bfloat16* dv;
-  int64_t lddk, lddv;
-  float inv_k_div, inv_v_div;
-};
-
-__device__ __forceinline__ bool is_masked(int qpos, int kpos, int S, int causal, int window) {
-  if (kpos >= S) return true;
-  if (causal && kpos > qpos) return true;
-  if (window > 0 && qpos - kpos >= window) return true;
-  return false;
-}
-
-__device__ __forceinline__ float ex2_approx(float x) {
-  float y;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
-
-// Per-row column window [lo, hi] (tile-relative) of keys that are NOT masked:
-//   key (kbase + c) is visible iff lo <= c <= hi.
-__device__ __forceinline__ void row_window(int qpos, int kbase, int S, int causal, int window, int& lo, int& hi) {
-  hi = S - 1 - kbase;
-  if (causal) hi = min(hi, qpos - kbase);
-  lo = window > 0 ? qpos - window + 1 - kbase : 0;
-}
-
-template <bool MASK>
-__device__ __forceinline__ float chunk_max(const uint32_t (&v)[32], int c0, int lo, int hi) {
-  float mx = -INFINITY;
-#pragma unroll
-  for (int i = 0; i < 32; ++i) {
-    float t = __uint_as_float(v[i]);
-    if (MASK) t = (c0 + i > hi || c0 + i < lo) ? -INFINITY : t;
-    mx = fmaxf(mx, t);
-  }
-  return mx;
-}
-
-// f[i] = 2^(s*scale_log2 - msub) (0 where masked); returns the chunk's sum
-template <bool MASK>
-__device__ __forceinline__ float chunk_exp(const uint32_t (&v)[32], float (&f)[32], float scale_log2, float msub, int c0,
-                                           int lo, int hi) {
-  float sum = 0.f;
-#pragma unroll
-  for (int i = 0; i < 32; ++i) {
-    float pe = ex2_approx(fmaf(__uint_as_float(v[i]), scale_log2, -msub));
-    if (MASK) pe = (c0 + i > hi || c0 + i < lo) ? 0.f : pe;
-    f[i] = pe;
-    sum += pe;
-  }
-  return sum;
-}
-
-// backward: P = 2^(s*scale_log2 - lse2), dS = P * (dP*scale - delta*scale)
-template <bool MASK>
-__device__ __forceinline__ void chunk_p_ds(const uint32_t (&vs)[32], const uint32_t (&vd)[32], float (&fp)[32], float (&fd)[32],
-                                           float scale_log2, float lse2, float scale, float delta_s, int c0, int lo, int hi) {
-#pragma unroll
-  for (int i = 0; i < 32; ++i) {
-    float pe = ex2_approx(fmaf(__uint_as_float(vs[i]), scale_log2, -lse2));
-    if (MASK) pe = (c0 + i > hi || c0 + i < lo) ? 0.f : pe;
-    fp[i] = pe;
-    fd[i] = pe * fmaf(__uint_as_float(vd[i]), scale, -delta_s);
-  }
-}
-
-// write 32 consecutive bf16 columns [c*32, c*32+32) of row r into a [128][128] tile stored as two
-// [128 rows][64 cols] 128B-swizzled blocks
-__device__ __forceinline__ void store_row_chunk_sw128(uint8_t* tile, int r, int c, const float (&f)[32]) {
-  uint8_t* rowp = tile + (c >> 1) * 16384 + r * 128;
-#pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    const int chunk = ((c & 1) * 4 + q) ^ (r & 7);
-    *reinterpret_cast<uint4*>(rowp + chunk * 16) =
-        make_uint4(pack_bf16x2(f[q * 8 + 0], f[q * 8 + 1]), pack_bf16x2(f[q * 8 + 2], f[q * 8 + 3]),
-                   pack_bf16x2(f[q * 8 + 4], f[q * 8 + 5]), pack_bf16x2(f[q * 8 + 6], f[q * 8 + 7]));
-  }
-}
-
-// ---- UMMA issue helpers (single thread) -------------------------------------------------------
-// C[128 x N] (+)= A_kmajor[128 x K] * B_kmajor[N x K]^T, K = KB*64, tiles as [rows][64]-blocks of 16 KiB
-//   a_blk / b_blk = byte distance between consecutive 64-column blocks of the A / B tile (= rows * 128 B)
-template <int N>
-__device__ __forceinline__ void mma_kk(uint32_t tmem_d, uint32_t a_base, uint32_t b_base, int ktot, bool acc_first,
-                                       uint32_t a_blk = 16384, uint32_t b_blk = 16384) {
-  constexpr uint32_t idesc = make_idesc_bf16(128, N, 0, 0);
-  for (int kk = 0; kk < ktot / 16; ++kk) {
-    const uint32_t aoff = (kk >> 2) * a_blk + (kk & 3) * 32;
-    const uint32_t boff = (kk >> 2) * b_blk + (kk & 3) * 32;
-    tc_mma_ss(tmem_d, make_sdesc_sw128(a_base + aoff, 16, 1024), make_sdesc_sw128(b_base + boff, 16, 1024), idesc,
-              (acc_first || kk > 0) ? 1u : 0u);
-  }
-}
-// C[128 x N] (+)= A_kmajor[128 x 128] * B_mnmajor[128(k) x N]
-//   ktot = contraction length (rows of B); b_lbo = byte distance between 64-column blocks of B (= ktot * 128 B)
-template <int N>
-__device__ __forceinline__ void mma_kmn(uint32_t tmem_d, uint32_t a_base, uint32_t b_base, bool acc_first, int ktot = 128,
-                                        uint32_t b_lbo = 16384) {
-  constexpr uint32_t idesc = make_idesc_bf16(128, N, 0, 1);
-  for (int kk = 0; kk < ktot / 16; ++kk) {
-    const uint32_t aoff = (kk >> 2) * 16384 + (kk & 3) * 32;
-    tc_mma_ss(tmem_d, make_sdesc_sw128(a_base + aoff, 16, 1024), make_sdesc_sw128(b_base + kk * 2048, b_lbo, 1024),
-              idesc, (acc_first || kk > 0) ? 1u : 0u);
-  }
-}
-// C[128 x N] (+)= A_mnmajor[128(k) x 128(m)]^T * B_mnmajor[128(k) x N]
-template <int N>
-__device__ __forceinline__ void mma_mnmn(uint32_t tmem_d, uint32_t a_base, uint32_t b_base, bool acc_first) {
-  constexpr uint32_t idesc = make_idesc_bf16(128, N, 1, 1);
-  for (int kk = 0; kk < 8; ++kk) {
-    tc_mma_ss(tmem_d, make_sdesc_sw128(a_base + kk * 2048, 16384, 1024),
-              make_sdesc_sw128(b_base + kk * 2048, 16384, 1024), idesc, (acc_first || kk > 0) ? 1u : 0u);
-  }
-}
-
-template <int D, int ROWS = 128>
-__device__ __forceinline__ void load_tile(uint8_t* dst, const CUtensorMap* tm, uint64_t* bar, int col0, int row0, int b) {
-#pragma unroll
-  for (int kb = 0; kb < D / 64; ++kb) tma_load_3d(dst + kb * (ROWS * 128), tm, bar, col0 + kb * 64, row0, b);
-}
 
 // =================================================================================================
 // forward
@@ -231,12 +92,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__
         if (jj == 0) mbar_wait(q_full, 0);
         mbar_wait(&k_full[st], (jj >> 1) & 1);
         tc_fence_after();
-        mma_kk<BN>(tmem_S, smem_u32(sQ), smem_u32(sK + st * KV_BYTES), D, false, 16384, BN * 128);   // S = Q K^T
+        mma_kk<BN, D, 16384, BN * 128>(tmem_S, smem_u32(sQ), smem_u32(sK + st * KV_BYTES), false);   // S = Q K^T
         tc_commit(s_full);
         mbar_wait(p_full, jj & 1);
         mbar_wait(&v_full[st], (jj >> 1) & 1);
         tc_fence_after();
-        mma_kmn<D>(tmem_O, smem_u32(sP), smem_u32(sV + st * KV_BYTES), jj > 0, BN, BN * 128);        // O += P V
+        mma_kmn<D, BN, BN * 128>(tmem_O, smem_u32(sP), smem_u32(sV + st * KV_BYTES), jj > 0);        // O += P V
         tc_commit(&kv_empty[st]);
         tc_commit(o_full);
       }
@@ -404,8 +265,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__
         mbar_wait(qdo_full, it & 1);
         if (it > 0) mbar_wait(dq_empty, (it - 1) & 1);
         tc_fence_after();
-        mma_kk<128>(tmem_S, smem_u32(sQ), smem_u32(sK), D, false);    // S  = Q K^T
-        mma_kk<128>(tmem_dP, smem_u32(sdO), smem_u32(sV), D, false);  // dP = dO V^T
+        mma_kk<128, D>(tmem_S, smem_u32(sQ), smem_u32(sK), false);    // S  = Q K^T
+        mma_kk<128, D>(tmem_dP, smem_u32(sdO), smem_u32(sV), false);  // dP = dO V^T
         tc_commit(s_full);
         mbar_wait(p_full, it & 1);
         tc_fence_after();
@@ -650,6 +511,13 @@ int lrp_attn_bwd(const void* q, const void* k, const void* v, int64_t ldq, int64
   const int64_t rows = int64_t(B) * S * H;
   attn_delta_kernel<<<unsigned((rows + 7) / 8), 256, 0, st>>>((const __nv_bfloat16*)o, (const __nv_bfloat16*)d_o, delta_ws, B, S, H, D);
   LRP_CHECK_LAUNCH();
+  // LRP_ATTN_BWD=v2 selects the two-kernel pipelined, atomic-free (bit-reproducible) backward of attn_bwd_v2.cu.
+  // Measured on B200 it is on par with / slightly slower than this single-kernel version (its 64-wide MMAs are
+  // smem-operand bound and S/dP/exp are recomputed for dQ), so the single kernel stays the default.
+  const char* sel = getenv("LRP_ATTN_BWD");
+  if (sel != nullptr && !strcmp(sel, "v2"))
+    return attn_bwd_v2(q, k, v, ldq, ldk, ldv, d_o, lse, delta_ws, dq, dk, dv, lddq, lddk, lddv, B, S, H, Hkv, D, scale, causal,
+                       window, q_div, k_div, v_div, st);
   cudaError_t ce = cudaMemsetAsync(dq_acc_ws, 0, size_t(rows) * D * sizeof(float), st);
   if (ce != cudaSuccess) return set_error(LRP_ERR_CUDA, cudaGetErrorString(ce));
   note_launch();  // the memset node
