@@ -9,7 +9,8 @@
 namespace lrp {
 
 constexpr int ATT_TILE = 128;       // query rows per CTA tile == keys per tile
-constexpr int ATT_THREADS = 160;
+constexpr int ATT_THREADS = 160;   // forward: 4 soft-max warps + 1 TMA/MMA warp
+constexpr int BWD_THREADS = 288;   // backward: 8 soft-max warps + 1 TMA/MMA warp
 constexpr float LOG2E = 1.4426950408889634f;
 constexpr float LN2 = 0.6931471805599453f;
 

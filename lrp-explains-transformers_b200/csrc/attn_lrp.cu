@@ -201,7 +201,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__
 // backward
 // =================================================================================================
 template <int D>
-__global__ void __launch_bounds__(ATT_THREADS, 1)
+__global__ void __launch_bounds__(BWD_THREADS, 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__ CUtensorMap tmk,
                 const __grid_constant__ CUtensorMap tmv, const __grid_constant__ CUtensorMap tmdo,
                 const AttnParams p) {
@@ -233,24 +233,24 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__
   const int ni = i_hi - i_lo + 1;
   const int n_it = ni > 0 ? ni * G : 0;
 
-  if (warp == 4 && lane == 0) {
+  if (warp == 8 && lane == 0) {
     tma_prefetch_desc(&tmq); tma_prefetch_desc(&tmk); tma_prefetch_desc(&tmv); tma_prefetch_desc(&tmdo);
     mbar_init(kv_full, 1);
     mbar_init(qdo_full, 1);
     mbar_init(s_full, 1);
-    mbar_init(p_full, 128);
+    mbar_init(p_full, 256);
     mbar_init(dq_full, 1);
-    mbar_init(dq_empty, 128);
+    mbar_init(dq_empty, 256);
     fence_barrier_init();
   }
-  if (warp == 4) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
+  if (warp == 8) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tmem_S = tmem_base, tmem_dP = tmem_base + 128, tmem_dV = tmem_base + 256, tmem_dK = tmem_base + 256 + D;
 
-  if (warp == 4) {
+  if (warp == 8) {
     if (lane == 0 && n_it > 0) {
       mbar_expect_tx(kv_full, 2 * TILE_BYTES);
       load_tile<D>(sK, &tmk, kv_full, hk * D, k0, b);
@@ -279,8 +279,11 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__
     }
     __syncwarp();
   } else {
-    const int r = warp * 32 + lane;
-    const uint32_t lane_base = uint32_t(warp * 32) << 16;
+    // 8 soft-max warps: warp w owns TMEM lane quarter w&3 and the 64-column half w>>2 of its rows (two warps per
+    // SM sub-partition hide each other's MUFU / TMEM latencies)
+    const int qd = warp & 3, ch = warp >> 2;
+    const int r = qd * 32 + lane;
+    const uint32_t lane_base = uint32_t(qd * 32) << 16;
     for (int it = 0; it < n_it; ++it) {
       const int g = it / ni, i = i_lo + (it - g * ni);
       const int h = hk * G + g;
@@ -303,7 +306,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__
       const bool mask_tile = need_mask || !__all_sync(0xffffffffu, row_ok);
       const float delta_s = delta * p.scale;
 #pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
+      for (int c = ch * 2; c < ch * 2 + 2; ++c) {
         uint32_t vs[32], vd[32];
         float fp[32], fd[32];
         tmem_ld32(tmem_S + lane_base + c * 32, vs);
@@ -323,7 +326,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__
       tc_fence_after();
       float* dqrow = p.dq_acc + ((int64_t(b) * p.S + qpos) * p.H + h) * D;
 #pragma unroll 1
-      for (int c = 0; c < D / 32; ++c) {
+      for (int c = ch; c < D / 32; c += 2) {
         uint32_t v[32];
         tmem_ld32(tmem_S + lane_base + c * 32, v);
         tmem_ld_wait();
@@ -351,7 +354,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__
         __nv_bfloat16* dst = which == 0 ? p.dv + (int64_t(b) * p.S + kpos) * p.lddv + hk * D
                                         : p.dk + (int64_t(b) * p.S + kpos) * p.lddk + hk * D;
 #pragma unroll 1
-        for (int c = 0; c < D / 32; ++c) {
+        for (int c = ch; c < D / 32; c += 2) {
           uint32_t v[32];
           tmem_ld32(src + lane_base + c * 32, v);
           tmem_ld_wait();
@@ -368,7 +371,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__
       }
     } else if (kpos < p.S) {
       // key tile attended by nobody (cannot happen with causal / full attention, kept for windowed edge cases)
-      for (int c = 0; c < D; c += 8) {
+      for (int c = ch * 8; c < D; c += 16) {
         *reinterpret_cast<uint4*>(p.dv + (int64_t(b) * p.S + kpos) * p.lddv + hk * D + c) = make_uint4(0, 0, 0, 0);
         *reinterpret_cast<uint4*>(p.dk + (int64_t(b) * p.S + kpos) * p.lddk + hk * D + c) = make_uint4(0, 0, 0, 0);
       }
@@ -376,7 +379,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) tmem_dealloc(tmem_base, 512);
+  if (warp == 8) tmem_dealloc(tmem_base, 512);
 }
 
 // delta[b,h,s] = sum_d o[b,s,h,d] * dO[b,s,h,d]   (one warp per row)
@@ -463,7 +466,7 @@ static int launch_bwd(const CUtensorMap& tq, const CUtensorMap& tk, const CUtens
     done = true;
   }
   dim3 grid((p.S + ATT_TILE - 1) / ATT_TILE, p.Hkv, p.B);
-  kern<<<grid, ATT_THREADS, bwd_smem_bytes<D>(), st>>>(tq, tk, tv, tdo, p);
+  kern<<<grid, BWD_THREADS, bwd_smem_bytes<D>(), st>>>(tq, tk, tv, tdo, p);
   LRP_CHECK_LAUNCH();
   return LRP_OK;
 }

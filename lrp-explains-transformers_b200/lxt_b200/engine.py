@@ -301,12 +301,11 @@ class LlamaAttnLRPEngine:
             nseg = math.ceil(m.L / seg)
             for sgi in range(nseg - 1, -1, -1):
                 lo, hi = sgi * seg, min(m.L, (sgi + 1) * seg)
-                if sgi != nseg - 1 or True:
-                    # recompute the segment's forward from its checkpoint (the last segment is still resident
-                    # only if L % seg == 0 and nothing overwrote it; recomputing keeps the logic uniform)
-                    h.copy_(ws["h_ckpt"][sgi])
-                    for l in range(lo, hi):
-                        self._layer_fwd(self.layers[l], ws["stores"][l % seg], h, ws, B, S)
+                # recompute this segment's forward from its checkpoint (uniformly, also for the last segment: its
+                # layer stores were overwritten unless L is a multiple of the segment length)
+                h.copy_(ws["h_ckpt"][sgi])
+                for l in range(lo, hi):
+                    self._layer_fwd(self.layers[l], ws["stores"][l % seg], h, ws, B, S)
                 for l in range(hi - 1, lo - 1, -1):
                     self._layer_bwd(self.layers[l], ws["stores"][l % seg], ws, B, S)
 
