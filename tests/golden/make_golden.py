@@ -248,8 +248,45 @@ def gen_llama_cp():
     print("llama_tiny_cp.npz rel norm", float(rel.norm()))
 
 
+def gen_gemma():
+    """Gemma-3 text model (sliding-window + global layers, q/k-norm, (1+w) RMSNorm, GELU-tanh gated MLP) under
+    lxt.efficient.monkey_patch(modeling_gemma3) — lxt/efficient/models/gemma3.py:11-19.  head_dim 64 (the B200 attention
+    tiles cover 64/128; Gemma's production head_dim 256 is a round-2 item)."""
+    from transformers import Gemma3TextConfig, Gemma3ForCausalLM
+    from transformers.models.gemma3 import modeling_gemma3
+    monkey_patch(modeling_gemma3, verbose=True)
+    cfg = Gemma3TextConfig(hidden_size=128, intermediate_size=256, num_hidden_layers=6, num_attention_heads=2,
+                           num_key_value_heads=1, head_dim=64, vocab_size=384, sliding_window=48, max_position_embeddings=512,
+                           query_pre_attn_scalar=64, rms_norm_eps=1e-6, tie_word_embeddings=True)
+    cfg._attn_implementation = "sdpa"
+    torch.manual_seed(11)
+    model = Gemma3ForCausalLM(cfg).float().eval()
+    g = torch.Generator().manual_seed(12)
+    sd = model.state_dict()
+    for k_, v_ in sd.items():
+        if "norm" in k_:
+            v_.copy_(0.1 * torch.randn(v_.shape, generator=g))
+        v_.copy_(v_.to(torch.bfloat16).float())   # bf16-representable weights
+    for p_ in model.parameters():
+        p_.requires_grad_(False)
+    ids = torch.randint(0, cfg.vocab_size, (2, 160), generator=torch.Generator().manual_seed(13))
+    emb = model.get_input_embeddings()(ids).detach().requires_grad_()
+    logits = model(inputs_embeds=emb, use_cache=False).logits
+    max_logits, max_idx = torch.max(logits[:, -1, :], dim=-1)
+    max_logits.sum().backward()
+    rel = (emb * emb.grad).float().sum(-1)
+    save = {"ids": ids.numpy(), "rel_fp32": rel.detach().numpy(), "idx": max_idx.numpy(), "layer_types": np.array(cfg.layer_types)}
+    for k_, v_ in model.state_dict().items():
+        save["sd_" + k_] = bf16_bits(v_)
+    np.savez_compressed(os.path.join(HERE, "gemma3_tiny.npz"), **save)
+    print("gemma3_tiny.npz", cfg.layer_types, "rel norm", float(rel.norm()))
+
+
 if __name__ == "__main__":
     torch.manual_seed(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "--gemma":
+        gen_gemma()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "--cp":
         gen_llama_cp()
         sys.exit(0)
