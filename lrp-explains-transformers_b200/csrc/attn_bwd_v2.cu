@@ -29,7 +29,9 @@ namespace lrp {
 constexpr int V2_THREADS = 288;
 constexpr int V2_SM_WARPS = 8;
 constexpr int QT = 64;   // kernel A: query rows per iteration;  kernel B: keys per iteration
-constexpr int NSTG = 3;  // TMA stages of the streamed operand pair
+// TMA stages of the streamed operand pair: 3 (software-pipelined issue order) for D <= 128; head_dim 256 only leaves
+// room for one stage, which forces the serial order  accumulate(it-1) -> load(it) -> S/dP(it).
+template <int D> struct V2Cfg { static constexpr int NSTG = D > 128 ? 1 : 3; static constexpr bool PIPE = NSTG > 1; };
 
 __device__ __forceinline__ void bar_sync_softmax() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
@@ -48,7 +50,8 @@ __device__ __forceinline__ void store_row_half_sw128(uint8_t* tile, int r, int c
 // =================================================================================================
 // kernel A: dK, dV
 // =================================================================================================
-template <int D>
+// MODE 0: dV and dK together (D <= 128);  MODE 1: dV only;  MODE 2: dK only  (D = 256: 256 TMEM columns per accumulator)
+template <int D, int MODE>
 __global__ void __launch_bounds__(V2_THREADS, 1)
 attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__ CUtensorMap tmk,
                      const __grid_constant__ CUtensorMap tmv, const __grid_constant__ CUtensorMap tmdo,
@@ -56,14 +59,17 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_const
   constexpr int KV_BYTES = ATT_TILE * D * 2;  // [128 keys][D]
   constexpr int QD_BYTES = QT * D * 2;        // [64 queries][D]
   constexpr int PT_BYTES = ATT_TILE * QT * 2; // [128 keys][64 queries]
+  constexpr int NSTG = V2Cfg<D>::NSTG;
+  constexpr bool PIPE = V2Cfg<D>::PIPE;
+  constexpr bool DO_V = MODE != 2, DO_K = MODE != 1;
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sK = smem;
   uint8_t* sV = sK + KV_BYTES;
   uint8_t* sQ = sV + KV_BYTES;                 // NSTG stages
   uint8_t* sdO = sQ + NSTG * QD_BYTES;         // NSTG stages
   uint8_t* sPt = sdO + NSTG * QD_BYTES;        // 2 buffers
-  uint8_t* sdSt = sPt + 2 * PT_BYTES;          // 2 buffers
-  float2* sLD = reinterpret_cast<float2*>(sdSt + 2 * PT_BYTES);  // [2][64] (lse*log2e, delta*scale) per query
+  uint8_t* sdSt = sPt + (DO_V ? 2 * PT_BYTES : 0);   // 2 buffers (each present only if its accumulator is)
+  float2* sLD = reinterpret_cast<float2*>(sdSt + (DO_K ? 2 * PT_BYTES : 0));  // [2][64] (lse*log2e, delta*scale) per query
   uint64_t* bars = reinterpret_cast<uint64_t*>(sLD + 2 * QT);
   uint64_t* kv_full = bars;
   uint64_t* qdo_full = bars + 1;             // [NSTG]
@@ -101,7 +107,7 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_const
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tmem_dV = tmem_base + 256, tmem_dK = tmem_base + 256 + D;
+  const uint32_t tmem_dV = tmem_base + 256, tmem_dK = tmem_base + 256 + (MODE == 0 ? D : 0);
   // S^T buffer b at columns [64 b, 64 b + 64), dP^T buffer b at [128 + 64 b, ...)
 
   if (warp == 8) {
@@ -116,46 +122,42 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_const
       mbar_expect_tx(kv_full, 2 * KV_BYTES);
       load_tile<D>(sK, &tmk, kv_full, hk * D, k0, b);
       load_tile<D>(sV, &tmv, kv_full, hk * D, k0, b);
+      auto accumulate = [&](int pit, bool last) {
+        const int ps = pit % NSTG, pb = pit & 1;
+        mbar_wait(&p_full[pb], (pit >> 1) & 1);
+        tc_fence_after();
+        // dV += P^T dO ; dK += dS^T Q     (A: [128 keys][64 q] K-major, B: [64 q][D] MN-major)
+        if (DO_V) mma_kmn<D, QT, QT * 128>(tmem_dV, smem_u32(sPt + pb * PT_BYTES), smem_u32(sdO + ps * QD_BYTES), pit > 0);
+        if (DO_K) mma_kmn<D, QT, QT * 128>(tmem_dK, smem_u32(sdSt + pb * PT_BYTES), smem_u32(sQ + ps * QD_BYTES), pit > 0);
+        if (last) {
+          tc_commit(done);
+        } else {
+          tc_commit(&p_empty[pb]);
+          tc_commit(&qdo_empty[ps]);
+        }
+      };
       for (int it = 0; it < min(NSTG - 1, n_it); ++it) issue_load(it);
       mbar_wait(kv_full, 0);
       for (int it = 0; it < n_it; ++it) {
         const int s = it % NSTG, tb = it & 1;
-        const bool dbg = p.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && it < 64;
-        if (dbg) p.dbg[it * 16 + 0] = clock64();
+        if (!PIPE) {
+          if (it >= 1) accumulate(it - 1, false);
+          issue_load(it);
+        }
         mbar_wait(&qdo_full[s], (it / NSTG) & 1);
-        if (dbg) p.dbg[it * 16 + 1] = clock64();
         mbar_wait(&st_empty[tb], ((it >> 1) & 1) ^ 1);
-        if (dbg) p.dbg[it * 16 + 2] = clock64();
         tc_fence_after();
         // S^T = K Q^T ; dP^T = V dO^T      (A: [128 keys][D] K-major, B: [64 queries][D] K-major)
         mma_kk<QT, D, 16384, QT * 128>(tmem_base + tb * QT, smem_u32(sK), smem_u32(sQ + s * QD_BYTES), false);
         mma_kk<QT, D, 16384, QT * 128>(tmem_base + 128 + tb * QT, smem_u32(sV), smem_u32(sdO + s * QD_BYTES), false);
         tc_commit(&st_full[tb]);
-        if (dbg) p.dbg[it * 16 + 3] = clock64();
-        if (it >= 1) {
-          const int pit = it - 1, ps = pit % NSTG, pb = pit & 1;
-          mbar_wait(&p_full[pb], (pit >> 1) & 1);
-          if (dbg) p.dbg[it * 16 + 4] = clock64();
-          tc_fence_after();
-          // dV += P^T dO ; dK += dS^T Q     (A: [128 keys][64 q] K-major, B: [64 q][D] MN-major)
-          mma_kmn<D, QT, QT * 128>(tmem_dV, smem_u32(sPt + pb * PT_BYTES), smem_u32(sdO + ps * QD_BYTES), pit > 0);
-          mma_kmn<D, QT, QT * 128>(tmem_dK, smem_u32(sdSt + pb * PT_BYTES), smem_u32(sQ + ps * QD_BYTES), pit > 0);
-          tc_commit(&p_empty[pb]);
-          tc_commit(&qdo_empty[ps]);
+        if (PIPE) {
+          if (it >= 1) accumulate(it - 1, false);
+          // prefetch ahead; its stage is released by the accumulate-MMAs just queued above
+          if (it + NSTG - 1 < n_it) issue_load(it + NSTG - 1);
         }
-        if (dbg) p.dbg[it * 16 + 5] = clock64();
-        // prefetch two iterations ahead; its stage is released by the accumulate-MMAs just queued above
-        if (it + NSTG - 1 < n_it) issue_load(it + NSTG - 1);
-        if (dbg) p.dbg[it * 16 + 6] = clock64();
       }
-      {
-        const int pit = n_it - 1, ps = pit % NSTG, pb = pit & 1;
-        mbar_wait(&p_full[pb], (pit >> 1) & 1);
-        tc_fence_after();
-        mma_kmn<D, QT, QT * 128>(tmem_dV, smem_u32(sPt + pb * PT_BYTES), smem_u32(sdO + ps * QD_BYTES), pit > 0);
-        mma_kmn<D, QT, QT * 128>(tmem_dK, smem_u32(sdSt + pb * PT_BYTES), smem_u32(sQ + ps * QD_BYTES), pit > 0);
-        tc_commit(done);
-      }
+      accumulate(n_it - 1, true);
     }
     __syncwarp();
   } else {
@@ -216,8 +218,8 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_const
       if (dbgt) p.dbg[it * 16 + 11] = clock64();
       mbar_wait(&p_empty[tb], ((it >> 1) & 1) ^ 1);
       if (dbgt) p.dbg[it * 16 + 12] = clock64();
-      store_row_half_sw128(sPt + tb * PT_BYTES, r, ch, fp);
-      store_row_half_sw128(sdSt + tb * PT_BYTES, r, ch, fd);
+      if (DO_V) store_row_half_sw128(sPt + tb * PT_BYTES, r, ch, fp);
+      if (DO_K) store_row_half_sw128(sdSt + tb * PT_BYTES, r, ch, fd);
       fence_proxy_async_smem();
       mbar_arrive(&p_full[tb]);
       if (dbgt) p.dbg[it * 16 + 13] = clock64();
@@ -227,7 +229,7 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_const
       mbar_wait(done, 0);
       tc_fence_after();
 #pragma unroll 1
-      for (int which = 0; which < 2; ++which) {
+      for (int which = (DO_V ? 0 : 1); which < (DO_K ? 2 : 1); ++which) {
         const uint32_t src = which == 0 ? tmem_dV : tmem_dK;
         const float sc = which == 0 ? p.inv_v_div : p.inv_k_div;
         __nv_bfloat16* dst = which == 0 ? p.dv + (int64_t(b) * p.S + key) * p.lddv + hk * D
@@ -250,8 +252,8 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_const
       }
     } else if (key < p.S) {
       for (int c = ch * 8; c < D; c += 16) {
-        *reinterpret_cast<uint4*>(p.dv + (int64_t(b) * p.S + key) * p.lddv + hk * D + c) = make_uint4(0, 0, 0, 0);
-        *reinterpret_cast<uint4*>(p.dk + (int64_t(b) * p.S + key) * p.lddk + hk * D + c) = make_uint4(0, 0, 0, 0);
+        if (DO_V) *reinterpret_cast<uint4*>(p.dv + (int64_t(b) * p.S + key) * p.lddv + hk * D + c) = make_uint4(0, 0, 0, 0);
+        if (DO_K) *reinterpret_cast<uint4*>(p.dk + (int64_t(b) * p.S + key) * p.lddk + hk * D + c) = make_uint4(0, 0, 0, 0);
       }
     }
   }
@@ -277,6 +279,8 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constan
   constexpr int QD_BYTES = ATT_TILE * D * 2;  // [128 queries][D]
   constexpr int KV_BYTES = QT * D * 2;        // [64 keys][D]
   constexpr int DS_BYTES = ATT_TILE * QT * 2; // [128 queries][64 keys]
+  constexpr int NSTG = V2Cfg<D>::NSTG;
+  constexpr bool PIPE = V2Cfg<D>::PIPE;
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sQ = smem;
   uint8_t* sdO = sQ + QD_BYTES;
@@ -334,10 +338,27 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constan
       mbar_expect_tx(qdo_full, 2 * QD_BYTES);
       load_tile<D>(sQ, &tmq, qdo_full, h * D, q0, b);
       load_tile<D>(sdO, &tmdo, qdo_full, h * D, q0, b);
+      auto accumulate = [&](int pj, bool last) {
+        const int ps = pj % NSTG, pb = pj & 1;
+        mbar_wait(&p_full[pb], (pj >> 1) & 1);
+        tc_fence_after();
+        // dQ += dS K      (A: [128 q][64 keys] K-major, B: [64 keys][D] MN-major)
+        mma_kmn<D, QT, QT * 128>(tmem_dQ, smem_u32(sdS + pb * DS_BYTES), smem_u32(sK + ps * KV_BYTES), pj > 0);
+        if (last) {
+          tc_commit(done);
+        } else {
+          tc_commit(&p_empty[pb]);
+          tc_commit(&kv_empty[ps]);
+        }
+      };
       for (int jj = 0; jj < min(NSTG - 1, n); ++jj) issue_load(jj);
       mbar_wait(qdo_full, 0);
       for (int jj = 0; jj < n; ++jj) {
         const int s = jj % NSTG, tb = jj & 1;
+        if (!PIPE) {
+          if (jj >= 1) accumulate(jj - 1, false);
+          issue_load(jj);
+        }
         mbar_wait(&kv_full[s], (jj / NSTG) & 1);
         mbar_wait(&st_empty[tb], ((jj >> 1) & 1) ^ 1);
         tc_fence_after();
@@ -345,24 +366,12 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constan
         mma_kk<QT, D, 16384, QT * 128>(tmem_base + tb * QT, smem_u32(sQ), smem_u32(sK + s * KV_BYTES), false);
         mma_kk<QT, D, 16384, QT * 128>(tmem_base + 128 + tb * QT, smem_u32(sdO), smem_u32(sV + s * KV_BYTES), false);
         tc_commit(&st_full[tb]);
-        if (jj >= 1) {
-          const int pj = jj - 1, ps = pj % NSTG, pb = pj & 1;
-          mbar_wait(&p_full[pb], (pj >> 1) & 1);
-          tc_fence_after();
-          // dQ += dS K      (A: [128 q][64 keys] K-major, B: [64 keys][D] MN-major)
-          mma_kmn<D, QT, QT * 128>(tmem_dQ, smem_u32(sdS + pb * DS_BYTES), smem_u32(sK + ps * KV_BYTES), pj > 0);
-          tc_commit(&p_empty[pb]);
-          tc_commit(&kv_empty[ps]);
+        if (PIPE) {
+          if (jj >= 1) accumulate(jj - 1, false);
+          if (jj + NSTG - 1 < n) issue_load(jj + NSTG - 1);
         }
-        if (jj + NSTG - 1 < n) issue_load(jj + NSTG - 1);
       }
-      {
-        const int pj = n - 1, ps = pj % NSTG, pb = pj & 1;
-        mbar_wait(&p_full[pb], (pj >> 1) & 1);
-        tc_fence_after();
-        mma_kmn<D, QT, QT * 128>(tmem_dQ, smem_u32(sdS + pb * DS_BYTES), smem_u32(sK + ps * KV_BYTES), pj > 0);
-        tc_commit(done);
-      }
+      accumulate(n - 1, true);
     }
     __syncwarp();
   } else {
@@ -431,28 +440,48 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constan
   if (warp == 8) tmem_dealloc(tmem_base, 512);
 }
 
+template <int D, int MODE>
+static int dkdv_smem() {
+  return 2 * ATT_TILE * D * 2 + 2 * V2Cfg<D>::NSTG * QT * D * 2 + (MODE == 0 ? 4 : 2) * ATT_TILE * QT * 2 + 2 * QT * 8 + 256;
+}
 template <int D>
-static int dkdv_smem() { return 2 * ATT_TILE * D * 2 + 2 * NSTG * QT * D * 2 + 4 * ATT_TILE * QT * 2 + 2 * QT * 8 + 256; }
-template <int D>
-static int dq_smem() { return 2 * ATT_TILE * D * 2 + 2 * NSTG * QT * D * 2 + 2 * ATT_TILE * QT * 2 + 256; }
+static int dq_smem() { return 2 * ATT_TILE * D * 2 + 2 * V2Cfg<D>::NSTG * QT * D * 2 + 2 * ATT_TILE * QT * 2 + 256; }
+
+template <int D, int MODE>
+static int launch_dkdv(const CUtensorMap& tq64, const CUtensorMap& tk128, const CUtensorMap& tv128, const CUtensorMap& tdo64,
+                       const AttnParams& p, cudaStream_t st) {
+  auto ka = attn_bwd_dkdv_kernel<D, MODE>;
+  static bool done = false;
+  if (!done) {
+    cudaError_t ce = cudaFuncSetAttribute(ka, cudaFuncAttributeMaxDynamicSharedMemorySize, dkdv_smem<D, MODE>());
+    if (ce != cudaSuccess) return set_error(LRP_ERR_CUDA, cudaGetErrorString(ce));
+    done = true;
+  }
+  const int tiles = (p.S + ATT_TILE - 1) / ATT_TILE;
+  ka<<<dim3(tiles, p.Hkv, p.B), V2_THREADS, dkdv_smem<D, MODE>(), st>>>(tq64, tk128, tv128, tdo64, p);
+  LRP_CHECK_LAUNCH();
+  return LRP_OK;
+}
 
 template <int D>
 static int launch_v2(const CUtensorMap& tq128, const CUtensorMap& tk128, const CUtensorMap& tv128, const CUtensorMap& tdo128,
                      const CUtensorMap& tq64, const CUtensorMap& tk64, const CUtensorMap& tv64, const CUtensorMap& tdo64,
                      const AttnParams& p, const DqParams& dqp, cudaStream_t st) {
-  auto ka = attn_bwd_dkdv_kernel<D>;
+  // kernel A streams 64-row query/dO tiles against a resident 128-key tile; kernel B the other way round
+  if (D <= 128) {
+    if (int e = launch_dkdv<D, 0>(tq64, tk128, tv128, tdo64, p, st)) return e;
+  } else {
+    if (int e = launch_dkdv<D, 1>(tq64, tk128, tv128, tdo64, p, st)) return e;   // dV pass
+    if (int e = launch_dkdv<D, 2>(tq64, tk128, tv128, tdo64, p, st)) return e;   // dK pass
+  }
   auto kb = attn_bwd_dq_kernel<D>;
   static bool done = false;
   if (!done) {
-    cudaError_t ce = cudaFuncSetAttribute(ka, cudaFuncAttributeMaxDynamicSharedMemorySize, dkdv_smem<D>());
-    if (ce == cudaSuccess) ce = cudaFuncSetAttribute(kb, cudaFuncAttributeMaxDynamicSharedMemorySize, dq_smem<D>());
+    cudaError_t ce = cudaFuncSetAttribute(kb, cudaFuncAttributeMaxDynamicSharedMemorySize, dq_smem<D>());
     if (ce != cudaSuccess) return set_error(LRP_ERR_CUDA, cudaGetErrorString(ce));
     done = true;
   }
   const int tiles = (p.S + ATT_TILE - 1) / ATT_TILE;
-  // kernel A streams 64-row query/dO tiles against a resident 128-key tile; kernel B the other way round
-  ka<<<dim3(tiles, p.Hkv, p.B), V2_THREADS, dkdv_smem<D>(), st>>>(tq64, tk128, tv128, tdo64, p);
-  LRP_CHECK_LAUNCH();
   if (dqp.inv_q_div != 0.f) {
     kb<<<dim3(tiles, p.H, p.B), V2_THREADS, dq_smem<D>(), st>>>(tq128, tk64, tv64, tdo128, p, dqp);
     LRP_CHECK_LAUNCH();
@@ -502,8 +531,9 @@ int attn_bwd_v2(const void* q, const void* k, const void* v, int64_t ldq, int64_
   dqp.dq = reinterpret_cast<__nv_bfloat16*>(dq);
   dqp.lddq = lddq;
   dqp.inv_q_div = q_div > 0.f ? 1.f / q_div : 0.f;
-  const int rc = D == 128 ? launch_v2<128>(tq128, tk128, tv128, tdo128, tq64, tk64, tv64, tdo64, p, dqp, st)
-                          : launch_v2<64>(tq128, tk128, tv128, tdo128, tq64, tk64, tv64, tdo64, p, dqp, st);
+  const int rc = D == 256   ? launch_v2<256>(tq128, tk128, tv128, tdo128, tq64, tk64, tv64, tdo64, p, dqp, st)
+                 : D == 128 ? launch_v2<128>(tq128, tk128, tv128, tdo128, tq64, tk64, tv64, tdo64, p, dqp, st)
+                            : launch_v2<64>(tq128, tk128, tv128, tdo128, tq64, tk64, tv64, tdo64, p, dqp, st);
   if (dbg_dev != nullptr) {
     static bool printed = false;
     long long h[64 * 16];

@@ -64,7 +64,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__
     mbar_init(o_full, 1);
     fence_barrier_init();
   }
-  if (warp == 4) { tmem_alloc(tmem_slot, 256); tmem_relinquish(); }
+  if (warp == 4) { tmem_alloc(tmem_slot, D > 128 ? 512 : 256); tmem_relinquish(); }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -194,7 +194,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) tmem_dealloc(tmem_base, 256);
+  if (warp == 4) tmem_dealloc(tmem_base, D > 128 ? 512 : 256);
 }
 
 // =================================================================================================
@@ -432,7 +432,7 @@ static int check_common(const void* q, const void* k, const void* v, int64_t ldq
                         int H, int Hkv, int D) {
   if (B <= 0 || S <= 0 || H <= 0 || Hkv <= 0) return set_error(LRP_ERR_ARG, "attn: empty problem");
   if (H % Hkv != 0) return set_error(LRP_ERR_ARG, "attn: H must be a multiple of Hkv");
-  if (D != 64 && D != 128) return set_error(LRP_ERR_ARG, "attn: head_dim must be 64 or 128");
+  if (D != 64 && D != 128 && D != 256) return set_error(LRP_ERR_ARG, "attn: head_dim must be 64, 128 or 256");
   if ((ldq % 8) || (ldk % 8) || (ldv % 8)) return set_error(LRP_ERR_ARG, "attn: row strides must be multiples of 8");
   if ((uintptr_t(q) & 15) || (uintptr_t(k) & 15) || (uintptr_t(v) & 15))
     return set_error(LRP_ERR_ARG, "attn: q/k/v must be 16-byte aligned");
@@ -482,7 +482,7 @@ int lrp_attn_fwd(const void* q, const void* k, const void* v, int64_t ldq, int64
   if (int e = check_common(q, k, v, ldq, ldk, ldv, B, S, H, Hkv, D)) return e;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   // key tile: 64 keys for D=128, 128 keys for D=64 -> 112 KiB of smem per CTA either way (2 CTAs per SM)
-  const int BN = D == 128 ? 64 : 128;
+  const int BN = D == 64 ? 128 : 64;   // head_dim 256: 208 KiB, one CTA per SM, 320 TMEM columns
   CUtensorMap tq, tk, tv;
   if (int e = make_tmap_3d_bf16(&tq, q, uint64_t(H) * D, S, B, ldq, uint64_t(S) * ldq, 64, ATT_TILE)) return e;
   if (int e = make_tmap_3d_bf16(&tk, k, uint64_t(Hkv) * D, S, B, ldk, uint64_t(S) * ldk, 64, BN)) return e;
@@ -494,7 +494,7 @@ int lrp_attn_fwd(const void* q, const void* k, const void* v, int64_t ldq, int64
   p.causal = causal; p.window = window;
   p.o = reinterpret_cast<__nv_bfloat16*>(o);
   p.lse = lse;
-  return D == 128 ? launch_fwd<128, 64>(tq, tk, tv, p, st) : launch_fwd<64, 128>(tq, tk, tv, p, st);
+  return D == 256 ? launch_fwd<256, 64>(tq, tk, tv, p, st) : D == 128 ? launch_fwd<128, 64>(tq, tk, tv, p, st) : launch_fwd<64, 128>(tq, tk, tv, p, st);
 }
 
 int lrp_attn_bwd(const void* q, const void* k, const void* v, int64_t ldq, int64_t ldk, int64_t ldv, const void* o,
@@ -518,7 +518,7 @@ int lrp_attn_bwd(const void* q, const void* k, const void* v, int64_t ldq, int64
   // Measured on B200 it is on par with / slightly slower than this single-kernel version (its 64-wide MMAs are
   // smem-operand bound and S/dP/exp are recomputed for dQ), so the single kernel stays the default.
   const char* sel = getenv("LRP_ATTN_BWD");
-  if (sel != nullptr && !strcmp(sel, "v2"))
+  if (D == 256 || (sel != nullptr && !strcmp(sel, "v2")))   // head_dim 256 exists only in the two-pass v2 form
     return attn_bwd_v2(q, k, v, ldq, ldk, ldv, d_o, lse, delta_ws, dq, dk, dv, lddq, lddk, lddv, B, S, H, Hkv, D, scale, causal,
                        window, q_div, k_div, v_div, st);
   cudaError_t ce = cudaMemsetAsync(dq_acc_ws, 0, size_t(rows) * D * sizeof(float), st);

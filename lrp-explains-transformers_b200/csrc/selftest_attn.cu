@@ -53,7 +53,7 @@ __global__ void ref_attn(const bf16* q, const bf16* k, const bf16* v, const bf16
     m = fmaxf(m, s * scale);
   }
   float l = 0;
-  float oacc[128];
+  float oacc[256];
   for (int d = 0; d < D; ++d) oacc[d] = 0;
   for (int j = 0; j < S; ++j) {
     if (masked(qi, j, causal, window)) continue;
@@ -228,10 +228,15 @@ int main(int argc, char** argv) {
   run_case(2, 197, 4, 4, 64, 0, 0, false);
   run_case(1, 520, 4, 1, 128, 1, 200, true);
   run_case(1, 640, 2, 2, 64, 1, 130, false);
+  run_case(1, 128, 1, 1, 256, 1, 0, false);
+  run_case(2, 300, 4, 2, 256, 1, 0, true);
+  run_case(1, 520, 2, 1, 256, 1, 200, true);
+  run_case(2, 197, 2, 2, 256, 0, 0, false);
   printf(g_fail ? "SELFTEST FAILED (%d)\n" : "SELFTEST PASSED\n", g_fail);
   if (perf) {
     perf_case(4, 2048, 32, 8, 128);
     perf_case(1, 512, 32, 4, 64);
+    perf_case(1, 8192, 8, 4, 256);
   }
   return g_fail ? 1 : 0;
 }

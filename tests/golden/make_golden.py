@@ -248,7 +248,7 @@ def gen_llama_cp():
     print("llama_tiny_cp.npz rel norm", float(rel.norm()))
 
 
-def gen_gemma():
+def gen_gemma(head_dim=64, name="gemma3_tiny"):
     """Gemma-3 text model (sliding-window + global layers, q/k-norm, (1+w) RMSNorm, GELU-tanh gated MLP) under
     lxt.efficient.monkey_patch(modeling_gemma3) — lxt/efficient/models/gemma3.py:11-19.  head_dim 64 (the B200 attention
     tiles cover 64/128; Gemma's production head_dim 256 is a round-2 item)."""
@@ -256,8 +256,8 @@ def gen_gemma():
     from transformers.models.gemma3 import modeling_gemma3
     monkey_patch(modeling_gemma3, verbose=True)
     cfg = Gemma3TextConfig(hidden_size=128, intermediate_size=256, num_hidden_layers=6, num_attention_heads=2,
-                           num_key_value_heads=1, head_dim=64, vocab_size=384, sliding_window=48, max_position_embeddings=512,
-                           query_pre_attn_scalar=64, rms_norm_eps=1e-6, tie_word_embeddings=True)
+                           num_key_value_heads=1, head_dim=head_dim, vocab_size=384, sliding_window=48, max_position_embeddings=512,
+                           query_pre_attn_scalar=head_dim, rms_norm_eps=1e-6, tie_word_embeddings=True)
     cfg._attn_implementation = "sdpa"
     torch.manual_seed(11)
     model = Gemma3ForCausalLM(cfg).float().eval()
@@ -278,14 +278,15 @@ def gen_gemma():
     save = {"ids": ids.numpy(), "rel_fp32": rel.detach().numpy(), "idx": max_idx.numpy(), "layer_types": np.array(cfg.layer_types)}
     for k_, v_ in model.state_dict().items():
         save["sd_" + k_] = bf16_bits(v_)
-    np.savez_compressed(os.path.join(HERE, "gemma3_tiny.npz"), **save)
-    print("gemma3_tiny.npz", cfg.layer_types, "rel norm", float(rel.norm()))
+    np.savez_compressed(os.path.join(HERE, f"{name}.npz"), **save)
+    print(f"{name}.npz", cfg.layer_types, "rel norm", float(rel.norm()))
 
 
 if __name__ == "__main__":
     torch.manual_seed(0)
     if len(sys.argv) > 1 and sys.argv[1] == "--gemma":
         gen_gemma()
+        gen_gemma(256, "gemma3_tiny_d256")   # Gemma's production head_dim
         sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "--cp":
         gen_llama_cp()
