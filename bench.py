@@ -275,7 +275,7 @@ def run_b200(args):
                      # per launch vs 1.31 GB algorithmic (A 134 MB + W 235 MB + C 940 MB): W panels re-streamed 8x via L2
                      "traffic": 2.94e9, "traffic_note": "bytes/launch, ncu --set full, gate|up fwd shape; algorithmic 1.31e9"},
     }
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:   # reported on rank 0 at N=1 only
         try:
             v, cores, desc, _ = cpu_reference_sample(dims, S)
             out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc}
