@@ -17,6 +17,29 @@ from .. import ops
 from .._capi import LrpError
 
 
+# Debug switch of the reference (lxt/explicit/functional.py:10-37, lxt/explicit/check.py:6-15): when set, every rule
+# redistributes the incoming relevance UNIFORMLY over its inputs so that conservation can be checked end to end.
+CONSERVATION_CHECK_FLAG = [False]
+
+
+def conservation_check_wrap(func):
+    """decorator for rule backwards: pass-through normally, uniform redistribution under `conservation_check()`"""
+
+    def wrapped(ctx, *out_relevance):
+        inp_relevance = func(ctx, *out_relevance)
+        if not CONSERVATION_CHECK_FLAG[0]:
+            return inp_relevance
+        total = sum(r.float().sum() for r in out_relevance if r is not None)
+        count = sum(r.numel() for r in inp_relevance if r is not None)
+        mean = total / count
+        if torch.isnan(mean).any():
+            raise ValueError(f"NaN at {func}")
+        return tuple(torch.full(r.shape, float(mean), dtype=r.dtype, device=r.device) if r is not None else None
+                     for r in inp_relevance)
+
+    return wrapped
+
+
 def _stabilize(input, epsilon=1e-6, inplace=False):
     """`z + eps` — no sign handling, exactly like the reference (functional.py:266-273)."""
     return input.add_(epsilon) if inplace else input + epsilon
@@ -44,6 +67,7 @@ class linear_epsilon_fn(Function):
         return out.view(*inputs.shape[:-1], weight.shape[0])
 
     @staticmethod
+    @conservation_check_wrap
     def backward(ctx, *out_relevance):
         inputs, weight, bias = ctx.saved_tensors
         R = out_relevance[0].reshape(-1, weight.shape[0])
@@ -82,6 +106,7 @@ class matmul_fn(Function):
         return out
 
     @staticmethod
+    @conservation_check_wrap
     def backward(ctx, *out_relevance):
         a, b, out = ctx.saved_tensors
         M, K = a.shape[-2:]
@@ -110,6 +135,7 @@ class softmax_fn(Function):
         return outputs
 
     @staticmethod
+    @conservation_check_wrap
     def backward(ctx, *out_relevance):
         inputs, outputs = ctx.saved_tensors
         dim = ctx.dim if ctx.dim >= 0 else inputs.dim() + ctx.dim
@@ -130,6 +156,7 @@ class add2_tensors_fn(Function):
         return outputs
 
     @staticmethod
+    @conservation_check_wrap
     def backward(ctx, *out_relevance):
         a, b = ctx.saved_tensors
         shape = torch.broadcast_shapes(a.shape, b.shape)
@@ -149,6 +176,7 @@ class rms_norm_identity_fn(Function):
         return weight * hs.to(hidden_states.dtype)
 
     @staticmethod
+    @conservation_check_wrap
     def backward(ctx, *out_relevance):
         return out_relevance + (None, None)
 
@@ -160,6 +188,7 @@ class mul2_fn(Function):
         return input_a * input_b
 
     @staticmethod
+    @conservation_check_wrap
     def backward(ctx, *out_relevance):
         r = ops.scale(out_relevance[0], 1.0 / len(ctx.requires_grads))
         return tuple(r if i in ctx.requires_grads else None for i in range(2)) + (None,)

@@ -13,6 +13,7 @@ from torch.autograd import Function
 
 from .. import ops
 from . import functional as lf
+from .functional import conservation_check_wrap
 
 
 class WrapModule(nn.Module):
@@ -29,6 +30,7 @@ class identity_fn(Function):
         return fn(input)
 
     @staticmethod
+    @conservation_check_wrap
     def backward(ctx, *out_relevance):
         return (None,) + out_relevance
 
@@ -39,6 +41,7 @@ class stop_relevance_fn(Function):
         return fn(input)
 
     @staticmethod
+    @conservation_check_wrap
     def backward(ctx, *out_relevance):
         return None, None
 
@@ -87,12 +90,14 @@ class epsilon_lrp_fn(Function):
         return (None, None) + tuple(next(rel) if r else None for r in ctx.requires_grads)
 
     @staticmethod
+    @conservation_check_wrap
     def backward(ctx, *out_relevance):
         return epsilon_lrp_fn._backward(ctx, out_relevance, False)
 
 
 class uniform_epsilon_lrp_fn(epsilon_lrp_fn):
     @staticmethod
+    @conservation_check_wrap
     def backward(ctx, *out_relevance):
         return epsilon_lrp_fn._backward(ctx, out_relevance, True)
 
@@ -134,6 +139,7 @@ class uniform_rule_fn(Function):
         return fn(*inputs)
 
     @staticmethod
+    @conservation_check_wrap
     def backward(ctx, *out_relevance):
         n = max(1, sum(ctx.requires_grads))
         r = ops.scale(out_relevance[0], 1.0 / n)

@@ -100,3 +100,27 @@ def test_shard_range_is_balanced_and_contiguous():
             assert all(spans[i][1] == spans[i + 1][0] for i in range(w - 1))
             sizes = [b - a for a, b in spans]
             assert max(sizes) - min(sizes) <= 1
+
+
+def test_conservation_check_flag_and_wrapper():
+    """lxt/explicit/check.py:6-15 + functional.py:12-37: uniform redistribution that conserves the relevance sum"""
+    from lxt_b200.explicit import functional as lf
+    from lxt_b200.explicit.check import conservation_check
+
+    class Ctx:
+        pass
+
+    @lf.conservation_check_wrap
+    def backward(ctx, *r):
+        return (r[0] * 2.0, None, r[0][:, :2] * 3.0)
+
+    R = torch.arange(12.0).reshape(3, 4)
+    out = backward(Ctx(), R)
+    assert torch.equal(out[0], R * 2) and out[1] is None
+    with conservation_check():
+        assert lf.CONSERVATION_CHECK_FLAG[0] is True
+        u = backward(Ctx(), R)
+        assert u[1] is None and u[0].shape == (3, 4) and u[2].shape == (3, 2)
+        assert abs(float(u[0].sum() + u[2].sum()) - float(R.sum())) < 1e-4     # conserved
+        assert float(u[0].max() - u[0].min()) == 0.0                               # uniform
+    assert lf.CONSERVATION_CHECK_FLAG[0] is False
