@@ -13,6 +13,7 @@
 //
 // Thread roles (160 threads): warps 0-3 own one query row each (row r <-> TMEM lane r, so soft-max needs no
 // shuffles); warp 4 lane 0 issues all TMA loads and all tcgen05.mma.
+#include <stdio.h>
 #include <stdlib.h>
 #include "attn_common.cuh"
 
@@ -258,23 +259,31 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__
       for (int it = 0; it < n_it; ++it) {
         const int g = it / ni, i = i_lo + (it - g * ni);
         const int h = hk * G + g;
+        const bool dbg = p.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && it < 64;
+        if (dbg) p.dbg[it * 16 + 0] = clock64();
         mbar_expect_tx(qdo_full, 2 * TILE_BYTES);
         load_tile<D>(sQ, &tmq, qdo_full, h * D, i * ATT_TILE, b);
         load_tile<D>(sdO, &tmdo, qdo_full, h * D, i * ATT_TILE, b);
         if (it == 0) mbar_wait(kv_full, 0);
         mbar_wait(qdo_full, it & 1);
+        if (dbg) p.dbg[it * 16 + 1] = clock64();
         if (it > 0) mbar_wait(dq_empty, (it - 1) & 1);
+        if (dbg) p.dbg[it * 16 + 2] = clock64();
         tc_fence_after();
         mma_kk<128, D>(tmem_S, smem_u32(sQ), smem_u32(sK), false);    // S  = Q K^T
         mma_kk<128, D>(tmem_dP, smem_u32(sdO), smem_u32(sV), false);  // dP = dO V^T
         tc_commit(s_full);
+        if (dbg) p.dbg[it * 16 + 3] = clock64();
         mbar_wait(p_full, it & 1);
+        if (dbg) p.dbg[it * 16 + 4] = clock64();
         tc_fence_after();
         mma_mnmn<D>(tmem_dV, smem_u32(sP), smem_u32(sdO), it > 0);    // dV += P^T dO
         mma_mnmn<D>(tmem_dK, smem_u32(sdS), smem_u32(sQ), it > 0);    // dK += dS^T Q
         mma_kmn<D>(tmem_S, smem_u32(sdS), smem_u32(sK), false);       // dQ  = dS K   (reuses the S columns)
         tc_commit(dq_full);
+        if (dbg) p.dbg[it * 16 + 5] = clock64();
         mbar_wait(dq_full, it & 1);  // Q/dO/P/dS smem reusable
+        if (dbg) p.dbg[it * 16 + 6] = clock64();
       }
     }
     __syncwarp();
@@ -298,7 +307,10 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__
       if (!row_ok) lse2 = 0.f;
       const bool need_mask = (p.causal && k0 + ATT_TILE - 1 > i * ATT_TILE) || (k0 + ATT_TILE > p.S) ||
                              (p.window > 0 && i * ATT_TILE + ATT_TILE - 1 - k0 >= p.window);
+      const bool dbgt = p.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && it < 64 && threadIdx.x == 0;
+      if (dbgt) p.dbg[it * 16 + 8] = clock64();
       mbar_wait(s_full, it & 1);
+      if (dbgt) p.dbg[it * 16 + 9] = clock64();
       tc_fence_after();
       int lo, hi;
       row_window(qpos, k0, p.S, p.causal, p.window, lo, hi);
@@ -322,19 +334,20 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__
       fence_proxy_async_smem();
       tc_fence_before();
       mbar_arrive(p_full);
+      if (dbgt) p.dbg[it * 16 + 10] = clock64();
       mbar_wait(dq_full, it & 1);
+      if (dbgt) p.dbg[it * 16 + 11] = clock64();
       tc_fence_after();
+      // dQ tile -> fp32 reductions into the dq workspace.  (Releasing the TMEM columns before issuing the reductions was
+      // tried and does not help: the red.global traffic saturates the SM's memory-instruction queue either way, see
+      // profiles/r01_attn_bwd_v1_timeline.txt.)
       float* dqrow = p.dq_acc + ((int64_t(b) * p.S + qpos) * p.H + h) * D;
 #pragma unroll 1
       for (int c = ch; c < D / 32; c += 2) {
         uint32_t v[32];
         tmem_ld32(tmem_S + lane_base + c * 32, v);
         tmem_ld_wait();
-#ifndef LRP_EXPERIMENT_NO_DQ_ATOMICS
         if (valid) {
-#else
-        if (valid && __uint_as_float(v[0]) == 123456.789f) {
-#endif
 #pragma unroll
           for (int q = 0; q < 8; ++q)
             red_add_v4(dqrow + c * 32 + q * 4, __uint_as_float(v[q * 4]), __uint_as_float(v[q * 4 + 1]),
@@ -343,6 +356,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__
       }
       tc_fence_before();
       mbar_arrive(dq_empty);
+      if (dbgt) p.dbg[it * 16 + 12] = clock64();
     }
     // dK, dV of this key tile
     const int kpos = k0 + r;
@@ -537,7 +551,30 @@ int lrp_attn_bwd(const void* q, const void* k, const void* v, int64_t ldq, int64
   p.lddk = lddk; p.lddv = lddv;
   p.inv_k_div = k_div > 0.f ? 1.f / k_div : 0.f;
   p.inv_v_div = v_div > 0.f ? 1.f / v_div : 0.f;
+  long long* dbg_dev = nullptr;
+  if (getenv("LRP_ATTN_DEBUG") != nullptr && int64_t(B) * S >= 4096) {
+    cudaMalloc(&dbg_dev, 64 * 16 * sizeof(long long));
+    cudaMemset(dbg_dev, 0, 64 * 16 * sizeof(long long));
+    p.dbg = dbg_dev;
+  }
   if (int e = (D == 128 ? launch_bwd<128>(tq, tk, tv, tdo, p, st) : launch_bwd<64>(tq, tk, tv, tdo, p, st))) return e;
+  if (dbg_dev != nullptr) {
+    static bool printed = false;
+    long long h[64 * 16];
+    cudaDeviceSynchronize();
+    cudaMemcpy(h, dbg_dev, sizeof(h), cudaMemcpyDeviceToHost);
+    cudaFree(dbg_dev);
+    if (!printed) {
+      printed = true;
+      printf("v1 it | ctl: load_wait dq_empty mma1 p_full mma2 dq_full | thr: wait_s compute+store wait_dq drain | iter\n");
+      for (int it = 1; it < 24; ++it) {
+        const long long* r = h + it * 16;
+        printf("%2d | %5lld %5lld %5lld %5lld %5lld %5lld | %5lld %5lld %5lld %5lld | %6lld\n", it, r[1] - r[0], r[2] - r[1], r[3] - r[2],
+               r[4] - r[3], r[5] - r[4], r[6] - r[5], r[9] - r[8], r[10] - r[9], r[11] - r[10], r[12] - r[11],
+               r[0] - (h + (it - 1) * 16)[0]);
+      }
+    }
+  }
   const int64_t tok = int64_t(B) * S;
   const int64_t total = tok * (HD / 8);
   int64_t g = (total + 255) / 256;
