@@ -282,8 +282,44 @@ def gen_gemma(head_dim=64, name="gemma3_tiny"):
     print(f"{name}.npz", cfg.layer_types, "rel norm", float(rel.norm()))
 
 
+def gen_gpt2():
+    """GPT-2 (LayerNorm + plain GELU MLP + Conv1D projections) under lxt.efficient.monkey_patch(modeling_gpt2) —
+    lxt/efficient/models/gpt2.py:11-32 (`mlp_forward`, `layer_norm_forward`, `patch_attention`)."""
+    from transformers import GPT2Config, GPT2LMHeadModel
+    from transformers.models.gpt2 import modeling_gpt2
+    monkey_patch(modeling_gpt2, verbose=True)
+    cfg = GPT2Config(n_embd=128, n_head=2, n_layer=2, vocab_size=384, n_positions=256, resid_pdrop=0.0, embd_pdrop=0.0, attn_pdrop=0.0)
+    cfg._attn_implementation = "sdpa"
+    torch.manual_seed(21)
+    model = GPT2LMHeadModel(cfg).float().eval()
+    sd = model.state_dict()
+    g = torch.Generator().manual_seed(22)
+    for k_, v_ in sd.items():
+        if v_.dtype.is_floating_point:
+            if "ln_" in k_ and k_.endswith("weight"):
+                v_.copy_(1 + 0.1 * torch.randn(v_.shape, generator=g))
+            v_.copy_(v_.to(torch.bfloat16).float())
+    for p_ in model.parameters():
+        p_.requires_grad_(False)
+    ids = torch.randint(0, cfg.vocab_size, (2, 144), generator=torch.Generator().manual_seed(23))
+    emb = model.transformer.wte(ids).detach().requires_grad_()
+    logits = model(inputs_embeds=emb, use_cache=False).logits
+    max_logits, max_idx = torch.max(logits[:, -1, :], dim=-1)
+    max_logits.sum().backward()
+    rel = (emb * emb.grad).float().sum(-1)
+    save = {"ids": ids.numpy(), "rel_fp32": rel.detach().numpy(), "idx": max_idx.numpy()}
+    for k_, v_ in model.state_dict().items():
+        if v_.dtype.is_floating_point:
+            save["sd_" + k_] = bf16_bits(v_)
+    np.savez_compressed(os.path.join(HERE, "gpt2_tiny.npz"), **save)
+    print("gpt2_tiny.npz rel norm", float(rel.norm()))
+
+
 if __name__ == "__main__":
     torch.manual_seed(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "--gpt2":
+        gen_gpt2()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "--gemma":
         gen_gemma()
         gen_gemma(256, "gemma3_tiny_d256")   # Gemma's production head_dim
