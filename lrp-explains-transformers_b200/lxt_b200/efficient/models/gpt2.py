@@ -1,22 +1,4 @@
-"""GPT-2 patch maps (reference lxt/efficient/models/gpt2.py:11-32): plain MLP + LayerNorm."""
-from functools import partial
+"""GPT-2: LayerNorm + plain GELU MLP (reference lxt/efficient/models/gpt2.py)."""
+from ._families import plain_decoder_maps
 
-from torch.nn import Dropout, LayerNorm
-from transformers.models.gpt2 import modeling_gpt2
-from transformers.models.gpt2.modeling_gpt2 import GPT2MLP
-
-from ..patches import (dropout_forward, layer_norm_forward, mlp_forward, patch_attention, patch_cp_attention, patch_method)
-
-attnLRP = {
-    GPT2MLP: partial(patch_method, mlp_forward),
-    LayerNorm: partial(patch_method, layer_norm_forward),
-    Dropout: partial(patch_method, dropout_forward),
-    modeling_gpt2: patch_attention,
-}
-
-cp_LRP = {
-    GPT2MLP: partial(patch_method, mlp_forward),
-    LayerNorm: partial(patch_method, layer_norm_forward),
-    Dropout: partial(patch_method, dropout_forward),
-    modeling_gpt2: patch_cp_attention,
-}
+modeling_gpt2, attnLRP, cp_LRP = plain_decoder_maps("gpt2", "GPT2MLP")

@@ -1,25 +1,4 @@
-"""Qwen2 patch maps (reference lxt/efficient/models/qwen2.py) — same rule set as Llama."""
-from functools import partial
+"""Qwen2: same rule set as Llama (reference lxt/efficient/models/qwen2.py)."""
+from ._families import gated_decoder_maps
 
-from torch.nn import Dropout, Linear
-from transformers.models.qwen2 import modeling_qwen2
-from transformers.models.qwen2.modeling_qwen2 import Qwen2MLP, Qwen2RMSNorm
-
-from ..patches import (cp_gated_mlp_forward, dropout_forward, gated_mlp_forward, linear_forward, patch_attention,
-                       patch_cp_attention, patch_method, rms_norm_forward)
-
-attnLRP = {
-    Qwen2MLP: partial(patch_method, gated_mlp_forward),
-    Qwen2RMSNorm: partial(patch_method, rms_norm_forward),
-    Dropout: partial(patch_method, dropout_forward),
-    Linear: partial(patch_method, linear_forward, keep_original=True),
-    modeling_qwen2: patch_attention,
-}
-
-cp_LRP = {
-    Qwen2MLP: partial(patch_method, cp_gated_mlp_forward),
-    Qwen2RMSNorm: partial(patch_method, rms_norm_forward),
-    Dropout: partial(patch_method, dropout_forward),
-    Linear: partial(patch_method, linear_forward, keep_original=True),
-    modeling_qwen2: patch_cp_attention,
-}
+modeling_qwen2, attnLRP, cp_LRP = gated_decoder_maps("qwen2", "Qwen2MLP", "Qwen2RMSNorm")
