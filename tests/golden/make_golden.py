@@ -315,8 +315,53 @@ def gen_gpt2():
     print("gpt2_tiny.npz rel norm", float(rel.norm()))
 
 
+def gen_qwen():
+    """Qwen2 (q/k/v biases) and Qwen3 (per-head q/k RMSNorm) under the reference's default maps
+    (lxt/efficient/models/qwen2.py, qwen3.py) — same rule set as Llama."""
+    import warnings
+    from transformers import Qwen2Config, Qwen2ForCausalLM, Qwen3Config, Qwen3ForCausalLM
+    from transformers.models.qwen2 import modeling_qwen2
+    from transformers.models.qwen3 import modeling_qwen3
+    for name, Cfg, Model, modeling in (("qwen2_tiny", Qwen2Config, Qwen2ForCausalLM, modeling_qwen2),
+                                       ("qwen3_tiny", Qwen3Config, Qwen3ForCausalLM, modeling_qwen3)):
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            monkey_patch(modeling, verbose=True)
+        kw = dict(hidden_size=128, intermediate_size=256, num_hidden_layers=2, num_attention_heads=2, num_key_value_heads=1,
+                  vocab_size=384, max_position_embeddings=512, rms_norm_eps=1e-6, tie_word_embeddings=False)
+        if Cfg is Qwen3Config:
+            kw["head_dim"] = 64
+        cfg = Cfg(**kw)
+        cfg._attn_implementation = "sdpa"
+        torch.manual_seed(31)
+        model = Model(cfg).float().eval()
+        g = torch.Generator().manual_seed(32)
+        for k_, v_ in model.state_dict().items():
+            if "norm" in k_:
+                v_.copy_(1 + 0.1 * torch.randn(v_.shape, generator=g))
+            if k_.endswith("bias"):
+                v_.copy_(0.05 * torch.randn(v_.shape, generator=g))
+            v_.copy_(v_.to(torch.bfloat16).float())
+        for p_ in model.parameters():
+            p_.requires_grad_(False)
+        ids = torch.randint(0, cfg.vocab_size, (2, 144), generator=torch.Generator().manual_seed(33))
+        emb = model.get_input_embeddings()(ids).detach().requires_grad_()
+        logits = model(inputs_embeds=emb, use_cache=False).logits
+        max_logits, max_idx = torch.max(logits[:, -1, :], dim=-1)
+        max_logits.sum().backward()
+        rel = (emb * emb.grad).float().sum(-1)
+        save = {"ids": ids.numpy(), "rel_fp32": rel.detach().numpy(), "idx": max_idx.numpy()}
+        for k_, v_ in model.state_dict().items():
+            save["sd_" + k_] = bf16_bits(v_)
+        np.savez_compressed(os.path.join(HERE, f"{name}.npz"), **save)
+        print(f"{name}.npz rel norm", float(rel.norm()), "biases:", sum(k_.endswith("bias") for k_ in model.state_dict()))
+
+
 if __name__ == "__main__":
     torch.manual_seed(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "--qwen":
+        gen_qwen()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "--gpt2":
         gen_gpt2()
         sys.exit(0)
