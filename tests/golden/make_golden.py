@@ -178,7 +178,8 @@ def gen_llama(name, cfg, B, S, seed):
             res[f"trace_{tag}_{impl}"] = torch.stack([(t * t.grad).float().sum(-1) for t in kept]).detach().numpy()
             res[f"rel_{tag}_{impl}"] = rel.detach().numpy()
             res[f"idx_{tag}_{impl}"] = max_idx.numpy()
-            res[f"gemb_{tag}_{impl}"] = emb.grad.float().numpy()
+            if tag == "fp32" and impl == "sdpa":
+                res[f"gemb_{tag}_{impl}"] = emb.grad.float().numpy()
     print(name, "sdpa-vs-eager fp32 rel diff",
           float(np.linalg.norm(res["rel_fp32_sdpa"] - res["rel_fp32_eager"]) / np.linalg.norm(res["rel_fp32_eager"])),
           " bf16-vs-fp32", float(np.linalg.norm(res["rel_bf16_sdpa"] - res["rel_fp32_sdpa"]) / np.linalg.norm(res["rel_fp32_sdpa"])))
