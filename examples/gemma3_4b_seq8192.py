@@ -43,6 +43,17 @@ def main(S=8192, layers=34):
     rel = once()
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
+    # the fused engine on the same weights (no autograd, fused epilogues, last-position lm_head)
+    from lxt_b200.engine import LlamaAttnLRPEngine
+    eng = LlamaAttnLRPEngine.from_hf(model, micro_batch=1)
+    r_eng = eng.attribute_device(ids)
+    torch.cuda.synchronize()
+    t1 = time.perf_counter()
+    r_eng = eng.attribute_device(ids)
+    torch.cuda.synchronize()
+    dt_eng = time.perf_counter() - t1
+    rl2 = float((r_eng.double() - rel.double()).norm() / rel.double().norm())
+    print(f"fused engine: {dt_eng * 1e3:.0f} ms per attribution = {1 / dt_eng:.2f} attributions/s; rel-L2 engine vs drop-in path {rl2:.2e}")
     print(f"Gemma-3-4B dims, {layers} layers ({cfg.layer_types.count('full_attention')} global), S={S}, B=1: {dt * 1e3:.0f} ms per attribution "
           f"= {1 / dt:.2f} attributions/s ({ops.launch_count() - n0} B200 kernel launches); relevance {tuple(rel.shape)}, "
           f"finite={bool(torch.isfinite(rel).all())}, peak memory {torch.cuda.max_memory_allocated() / 2**30:.1f} GiB")

@@ -107,6 +107,16 @@ int lrp_rmsnorm_fwd(const void* x, int x_is_f32, const void* w, float w_offset, 
 int lrp_rmsnorm_bwd(const void* gy, const void* w, float w_offset, const float* rstd, void* gx, int gx_is_f32,
                     int accumulate, int T, int d, void* stream);
 
+/* Gemma layer layout `h = residual + post_norm(branch)`: h[t,:] += rmsnorm(y[t,:]) * (w + w_offset), rstd of y saved
+ * (transformers modeling_gemma3.py Gemma3DecoderLayer.forward; the backward of the norm is lrp_rmsnorm_bwd). y,w bf16, h fp32. */
+int lrp_rmsnorm_fwd_residual(const void* y, const void* w, float w_offset, float eps, float* h, float* rstd, int T, int d,
+                             void* stream);
+/* Per-head RMSNorm over D of the q and k slices of a packed [T, ld] bf16 buffer, in place (Gemma-3 / Qwen3 q_norm, k_norm):
+ * heads [0, n_q_heads) use wq, the next n_k_heads use wk.  backward = 0: normalise and save rstd [T, n_q+n_k];
+ * backward = 1: identity rule g <- g * (w + w_offset) * rstd with the saved rstd. */
+int lrp_headnorm_inplace(void* qk, int64_t ld, int n_q_heads, int n_k_heads, int D, const void* wq, const void* wk,
+                         float w_offset, float eps, float* rstd, int T, int backward, void* stream);
+
 /* LayerNorm with detached std (lxt/efficient/patches.py:126-142 `layer_norm_forward`); x,w,b,y all bf16 or
  * all fp32 (is_f32).
  *   fwd: y = (x-mean)/sqrt(var+eps) * w + b ; saves mean,rstd.  bwd: g_x = (g_y*w*rstd) - mean_d(g_y*w*rstd) */

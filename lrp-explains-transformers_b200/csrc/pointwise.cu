@@ -109,6 +109,74 @@ __global__ void __launch_bounds__(NORM_THREADS) rmsnorm_bwd_kernel(const __nv_bf
   }
 }
 
+// h[t,:] += (y[t,:] * rsqrt(mean(y^2)+eps)) * (w_offset + w)   — Gemma's post-branch RMSNorm fused with the residual add
+// (HF Gemma3DecoderLayer: hidden = residual + post_norm(branch)); rstd of the branch output saved for the backward.
+__global__ void __launch_bounds__(NORM_THREADS) rmsnorm_fwd_residual_kernel(const __nv_bfloat16* __restrict__ y,
+                                                                            const __nv_bfloat16* __restrict__ w,
+                                                                            float w_offset, float eps, float* __restrict__ h,
+                                                                            float* __restrict__ rstd_out, int d) {
+  __shared__ float red[NORM_THREADS / 32];
+  const int64_t row = blockIdx.x;
+  const __nv_bfloat16* yr = y + row * d;
+  float ss = 0.f;
+  for (int i = threadIdx.x * 8; i < d; i += NORM_THREADS * 8) {
+    float f[8];
+    load8(yr + i, f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) ss += f[j] * f[j];
+  }
+  ss = block_sum<NORM_THREADS>(ss, red);
+  const float rstd = rsqrtf(ss / float(d) + eps);
+  if (threadIdx.x == 0) rstd_out[row] = rstd;
+  for (int i = threadIdx.x * 8; i < d; i += NORM_THREADS * 8) {
+    float f[8], wf[8], o[8];
+    load8(yr + i, f);
+    load8(w + i, wf);
+    load8(h + row * d + i, o);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] += (f[j] * rstd) * (w_offset + wf[j]);
+    store8(h + row * d + i, o);
+  }
+}
+
+// Per-head RMSNorm over D on the q and k slices of a packed qkv buffer, in place (Gemma-3 / Qwen3 q_norm, k_norm), one
+// warp per (token, head).  backward = 0: x <- x * rstd * (off + w), rstd saved [T, n_heads];
+// backward = 1 (identity rule): g <- g * (off + w) * rstd with the saved rstd.
+__global__ void __launch_bounds__(256) headnorm_kernel(__nv_bfloat16* __restrict__ qk, int64_t ld, int n_q, int n_heads, int D,
+                                                       const __nv_bfloat16* __restrict__ wq, const __nv_bfloat16* __restrict__ wk,
+                                                       float w_offset, float eps, float* __restrict__ rstd, int64_t T, int backward) {
+  const int64_t row = blockIdx.x * int64_t(blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= T * n_heads) return;
+  const int lane = threadIdx.x & 31;
+  const int64_t t = row / n_heads;
+  const int hd = int(row - t * n_heads);
+  __nv_bfloat16* p = qk + t * ld + int64_t(hd) * D;
+  const __nv_bfloat16* w = hd < n_q ? wq : wk;
+  float r;
+  if (!backward) {
+    float ss = 0.f;
+    for (int i = lane * 8; i < D; i += 256) {
+      float f[8];
+      load8(p + i, f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) ss += f[j] * f[j];
+    }
+    ss = warp_sum(ss);
+    r = rsqrtf(ss / float(D) + eps);
+    if (lane == 0) rstd[row] = r;
+  } else {
+    r = rstd[row];
+  }
+  for (int i = lane * 8; i < D; i += 256) {
+    float f[8], wf[8];
+    load8(p + i, f);
+    load8(w + i, wf);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) f[j] = f[j] * r * (w_offset + wf[j]);
+    store8(p + i, f);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // LayerNorm with detached std (ViT path), bf16 or fp32 rows
 // ------------------------------------------------------------------------------------------------
@@ -490,6 +558,26 @@ int lrp_rmsnorm_bwd(const void* gy, const void* w, float w_offset, const float* 
     rmsnorm_bwd_kernel<float><<<T, NORM_THREADS, 0, st>>>((const bf16*)gy, (const bf16*)w, w_offset, rstd, (float*)gx, accumulate, d);
   else
     rmsnorm_bwd_kernel<bf16><<<T, NORM_THREADS, 0, st>>>((const bf16*)gy, (const bf16*)w, w_offset, rstd, (bf16*)gx, accumulate, d);
+  LRP_CHECK_LAUNCH();
+  return LRP_OK;
+}
+
+int lrp_rmsnorm_fwd_residual(const void* y, const void* w, float w_offset, float eps, float* h, float* rstd, int T, int d,
+                             void* stream) {
+  if (T <= 0 || d <= 0 || (d % 8) != 0) return set_error(LRP_ERR_ARG, "rmsnorm_fwd_residual: d must be a positive multiple of 8");
+  rmsnorm_fwd_residual_kernel<<<T, NORM_THREADS, 0, static_cast<cudaStream_t>(stream)>>>((const bf16*)y, (const bf16*)w, w_offset,
+                                                                                        eps, h, rstd, d);
+  LRP_CHECK_LAUNCH();
+  return LRP_OK;
+}
+
+int lrp_headnorm_inplace(void* qk, int64_t ld, int n_q_heads, int n_k_heads, int D, const void* wq, const void* wk,
+                         float w_offset, float eps, float* rstd, int T, int backward, void* stream) {
+  if (T <= 0 || n_q_heads < 0 || n_k_heads < 0 || n_q_heads + n_k_heads <= 0 || D <= 0 || (D % 8) != 0 || (ld % 8) != 0)
+    return set_error(LRP_ERR_ARG, "headnorm: D and ld must be multiples of 8");
+  const int64_t rows = int64_t(T) * (n_q_heads + n_k_heads);
+  headnorm_kernel<<<unsigned((rows + 7) / 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      (bf16*)qk, ld, n_q_heads, n_q_heads + n_k_heads, D, (const bf16*)wq, (const bf16*)wk, w_offset, eps, rstd, T, backward);
   LRP_CHECK_LAUNCH();
   return LRP_OK;
 }

@@ -53,6 +53,8 @@ SIGNATURES = {
     "lrp_linear_eps_flags_count": (_i64, [_i]),
     "lrp_rmsnorm_fwd": (_i, [_vp, _i, _vp, _f, _f, _vp, _vp, _i, _i, _vp]),
     "lrp_rmsnorm_bwd": (_i, [_vp, _vp, _f, _vp, _vp, _i, _i, _i, _i, _vp]),
+    "lrp_rmsnorm_fwd_residual": (_i, [_vp, _vp, _f, _f, _vp, _vp, _i, _i, _vp]),
+    "lrp_headnorm_inplace": (_i, [_vp, _i64, _i, _i, _i, _vp, _vp, _f, _f, _vp, _i, _i, _vp]),
     "lrp_layernorm_fwd": (_i, [_vp, _vp, _vp, _f, _vp, _vp, _vp, _i, _i, _i, _vp]),
     "lrp_layernorm_bwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
     "lrp_rope_inplace": (_i, [_vp, _i64, _i, _i, _vp, _vp, _i, _i, _i, _vp]),

@@ -30,7 +30,7 @@ from __future__ import annotations
 
 import math
 from dataclasses import dataclass
-from typing import Dict, List, Optional
+from typing import Dict, List, Optional, Sequence
 
 import torch
 
@@ -39,6 +39,8 @@ from . import ops
 
 @dataclass
 class LlamaDims:
+    """Decoder description.  The defaults are the Llama layout; the optional fields describe Gemma-3 / Qwen3 variants
+    (reference maps lxt/efficient/models/{llama,gemma3,qwen3}.py share one rule set)."""
     d: int
     I: int
     H: int
@@ -48,18 +50,48 @@ class LlamaDims:
     V: int
     eps: float = 1e-5
     theta: float = 10000.0
+    norm_offset: float = 0.0          # RMSNorm weight offset: 0 = `w * x_hat` (Llama), 1 = `(1 + w) * x_hat` (Gemma)
+    act: str = "silu"                 # gated-MLP activation: "silu" | "gelu_tanh"
+    qk_norm: bool = False             # per-head RMSNorm on q and k before RoPE (weights 'qn', 'kn')
+    post_norms: bool = False          # Gemma layer layout: h += post_norm(branch(pre_norm(h)))
+    windows: Optional[Sequence[int]] = None   # per-layer sliding window (0 = global attention)
+    thetas: Optional[Sequence[float]] = None  # per-layer RoPE base
+    attn_scale: Optional[float] = None        # soft-max scale (default D^-0.5; Gemma: query_pre_attn_scalar^-0.5)
+    emb_scale: float = 1.0                    # embedding multiplier (Gemma: sqrt(d))
 
     @property
     def qkv_width(self) -> int:
         return (self.H + 2 * self.Hkv) * self.D
 
+    def window(self, l: int) -> int:
+        return int(self.windows[l]) if self.windows else 0
+
+    def layer_theta(self, l: int) -> float:
+        return float(self.thetas[l]) if self.thetas else self.theta
+
+    @property
+    def act_code(self) -> int:
+        return {"silu": ops.ACT_SILU, "gelu_tanh": ops.ACT_GELU_TANH}[self.act]
+
+
+DecoderDims = LlamaDims
+
+
+def gemma3_dims(d, I, H, Hkv, D, L, V, sliding_window=1024, pattern=6, eps=1e-6) -> "LlamaDims":
+    """Gemma-3 text layout: `pattern-1` sliding-window layers then one global layer, local / global RoPE bases 1e4 / 1e6."""
+    glob = [(l + 1) % pattern == 0 for l in range(L)]
+    return LlamaDims(d=d, I=I, H=H, Hkv=Hkv, D=D, L=L, V=V, eps=eps, norm_offset=1.0, act="gelu_tanh", qk_norm=True, post_norms=True,
+                     windows=[0 if g else sliding_window for g in glob], thetas=[1000000.0 if g else 10000.0 for g in glob],
+                     attn_scale=float(D) ** -0.5, emb_scale=float(d) ** 0.5)
+
 
 LLAMA3_8B = LlamaDims(d=4096, I=14336, H=32, Hkv=8, D=128, L=32, V=128256, eps=1e-5, theta=500000.0)
 TINYLLAMA_1B = LlamaDims(d=2048, I=5632, H=32, Hkv=4, D=64, L=22, V=32000, eps=1e-5, theta=10000.0)
+GEMMA3_4B = gemma3_dims(d=2560, I=10240, H=8, Hkv=4, D=256, L=34, V=262208)
 
 
 class _LayerStore:
-    __slots__ = ("qkv", "o", "lse", "gu", "rstd1", "rstd2")
+    __slots__ = ("qkv", "o", "lse", "gu", "rstd1", "rstd2", "rstd_qk", "rstd_pa", "rstd_pf")
 
 
 class LlamaAttnLRPEngine:
@@ -87,11 +119,17 @@ class LlamaAttnLRPEngine:
         for lw in weights["layers"]:
             wqkv = torch.cat([lw["wq"], lw["wk"], lw["wv"]], dim=0)
             wgu = torch.cat([lw["wg"], lw["wu"]], dim=0)
-            self.layers.append(dict(wqkv=bf(wqkv), wo=bf(lw["wo"]), wgu=bf(wgu), wd=bf(lw["wd"]), ln1=bf(lw["ln1"]),
-                                    ln2=bf(lw["ln2"]), ln1_f=f32(bf(lw["ln1"])), ln2_f=f32(bf(lw["ln2"]))))
+            ln2 = lw["ln_pre_ff"] if dims.post_norms else lw["ln2"]
+            layer = dict(wqkv=bf(wqkv), wo=bf(lw["wo"]), wgu=bf(wgu), wd=bf(lw["wd"]), ln1=bf(lw["ln1"]), ln2=bf(ln2),
+                         ln1_f=f32(bf(lw["ln1"])) + dims.norm_offset, ln2_f=f32(bf(ln2)) + dims.norm_offset)
+            if dims.qk_norm:
+                layer.update(qn=bf(lw["qn"]), kn=bf(lw["kn"]))
+            if dims.post_norms:
+                layer.update(ln_post_attn=bf(lw["ln_post_attn"]), ln_post_ff=bf(lw["ln_post_ff"]))
+            self.layers.append(layer)
         self._ws_key = None
         self._ws = None
-        self._rope_key = None
+        self._rope_cache = {}
         # cuda_graph=True captures the whole attribution (≈20 launches per layer) of a given [B,S] once and replays it:
         # small / latency-bound shapes (e.g. TinyLlama, B=1, S=512) stop being bound by host launch overhead.
         self.cuda_graph = cuda_graph
@@ -104,22 +142,45 @@ class LlamaAttnLRPEngine:
 
     @classmethod
     def from_hf(cls, model, device="cuda", **kw):
-        """Build from a HuggingFace LlamaForCausalLM (weights are copied to bf16 on the device)."""
+        """Build from a HuggingFace causal LM of the Llama, Qwen3 or Gemma-3 (text) family; weights are copied to bf16."""
         c = model.config
+        mt = getattr(c, "model_type", "llama")
         D = getattr(c, "head_dim", None) or c.hidden_size // c.num_attention_heads
-        theta = (getattr(c, "rope_parameters", None) or {}).get("rope_theta", getattr(c, "rope_theta", 10000.0))
+        rp = getattr(c, "rope_parameters", None) or {}
+        theta = rp.get("rope_theta") or getattr(c, "rope_theta", None) or 10000.0
+        extra = {}
+        if mt.startswith("gemma3"):
+            lt = list(c.layer_types)
+            th = lambda kind: float((rp.get(kind) or {}).get("rope_theta", 10000.0 if kind == "sliding_attention" else 1000000.0))
+            extra = dict(norm_offset=1.0, act="gelu_tanh", qk_norm=True, post_norms=True,
+                         windows=[int(c.sliding_window) if t == "sliding_attention" else 0 for t in lt],
+                         thetas=[th(t) for t in lt], attn_scale=float(c.query_pre_attn_scalar) ** -0.5,
+                         emb_scale=float(c.hidden_size) ** 0.5)
+        elif mt == "qwen3":
+            extra = dict(qk_norm=True)
+        elif mt not in ("llama",):
+            raise ValueError(f"LlamaAttnLRPEngine.from_hf: unsupported model_type {mt!r} (use the drop-in monkey_patch API)")
         dims = LlamaDims(d=c.hidden_size, I=c.intermediate_size, H=c.num_attention_heads, Hkv=c.num_key_value_heads, D=D,
-                         L=c.num_hidden_layers, V=c.vocab_size, eps=c.rms_norm_eps, theta=theta)
+                         L=c.num_hidden_layers, V=c.vocab_size, eps=c.rms_norm_eps, theta=float(theta), **extra)
         sd = model.state_dict()
+        if any(k.endswith("self_attn.q_proj.bias") for k in sd):
+            raise ValueError("projection biases are not supported by the fused engine (use the drop-in monkey_patch API)")
         w = dict(emb=sd["model.embed_tokens.weight"], norm=sd["model.norm.weight"],
                  lm_head=sd.get("lm_head.weight", sd["model.embed_tokens.weight"]), layers=[])
         for i in range(dims.L):
             p = f"model.layers.{i}."
-            w["layers"].append(dict(wq=sd[p + "self_attn.q_proj.weight"], wk=sd[p + "self_attn.k_proj.weight"],
-                                    wv=sd[p + "self_attn.v_proj.weight"], wo=sd[p + "self_attn.o_proj.weight"],
-                                    wg=sd[p + "mlp.gate_proj.weight"], wu=sd[p + "mlp.up_proj.weight"],
-                                    wd=sd[p + "mlp.down_proj.weight"], ln1=sd[p + "input_layernorm.weight"],
-                                    ln2=sd[p + "post_attention_layernorm.weight"]))
+            lw = dict(wq=sd[p + "self_attn.q_proj.weight"], wk=sd[p + "self_attn.k_proj.weight"],
+                      wv=sd[p + "self_attn.v_proj.weight"], wo=sd[p + "self_attn.o_proj.weight"],
+                      wg=sd[p + "mlp.gate_proj.weight"], wu=sd[p + "mlp.up_proj.weight"],
+                      wd=sd[p + "mlp.down_proj.weight"], ln1=sd[p + "input_layernorm.weight"])
+            if dims.qk_norm:
+                lw.update(qn=sd[p + "self_attn.q_norm.weight"], kn=sd[p + "self_attn.k_norm.weight"])
+            if dims.post_norms:
+                lw.update(ln_post_attn=sd[p + "post_attention_layernorm.weight"], ln_pre_ff=sd[p + "pre_feedforward_layernorm.weight"],
+                          ln_post_ff=sd[p + "post_feedforward_layernorm.weight"])
+            else:
+                lw.update(ln2=sd[p + "post_attention_layernorm.weight"])
+            w["layers"].append(lw)
         return cls(dims, torch.device(device), w, **kw)
 
     @classmethod
@@ -129,12 +190,20 @@ class LlamaAttnLRPEngine:
         g = torch.Generator(device=dev).manual_seed(seed)
         rn = lambda *s: (torch.randn(*s, generator=g, device=dev, dtype=torch.float32) * std).to(torch.bfloat16)
         ones = lambda n: torch.ones(n, device=dev, dtype=torch.bfloat16)
+        nw = (lambda n: torch.zeros(n, device=dev, dtype=torch.bfloat16)) if dims.norm_offset else ones  # (1 + 0) = 1
         layers = []
         for _ in range(dims.L):
-            layers.append(dict(wq=rn(dims.H * dims.D, dims.d), wk=rn(dims.Hkv * dims.D, dims.d), wv=rn(dims.Hkv * dims.D, dims.d),
-                               wo=rn(dims.d, dims.H * dims.D), wg=rn(dims.I, dims.d), wu=rn(dims.I, dims.d),
-                               wd=rn(dims.d, dims.I), ln1=ones(dims.d), ln2=ones(dims.d)))
-        w = dict(emb=rn(dims.V, dims.d), norm=ones(dims.d), lm_head=rn(dims.V, dims.d), layers=layers)
+            lw = dict(wq=rn(dims.H * dims.D, dims.d), wk=rn(dims.Hkv * dims.D, dims.d), wv=rn(dims.Hkv * dims.D, dims.d),
+                      wo=rn(dims.d, dims.H * dims.D), wg=rn(dims.I, dims.d), wu=rn(dims.I, dims.d), wd=rn(dims.d, dims.I), ln1=nw(dims.d))
+            if dims.qk_norm:
+                lw.update(qn=nw(dims.D), kn=nw(dims.D))
+            if dims.post_norms:
+                lw.update(ln_post_attn=nw(dims.d), ln_pre_ff=nw(dims.d), ln_post_ff=nw(dims.d))
+            else:
+                lw.update(ln2=nw(dims.d))
+            layers.append(lw)
+        emb = rn(dims.V, dims.d)
+        w = dict(emb=emb, norm=nw(dims.d), lm_head=emb if dims.post_norms else rn(dims.V, dims.d), layers=layers)
         return cls(dims, dev, w, **kw)
 
     # ------------------------------------------------------------------ workspace
@@ -158,6 +227,9 @@ class LlamaAttnLRPEngine:
             st.qkv, st.o, st.gu = e(T, m.qkv_width), e(T, m.H * m.D), e(T, 2 * m.I)
             st.lse = e(B, m.H, S, dt=torch.float32)
             st.rstd1, st.rstd2 = e(T, dt=torch.float32), e(T, dt=torch.float32)
+            st.rstd_qk = e(T, m.H + m.Hkv, dt=torch.float32) if m.qk_norm else None
+            st.rstd_pa = e(T, dt=torch.float32) if m.post_norms else None
+            st.rstd_pf = e(T, dt=torch.float32) if m.post_norms else None
             stores.append(st)
         ws["stores"] = stores
         if self.store_policy != "all":
@@ -166,6 +238,8 @@ class LlamaAttnLRPEngine:
         ws["g_h"] = e(T, m.d, dt=torch.float32)
         ws["g_hb"] = e(T, m.d)
         ws["xn"] = e(T, m.d)
+        if m.post_norms:
+            ws["y"] = e(T, m.d)      # branch output before its post-norm (forward) / gradient after it (backward)
         ws["a"] = e(T, m.I)          # act(gate)*up in forward, g_a in backward
         ws["g_gu"] = e(T, 2 * m.I)
         ws["g_o"] = e(T, m.H * m.D)
@@ -180,63 +254,88 @@ class LlamaAttnLRPEngine:
     def _segment_len(self) -> int:
         return max(1, int(math.ceil(math.sqrt(self.dims.L))))
 
-    def _rope(self, S: int):
-        if self._rope_key != S:
+    def _rope(self, S: int, l: int = 0):
+        theta = self.dims.layer_theta(l)
+        key = (S, theta)
+        if key not in self._rope_cache:
             m = self.dims
-            inv_freq = 1.0 / (m.theta ** (torch.arange(0, m.D, 2, dtype=torch.int64).float() / m.D))
+            inv_freq = 1.0 / (theta ** (torch.arange(0, m.D, 2, dtype=torch.int64).float() / m.D))
             fr = torch.outer(torch.arange(S, dtype=torch.float32), inv_freq)
-            self._cos, self._sin = fr.cos().to(self.device).contiguous(), fr.sin().to(self.device).contiguous()
-            self._rope_key = S
-        return self._cos, self._sin
+            self._rope_cache[key] = (fr.cos().to(self.device).contiguous(), fr.sin().to(self.device).contiguous())
+        return self._rope_cache[key]
 
     # ------------------------------------------------------------------ one layer
-    def _layer_fwd(self, lw, st: _LayerStore, h, ws, B, S):
+    def _layer_fwd(self, lw, st: _LayerStore, h, ws, B, S, l: int = 0):
         m = self.dims
         T = B * S
-        cos, sin = self._rope(S)
-        scale = 1.0 / math.sqrt(m.D)
+        cos, sin = self._rope(S, l)
+        scale = m.attn_scale or 1.0 / math.sqrt(m.D)
+        off, win = m.norm_offset, m.window(l)
         lib, C = ops._capi.lib(), ops._capi
-        C.check(lib.lrp_rmsnorm_fwd(h.data_ptr(), 1, lw["ln1"].data_ptr(), 0.0, m.eps, ws["xn"].data_ptr(), st.rstd1.data_ptr(),
+        C.check(lib.lrp_rmsnorm_fwd(h.data_ptr(), 1, lw["ln1"].data_ptr(), off, m.eps, ws["xn"].data_ptr(), st.rstd1.data_ptr(),
                                     T, m.d, ops._stream()), "rmsnorm_fwd")
         ops.linear_fwd(ws["xn"], lw["wqkv"], st.qkv)
+        if m.qk_norm:
+            C.check(lib.lrp_headnorm_inplace(st.qkv.data_ptr(), m.qkv_width, m.H, m.Hkv, m.D, lw["qn"].data_ptr(), lw["kn"].data_ptr(),
+                                             off, m.eps, st.rstd_qk.data_ptr(), T, 0, ops._stream()), "headnorm_fwd")
         ops.rope_inplace(st.qkv, m.H + m.Hkv, m.D, cos, sin, S)
         q, k, v = self._qkv_views(st.qkv, B, S)
         C.check(lib.lrp_attn_fwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), m.qkv_width, m.qkv_width, m.qkv_width,
-                                 st.o.data_ptr(), st.lse.data_ptr(), B, S, m.H, m.Hkv, m.D, scale, 1, 0, ops._stream()), "attn_fwd")
-        ops.linear_fwd(st.o, lw["wo"], h, resid=h)
-        C.check(lib.lrp_rmsnorm_fwd(h.data_ptr(), 1, lw["ln2"].data_ptr(), 0.0, m.eps, ws["xn"].data_ptr(), st.rstd2.data_ptr(),
+                                 st.o.data_ptr(), st.lse.data_ptr(), B, S, m.H, m.Hkv, m.D, scale, 1, win, ops._stream()), "attn_fwd")
+        if m.post_norms:
+            ops.linear_fwd(st.o, lw["wo"], ws["y"])
+            C.check(lib.lrp_rmsnorm_fwd_residual(ws["y"].data_ptr(), lw["ln_post_attn"].data_ptr(), off, m.eps, h.data_ptr(),
+                                                 st.rstd_pa.data_ptr(), T, m.d, ops._stream()), "rmsnorm_fwd_residual")
+        else:
+            ops.linear_fwd(st.o, lw["wo"], h, resid=h)
+        C.check(lib.lrp_rmsnorm_fwd(h.data_ptr(), 1, lw["ln2"].data_ptr(), off, m.eps, ws["xn"].data_ptr(), st.rstd2.data_ptr(),
                                     T, m.d, ops._stream()), "rmsnorm_fwd")
         ops.linear_fwd(ws["xn"], lw["wgu"], st.gu)
-        C.check(lib.lrp_gated_act_fwd(st.gu.data_ptr(), ws["a"].data_ptr(), T, m.I, ops.ACT_SILU, ops._stream()), "gated_act_fwd")
-        ops.linear_fwd(ws["a"], lw["wd"], h, resid=h)
+        C.check(lib.lrp_gated_act_fwd(st.gu.data_ptr(), ws["a"].data_ptr(), T, m.I, m.act_code, ops._stream()), "gated_act_fwd")
+        if m.post_norms:
+            ops.linear_fwd(ws["a"], lw["wd"], ws["y"])
+            C.check(lib.lrp_rmsnorm_fwd_residual(ws["y"].data_ptr(), lw["ln_post_ff"].data_ptr(), off, m.eps, h.data_ptr(),
+                                                 st.rstd_pf.data_ptr(), T, m.d, ops._stream()), "rmsnorm_fwd_residual")
+        else:
+            ops.linear_fwd(ws["a"], lw["wd"], h, resid=h)
 
-    def _layer_bwd(self, lw, st: _LayerStore, ws, B, S):
+    def _layer_bwd(self, lw, st: _LayerStore, ws, B, S, l: int = 0):
         m = self.dims
         T = B * S
-        cos, sin = self._rope(S)
-        scale = 1.0 / math.sqrt(m.D)
+        cos, sin = self._rope(S, l)
+        scale = m.attn_scale or 1.0 / math.sqrt(m.D)
+        off, win = m.norm_offset, m.window(l)
         lib, C = ops._capi.lib(), ops._capi
         g_h, g_hb = ws["g_h"], ws["g_hb"]
         # ---- gated MLP
+        src = g_hb
+        if m.post_norms:   # identity rule through the post-feed-forward norm: g * (off + w) * rstd of the branch output
+            src = ops.rmsnorm_bwd(g_hb, lw["ln_post_ff"], st.rstd_pf, w_offset=off, out=ws["y"])
         if self.fuse_gated:
             # down dgrad with (÷2, identity rule on SiLU, product rule) fused into its epilogue: g_a never touches HBM
-            ops.linear_dgrad_gated_bwd(g_hb, lw["wd"], st.gu, ws["g_gu"], ops.ACT_SILU, self.cp)
+            ops.linear_dgrad_gated_bwd(src, lw["wd"], st.gu, ws["g_gu"], m.act_code, self.cp)
         else:
-            ops.linear_dgrad(g_hb, lw["wd"], ws["a"])                              # g_a [T, I]
-            C.check(lib.lrp_gated_act_bwd(ws["a"].data_ptr(), st.gu.data_ptr(), ws["g_gu"].data_ptr(), T, m.I, ops.ACT_SILU,
+            ops.linear_dgrad(src, lw["wd"], ws["a"])                               # g_a [T, I]
+            C.check(lib.lrp_gated_act_bwd(ws["a"].data_ptr(), st.gu.data_ptr(), ws["g_gu"].data_ptr(), T, m.I, m.act_code,
                                           int(self.cp), ops._stream()), "gated_act_bwd")
         ops.linear_dgrad(ws["g_gu"], lw["wgu"], g_h, resid=g_h, rowscale=st.rstd2, colscale=lw["ln2_f"], shadow=g_hb)
         # ---- attention
-        ops.linear_dgrad(g_hb, lw["wo"], ws["g_o"])                                # g_o [T, H D]
+        src = g_hb
+        if m.post_norms:
+            src = ops.rmsnorm_bwd(g_hb, lw["ln_post_attn"], st.rstd_pa, w_offset=off, out=ws["y"])
+        ops.linear_dgrad(src, lw["wo"], ws["g_o"])                                 # g_o [T, H D]
         q, k, v = self._qkv_views(st.qkv, B, S)
         dq, dk, dv = self._qkv_views(ws["g_qkv"], B, S)
         C.check(lib.lrp_attn_bwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), m.qkv_width, m.qkv_width, m.qkv_width,
                                  st.o.data_ptr(), ws["g_o"].data_ptr(), st.lse.data_ptr(), dq.data_ptr(), dk.data_ptr(),
                                  dv.data_ptr(), m.qkv_width, m.qkv_width, m.qkv_width, ws["dq_acc"].data_ptr(),
-                                 ws["delta"].data_ptr(), B, S, m.H, m.Hkv, m.D, scale, 1, 0, *((0.0, 0.0, 1.0) if self.cp else (4.0, 4.0, 2.0)),
+                                 ws["delta"].data_ptr(), B, S, m.H, m.Hkv, m.D, scale, 1, win, *((0.0, 0.0, 1.0) if self.cp else (4.0, 4.0, 2.0)),
                                  ops._stream()),
                 "attn_bwd")
         ops.rope_inplace(ws["g_qkv"], m.H + m.Hkv, m.D, cos, sin, S, inverse=True)
+        if m.qk_norm:
+            C.check(lib.lrp_headnorm_inplace(ws["g_qkv"].data_ptr(), m.qkv_width, m.H, m.Hkv, m.D, lw["qn"].data_ptr(),
+                                             lw["kn"].data_ptr(), off, m.eps, st.rstd_qk.data_ptr(), T, 1, ops._stream()), "headnorm_bwd")
         ops.linear_dgrad(ws["g_qkv"], lw["wqkv"], g_h, resid=g_h, rowscale=st.rstd1, colscale=lw["ln1_f"], shadow=g_hb)
 
     def _qkv_views(self, buf, B, S):
@@ -263,29 +362,29 @@ class LlamaAttnLRPEngine:
         lib, C = ops._capi.lib(), ops._capi
         h, g_h, g_hb = ws["h"], ws["g_h"], ws["g_hb"]
         flat = ids.reshape(-1).contiguous()
-        C.check(lib.lrp_embed_gather(flat.data_ptr(), self.emb.data_ptr(), 1.0, h.data_ptr(), T, m.d, ops._stream()), "embed")
+        C.check(lib.lrp_embed_gather(flat.data_ptr(), self.emb.data_ptr(), m.emb_scale, h.data_ptr(), T, m.d, ops._stream()), "embed")
 
         seg = self._segment_len()
         if self.store_policy == "all":
             h_outs = [] if trace else None
             for l, lw in enumerate(self.layers):
-                self._layer_fwd(lw, ws["stores"][l], h, ws, B, S)
+                self._layer_fwd(lw, ws["stores"][l], h, ws, B, S, l)
                 if trace:
                     h_outs.append(h.clone())
         else:
             for l, lw in enumerate(self.layers):
                 if l % seg == 0:
                     ws["h_ckpt"][l // seg].copy_(h)
-                self._layer_fwd(lw, ws["stores"][l % seg], h, ws, B, S)
+                self._layer_fwd(lw, ws["stores"][l % seg], h, ws, B, S, l)
 
         # ---- head: only the last position is read (examples/quantized_llama.py:40)
         h_last = h.index_select(0, ws["last_rows"])
-        xn_last, rstd_last = ops.rmsnorm_fwd(h_last, self.norm_w, m.eps)
+        xn_last, rstd_last = ops.rmsnorm_fwd(h_last, self.norm_w, m.eps, w_offset=m.norm_offset)
         ops.linear_fwd(xn_last, self.lm_head, ws["logits"])
         idx, _ = ops.argmax_rows(ws["logits"])
         # seed: d(max logit)/d(xn_last) = lm_head[idx]; through the final norm with the identity rule
         g_xn_last = self.lm_head.index_select(0, idx.long())
-        g_last = ops.rmsnorm_bwd(g_xn_last, self.norm_w, rstd_last, out_dtype=torch.float32)
+        g_last = ops.rmsnorm_bwd(g_xn_last, self.norm_w, rstd_last, w_offset=m.norm_offset, out_dtype=torch.float32)
         g_h.zero_()
         g_h.index_copy_(0, ws["last_rows"], g_last)
         ops.cast_bf16(g_h, g_hb)
@@ -296,7 +395,7 @@ class LlamaAttnLRPEngine:
                 if trace:
                     layer_rel[l] = ops.gxi_reduce(h_outs[l], g_h).view(B, S)
                     h_outs[l] = None
-                self._layer_bwd(self.layers[l], ws["stores"][l], ws, B, S)
+                self._layer_bwd(self.layers[l], ws["stores"][l], ws, B, S, l)
         else:
             nseg = math.ceil(m.L / seg)
             for sgi in range(nseg - 1, -1, -1):
@@ -305,12 +404,12 @@ class LlamaAttnLRPEngine:
                 # layer stores were overwritten unless L is a multiple of the segment length)
                 h.copy_(ws["h_ckpt"][sgi])
                 for l in range(lo, hi):
-                    self._layer_fwd(self.layers[l], ws["stores"][l % seg], h, ws, B, S)
+                    self._layer_fwd(self.layers[l], ws["stores"][l % seg], h, ws, B, S, l)
                 for l in range(hi - 1, lo - 1, -1):
-                    self._layer_bwd(self.layers[l], ws["stores"][l % seg], ws, B, S)
+                    self._layer_bwd(self.layers[l], ws["stores"][l % seg], ws, B, S, l)
 
         # ---- Gradient x Input at the embedding
-        C.check(lib.lrp_embed_gather(flat.data_ptr(), self.emb.data_ptr(), 1.0, h.data_ptr(), T, m.d, ops._stream()), "embed")
+        C.check(lib.lrp_embed_gather(flat.data_ptr(), self.emb.data_ptr(), m.emb_scale, h.data_ptr(), T, m.d, ops._stream()), "embed")
         rel = ops.gxi_reduce(h, g_h).view(B, S)
         if return_aux or trace:
             aux = {"idx": idx, "logits": ws["logits"], "g_emb": g_h.view(B, S, m.d)}

@@ -230,6 +230,115 @@ def llama_attnlrp(weights: Dict, ids: torch.Tensor, cfg: Dict, dtype=torch.float
     return rel
 
 
+def _act(x, kind):
+    return F.silu(x) if kind == "silu" else F.gelu(x, approximate="tanh")
+
+
+def decoder_attnlrp(weights: Dict, ids: torch.Tensor, cfg: Dict, dtype=torch.float32, return_aux: bool = False):
+    """Generalised decoder restatement (explicit formulas, no autograd) covering Llama and Gemma-3 text models under the
+    reference's attnLRP maps (lxt/efficient/models/llama.py:9-14, gemma3.py:11-19).  Options in `cfg` beyond d,H,Hkv,D,eps:
+      norm_offset  0 (Llama `w*x_hat`) or 1 (Gemma `(1+w)*x_hat`, gemma3.py:11-12 + HF Gemma3RMSNorm.forward)
+      act          "silu" | "gelu_tanh"           qk_norm     per-head RMSNorm on q,k before RoPE (weights 'qn','kn' [D])
+      post_norms   Gemma layer layout: h += post_norm(branch(pre_norm(h)))  (weights 'ln_post_attn','ln_pre_ff','ln_post_ff')
+      windows      per-layer sliding window (0 = global), thetas: per-layer RoPE base
+      attn_scale   soft-max scale (default D^-0.5), emb_scale: embedding multiplier (Gemma sqrt(d))
+    """
+    H, Hkv, D, eps = cfg["H"], cfg["Hkv"], cfg["D"], cfg["eps"]
+    off, act = float(cfg.get("norm_offset", 0)), cfg.get("act", "silu")
+    qk_norm, post = bool(cfg.get("qk_norm", False)), bool(cfg.get("post_norms", False))
+    L = len(weights["layers"])
+    windows = cfg.get("windows") or [0] * L
+    thetas = cfg.get("thetas") or [cfg["theta"]] * L
+    scale = cfg.get("attn_scale") or 1.0 / math.sqrt(D)
+    emb_scale = cfg.get("emb_scale", 1.0)
+    G = H // Hkv
+    B, S = ids.shape
+    W = lambda t: t.to(dtype)
+
+    def norm_f(x, w):  # rms norm with detached variance; returns (y, rstd)
+        xf = x.to(torch.float32)
+        r = torch.rsqrt(xf.pow(2).mean(-1, keepdim=True) + eps)
+        return ((xf * r) * (off + w.to(torch.float32))).to(x.dtype), r
+
+    def norm_b(g, w, r):  # identity rule: g * (off + w) * rstd
+        return (g.to(torch.float32) * (off + w.to(torch.float32)) * r).to(g.dtype)
+
+    i = torch.arange(S)
+    emb = (W(weights["emb"])[ids] * torch.tensor(emb_scale, dtype=dtype)) if emb_scale != 1.0 else W(weights["emb"])[ids]
+    h = emb
+    stash = []
+    for l, lw in enumerate(weights["layers"]):
+        st = {}
+        cos, sin = rope_tables(S, D, thetas[l], dtype)
+        mask = torch.zeros(S, S)
+        bad = i[None, :] > i[:, None]
+        if windows[l]:
+            bad = bad | ((i[:, None] - i[None, :]) >= windows[l])
+        mask = mask.masked_fill(bad, float("-inf"))
+        xn, st["r1"] = norm_f(h, W(lw["ln1"]))
+        q = (xn @ W(lw["wq"]).T).view(B, S, H, D).transpose(1, 2)
+        k = (xn @ W(lw["wk"]).T).view(B, S, Hkv, D).transpose(1, 2)
+        v = (xn @ W(lw["wv"]).T).view(B, S, Hkv, D).transpose(1, 2)
+        if "bq" in lw:
+            q = q + W(lw["bq"]).view(1, H, 1, D); k = k + W(lw["bk"]).view(1, Hkv, 1, D); v = v + W(lw["bv"]).view(1, Hkv, 1, D)
+        if qk_norm:
+            q, st["rq"] = norm_f(q, W(lw["qn"]))
+            k, st["rk"] = norm_f(k, W(lw["kn"]))
+        q = q * cos + _rotate_half(q) * sin
+        k = k * cos + _rotate_half(k) * sin
+        kr, vr = k.repeat_interleave(G, 1), v.repeat_interleave(G, 1)
+        P = F.softmax((q @ kr.transpose(-1, -2)) * scale + mask, dim=-1, dtype=torch.float32).to(dtype)
+        o = (P @ vr).transpose(1, 2).reshape(B, S, H * D)
+        st.update(q=q, kr=kr, vr=vr, P=P, cos=cos, sin=sin)
+        a_out = o @ W(lw["wo"]).T
+        if post:
+            a_out, st["rpa"] = norm_f(a_out, W(lw["ln_post_attn"]))
+        h = h + a_out
+        xn2, st["r2"] = norm_f(h, W(lw["ln_pre_ff"] if post else lw["ln2"]))
+        gate, up = xn2 @ W(lw["wg"]).T, xn2 @ W(lw["wu"]).T
+        sg = _act(gate, act)
+        st.update(gate=gate, up=up, s=sg)
+        m_out = (sg * up) @ W(lw["wd"]).T
+        if post:
+            m_out, st["rpf"] = norm_f(m_out, W(lw["ln_post_ff"]))
+        h = h + m_out
+        stash.append(st)
+    hN, rN = norm_f(h, W(weights["norm"]))
+    logits = hN[:, -1, :] @ W(weights["lm_head"]).T
+    idx = logits.float().argmax(-1)
+
+    g_h = torch.zeros_like(h)
+    g_h[:, -1, :] = norm_b(W(weights["lm_head"])[idx], W(weights["norm"]), rN[:, -1, :])
+    for lw, st in zip(reversed(weights["layers"]), reversed(stash)):
+        g_m = norm_b(g_h, W(lw["ln_post_ff"]), st["rpf"]) if post else g_h
+        g_a = divide_gradient_grad(g_m @ W(lw["wd"]), 2)
+        g_gate = identity_rule_implicit_grad(st["s"], st["gate"], g_a * st["up"])
+        g_xn2 = g_gate @ W(lw["wg"]) + (g_a * st["s"]) @ W(lw["wu"])
+        g_h = g_h + norm_b(g_xn2, W(lw["ln_pre_ff"] if post else lw["ln2"]), st["r2"])
+        g_ao = norm_b(g_h, W(lw["ln_post_attn"]), st["rpa"]) if post else g_h
+        g_o = (g_ao @ W(lw["wo"])).view(B, S, H, D).transpose(1, 2)
+        P, q, kr, vr, cos, sin = st["P"], st["q"], st["kr"], st["vr"], st["cos"], st["sin"]
+        dV = P.transpose(-1, -2) @ g_o
+        dP = (g_o @ vr.transpose(-1, -2)).to(torch.float32)
+        Pf = P.to(torch.float32)
+        dS = (Pf * (dP - (dP * Pf).sum(-1, keepdim=True))).to(dtype) * scale
+        dQ = (dS @ kr) / 4
+        dK = (dS.transpose(-1, -2) @ q).view(B, Hkv, G, S, D).sum(2) / 4
+        dV = dV.view(B, Hkv, G, S, D).sum(2) / 2
+        dQ = dQ * cos + _rotate_half_T(dQ * sin)
+        dK = dK * cos + _rotate_half_T(dK * sin)
+        if qk_norm:
+            dQ = norm_b(dQ, W(lw["qn"]), st["rq"])
+            dK = norm_b(dK, W(lw["kn"]), st["rk"])
+        g_xn = (dQ.transpose(1, 2).reshape(B, S, H * D) @ W(lw["wq"]) + dK.transpose(1, 2).reshape(B, S, Hkv * D) @ W(lw["wk"])
+                + dV.transpose(1, 2).reshape(B, S, Hkv * D) @ W(lw["wv"]))
+        g_h = g_h + norm_b(g_xn, W(lw["ln1"]), st["r1"])
+    rel = (emb * g_h).float().sum(-1)
+    if return_aux:
+        return rel, {"idx": idx, "logits": logits.float(), "g_emb": g_h}
+    return rel
+
+
 def random_llama_weights(cfg: Dict, seed: int = 0, std: float = 0.02, dtype=torch.bfloat16) -> Dict:
     """HF-style random init (normal(0, 0.02), norm weights 1) for the synthetic workloads."""
     g = torch.Generator().manual_seed(seed)

@@ -30,3 +30,28 @@ def rel_l2(a, b) -> float:
     a = torch.as_tensor(a).double().flatten()
     b = torch.as_tensor(b).double().flatten()
     return float((a - b).norm() / (b.norm() + 1e-300))
+
+
+def load_gemma_golden(name):
+    """-> (cfg for oracle.decoder_attnlrp / engine, weights dict (bf16), ids, raw npz) from tests/golden/gemma3_tiny*.npz"""
+    z = load_npz(name)
+    sd = {k[3:]: bf16_from_bits(v) for k, v in z.items() if k.startswith("sd_")}
+    L = len(z["layer_types"])
+    D = sd["model.layers.0.self_attn.q_norm.weight"].shape[0]
+    d = sd["model.embed_tokens.weight"].shape[1]
+    H = sd["model.layers.0.self_attn.q_proj.weight"].shape[0] // D
+    Hkv = sd["model.layers.0.self_attn.k_proj.weight"].shape[0] // D
+    cfg = dict(d=d, I=sd["model.layers.0.mlp.gate_proj.weight"].shape[0], H=H, Hkv=Hkv, D=D, L=L, V=sd["model.embed_tokens.weight"].shape[0],
+               eps=1e-6, theta=10000.0, norm_offset=1, act="gelu_tanh", qk_norm=True, post_norms=True,
+               windows=[48 if t == "sliding_attention" else 0 for t in z["layer_types"]],
+               thetas=[10000.0 if t == "sliding_attention" else 1000000.0 for t in z["layer_types"]],
+               attn_scale=float(D) ** -0.5, emb_scale=float(d) ** 0.5)
+    w = {"emb": sd["model.embed_tokens.weight"], "norm": sd["model.norm.weight"], "lm_head": sd["model.embed_tokens.weight"], "layers": []}
+    for i in range(L):
+        p = f"model.layers.{i}."
+        w["layers"].append(dict(wq=sd[p + "self_attn.q_proj.weight"], wk=sd[p + "self_attn.k_proj.weight"], wv=sd[p + "self_attn.v_proj.weight"],
+                                wo=sd[p + "self_attn.o_proj.weight"], qn=sd[p + "self_attn.q_norm.weight"], kn=sd[p + "self_attn.k_norm.weight"],
+                                wg=sd[p + "mlp.gate_proj.weight"], wu=sd[p + "mlp.up_proj.weight"], wd=sd[p + "mlp.down_proj.weight"],
+                                ln1=sd[p + "input_layernorm.weight"], ln_post_attn=sd[p + "post_attention_layernorm.weight"],
+                                ln_pre_ff=sd[p + "pre_feedforward_layernorm.weight"], ln_post_ff=sd[p + "post_feedforward_layernorm.weight"]))
+    return cfg, w, torch.from_numpy(z["ids"]), z

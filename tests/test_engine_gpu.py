@@ -110,3 +110,23 @@ def test_engine_cuda_graph_replay_matches_eager():
         assert rel_l2(got, eager) < 1e-5   # dQ uses fp32 atomics: order-dependent in the last bits only
     ids2 = torch.roll(ids, 1, 0)           # different content, same shape: replay must pick up the new ids
     assert rel_l2(eng.attribute(ids2.pin_memory()), torch.roll(eager, 1, 0)) < 1e-5
+
+
+@pytest.mark.parametrize("name", ["gemma3_tiny.npz", "gemma3_tiny_d256.npz"])
+def test_engine_gemma3_matches_reference_golden(name):
+    """The fused engine on the Gemma-3 layer layout ((1+w) norms, pre/post norms around both branches, per-head q/k-norm,
+    GELU-tanh gate, sliding-window + global layers with their own RoPE base, scaled embedding, tied lm_head) vs the golden
+    relevance of the real reference (lxt.efficient.monkey_patch(modeling_gemma3)) and vs the CPU oracle."""
+    from helpers import load_gemma_golden
+    from lxt_b200.engine import LlamaAttnLRPEngine, LlamaDims
+    from oracle import attnlrp_oracle as O
+    cfg, w, ids, z = load_gemma_golden(name)
+    keys = ("d", "I", "H", "Hkv", "D", "L", "V", "eps", "theta", "norm_offset", "act", "qk_norm", "post_norms", "windows", "thetas",
+            "attn_scale", "emb_scale")
+    eng = LlamaAttnLRPEngine.from_weights(LlamaDims(**{k: cfg[k] for k in keys}), w, device="cuda", micro_batch=2)
+    rel, aux = eng.attribute_device(ids.cuda(), return_aux=True)
+    assert np.array_equal(aux["idx"].cpu().numpy(), z["idx"])
+    err = rel_l2(rel.cpu(), z["rel_fp32"])
+    ora = O.decoder_attnlrp(w, ids, cfg, dtype=torch.float32)
+    print(f"{name}: Gemma-3 engine rel-L2 vs reference fp32 = {err:.3e}, vs oracle = {rel_l2(rel.cpu(), ora):.3e}")
+    assert err < 6e-3

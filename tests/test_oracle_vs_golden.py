@@ -90,3 +90,17 @@ def test_latent_relevance_trace_matches_reference_hooks(name):
     cfg, w, ids, z = load_llama_golden(name)
     _, aux = O.llama_attnlrp(w, ids, cfg, dtype=torch.float32, return_aux=True)
     assert rel_l2(aux["layer_relevance"], z["trace_fp32_sdpa"]) < 1e-4
+
+
+@pytest.mark.parametrize("name", ["gemma3_tiny.npz", "gemma3_tiny_d256.npz"])
+def test_generalised_decoder_oracle_matches_reference_gemma3(name):
+    from helpers import load_gemma_golden
+    cfg, w, ids, z = load_gemma_golden(name)
+    rel, aux = O.decoder_attnlrp(w, ids, cfg, dtype=torch.float32, return_aux=True)
+    assert np.array_equal(aux["idx"].numpy(), z["idx"])
+    assert rel_l2(rel, z["rel_fp32"]) < 1e-4
+
+
+def test_generalised_decoder_oracle_equals_llama_restatement():
+    cfg, w, ids, z = load_llama_golden("llama_tiny_d128.npz")
+    assert rel_l2(O.decoder_attnlrp(w, ids, cfg), O.llama_attnlrp(w, ids, cfg)) < 1e-6
