@@ -122,6 +122,8 @@ class LlamaAttnLRPEngine:
             ln2 = lw["ln_pre_ff"] if dims.post_norms else lw["ln2"]
             layer = dict(wqkv=bf(wqkv), wo=bf(lw["wo"]), wgu=bf(wgu), wd=bf(lw["wd"]), ln1=bf(lw["ln1"]), ln2=bf(ln2),
                          ln1_f=f32(bf(lw["ln1"])) + dims.norm_offset, ln2_f=f32(bf(ln2)) + dims.norm_offset)
+            if "bq" in lw:   # Qwen2-style projection biases: one fp32 vector for the packed QKV GEMM epilogue
+                layer["bqkv"] = f32(torch.cat([lw["bq"], lw["bk"], lw["bv"]], dim=0))
             if dims.qk_norm:
                 layer.update(qn=bf(lw["qn"]), kn=bf(lw["kn"]))
             if dims.post_norms:
@@ -158,13 +160,14 @@ class LlamaAttnLRPEngine:
                          emb_scale=float(c.hidden_size) ** 0.5)
         elif mt == "qwen3":
             extra = dict(qk_norm=True)
-        elif mt not in ("llama",):
+        elif mt not in ("llama", "qwen2"):
             raise ValueError(f"LlamaAttnLRPEngine.from_hf: unsupported model_type {mt!r} (use the drop-in monkey_patch API)")
         dims = LlamaDims(d=c.hidden_size, I=c.intermediate_size, H=c.num_attention_heads, Hkv=c.num_key_value_heads, D=D,
                          L=c.num_hidden_layers, V=c.vocab_size, eps=c.rms_norm_eps, theta=float(theta), **extra)
         sd = model.state_dict()
-        if any(k.endswith("self_attn.q_proj.bias") for k in sd):
-            raise ValueError("projection biases are not supported by the fused engine (use the drop-in monkey_patch API)")
+        has_bias = any(k.endswith("self_attn.q_proj.bias") for k in sd)
+        if any(k.endswith(("o_proj.bias", "gate_proj.bias", "up_proj.bias", "down_proj.bias")) for k in sd):
+            raise ValueError("only q/k/v projection biases are supported by the fused engine (use the drop-in monkey_patch API)")
         w = dict(emb=sd["model.embed_tokens.weight"], norm=sd["model.norm.weight"],
                  lm_head=sd.get("lm_head.weight", sd["model.embed_tokens.weight"]), layers=[])
         for i in range(dims.L):
@@ -173,6 +176,8 @@ class LlamaAttnLRPEngine:
                       wv=sd[p + "self_attn.v_proj.weight"], wo=sd[p + "self_attn.o_proj.weight"],
                       wg=sd[p + "mlp.gate_proj.weight"], wu=sd[p + "mlp.up_proj.weight"],
                       wd=sd[p + "mlp.down_proj.weight"], ln1=sd[p + "input_layernorm.weight"])
+            if has_bias:
+                lw.update(bq=sd[p + "self_attn.q_proj.bias"], bk=sd[p + "self_attn.k_proj.bias"], bv=sd[p + "self_attn.v_proj.bias"])
             if dims.qk_norm:
                 lw.update(qn=sd[p + "self_attn.q_norm.weight"], kn=sd[p + "self_attn.k_norm.weight"])
             if dims.post_norms:
@@ -274,7 +279,7 @@ class LlamaAttnLRPEngine:
         lib, C = ops._capi.lib(), ops._capi
         C.check(lib.lrp_rmsnorm_fwd(h.data_ptr(), 1, lw["ln1"].data_ptr(), off, m.eps, ws["xn"].data_ptr(), st.rstd1.data_ptr(),
                                     T, m.d, ops._stream()), "rmsnorm_fwd")
-        ops.linear_fwd(ws["xn"], lw["wqkv"], st.qkv)
+        ops.linear_fwd(ws["xn"], lw["wqkv"], st.qkv, bias=lw.get("bqkv"))
         if m.qk_norm:
             C.check(lib.lrp_headnorm_inplace(st.qkv.data_ptr(), m.qkv_width, m.H, m.Hkv, m.D, lw["qn"].data_ptr(), lw["kn"].data_ptr(),
                                              off, m.eps, st.rstd_qk.data_ptr(), T, 0, ops._stream()), "headnorm_fwd")

@@ -47,3 +47,12 @@ def test_patched_qwen_matches_reference(family):
     err = rel_l2(rel, z["rel_fp32"])
     print(f"{family} tiny: rel-L2 vs reference fp32 = {err:.3e}")
     assert err < 2e-2
+    # the fused engine built from the same HF model (Qwen2: q/k/v biases in the packed-QKV GEMM epilogue; Qwen3: per-head
+    # q/k RMSNorm kernel)
+    from lxt_b200.engine import LlamaAttnLRPEngine
+    eng = LlamaAttnLRPEngine.from_hf(model, micro_batch=2)
+    r_eng, aux = eng.attribute_device(ids, return_aux=True)
+    assert np.array_equal(aux["idx"].cpu().numpy(), z["idx"])
+    e2 = rel_l2(r_eng.cpu(), z["rel_fp32"])
+    print(f"{family} tiny: fused engine rel-L2 vs reference fp32 = {e2:.3e}")
+    assert e2 < 6e-3
