@@ -201,11 +201,15 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__
 // =================================================================================================
 // backward
 // =================================================================================================
-template <int D>
+// TMA_DQ: the fp32 dQ tile leaves through the (then free) P/dS staging smem as D/32 bulk tensor reductions
+// (cp.reduce.async.bulk.tensor .add, issued by one thread, asynchronous) instead of 16 red.global.add.v4.f32 per thread.
+__device__ __forceinline__ void bar_sync_softmax8() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
+template <int D, bool TMA_DQ>
 __global__ void __launch_bounds__(BWD_THREADS, 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__ CUtensorMap tmk,
                 const __grid_constant__ CUtensorMap tmv, const __grid_constant__ CUtensorMap tmdo,
-                const AttnParams p) {
+                const __grid_constant__ CUtensorMap tmdq, const AttnParams p) {
   constexpr int TILE_BYTES = ATT_TILE * D * 2;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -312,6 +316,10 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__
       mbar_wait(s_full, it & 1);
       if (dbgt) p.dbg[it * 16 + 9] = clock64();
       tc_fence_after();
+      if (TMA_DQ && it > 0) {  // the previous tile's dQ reductions must have read the staging smem (= P/dS) out
+        if (threadIdx.x == 0) tma_store_wait_read<0>();
+        bar_sync_softmax8();
+      }
       int lo, hi;
       row_window(qpos, k0, p.S, p.causal, p.window, lo, hi);
       if (!row_ok) { lo = 1; hi = 0; }  // padded / fully masked query row: everything is masked
@@ -341,23 +349,47 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__
       // dQ tile -> fp32 reductions into the dq workspace.  (Releasing the TMEM columns before issuing the reductions was
       // tried and does not help: the red.global traffic saturates the SM's memory-instruction queue either way, see
       // profiles/r01_attn_bwd_v1_timeline.txt.)
-      float* dqrow = p.dq_acc + ((int64_t(b) * p.S + qpos) * p.H + h) * D;
+      if (TMA_DQ) {
+        // MMA2 has retired (dq_full), so P/dS are dead: stage the fp32 tile there as D/32 128B-swizzled [128 x 32] boxes
 #pragma unroll 1
-      for (int c = ch; c < D / 32; c += 2) {
-        uint32_t v[32];
-        tmem_ld32(tmem_S + lane_base + c * 32, v);
-        tmem_ld_wait();
-        if (valid) {
+        for (int c = ch; c < D / 32; c += 2) {
+          uint32_t v[32];
+          tmem_ld32(tmem_S + lane_base + c * 32, v);
+          tmem_ld_wait();
+          uint8_t* rowp = sP + c * 16384 + r * 128;
 #pragma unroll
           for (int q = 0; q < 8; ++q)
-            red_add_v4(dqrow + c * 32 + q * 4, __uint_as_float(v[q * 4]), __uint_as_float(v[q * 4 + 1]),
-                       __uint_as_float(v[q * 4 + 2]), __uint_as_float(v[q * 4 + 3]));
+            *reinterpret_cast<uint4*>(rowp + ((q ^ (r & 7)) * 16)) = make_uint4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
         }
+        fence_proxy_async_smem();
+        tc_fence_before();
+        mbar_arrive(dq_empty);
+        bar_sync_softmax8();
+        if (threadIdx.x == 0) {
+#pragma unroll
+          for (int c = 0; c < D / 32; ++c) tma_reduce_add_3d(&tmdq, sP + c * 16384, h * D + c * 32, i * ATT_TILE, b);
+          tma_store_commit();
+        }
+      } else {
+        float* dqrow = p.dq_acc + ((int64_t(b) * p.S + qpos) * p.H + h) * D;
+#pragma unroll 1
+        for (int c = ch; c < D / 32; c += 2) {
+          uint32_t v[32];
+          tmem_ld32(tmem_S + lane_base + c * 32, v);
+          tmem_ld_wait();
+          if (valid) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+              red_add_v4(dqrow + c * 32 + q * 4, __uint_as_float(v[q * 4]), __uint_as_float(v[q * 4 + 1]),
+                         __uint_as_float(v[q * 4 + 2]), __uint_as_float(v[q * 4 + 3]));
+          }
+        }
+        tc_fence_before();
+        mbar_arrive(dq_empty);
       }
-      tc_fence_before();
-      mbar_arrive(dq_empty);
       if (dbgt) p.dbg[it * 16 + 12] = clock64();
     }
+    if (TMA_DQ && threadIdx.x == 0) tma_store_wait<0>();
     // dK, dV of this key tile
     const int kpos = k0 + r;
     if (n_it > 0) {
@@ -469,10 +501,10 @@ static int launch_fwd(const CUtensorMap& tq, const CUtensorMap& tk, const CUtens
   return LRP_OK;
 }
 
-template <int D>
+template <int D, bool TMA_DQ>
 static int launch_bwd(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const CUtensorMap& tdo,
-                      const AttnParams& p, cudaStream_t st) {
-  auto kern = attn_bwd_kernel<D>;
+                      const CUtensorMap& tdq, const AttnParams& p, cudaStream_t st) {
+  auto kern = attn_bwd_kernel<D, TMA_DQ>;
   static bool done = false;
   if (!done) {
     cudaError_t ce = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bwd_smem_bytes<D>());
@@ -480,7 +512,7 @@ static int launch_bwd(const CUtensorMap& tq, const CUtensorMap& tk, const CUtens
     done = true;
   }
   dim3 grid((p.S + ATT_TILE - 1) / ATT_TILE, p.Hkv, p.B);
-  kern<<<grid, BWD_THREADS, bwd_smem_bytes<D>(), st>>>(tq, tk, tv, tdo, p);
+  kern<<<grid, BWD_THREADS, bwd_smem_bytes<D>(), st>>>(tq, tk, tv, tdo, tdq, p);
   LRP_CHECK_LAUNCH();
   return LRP_OK;
 }
@@ -557,7 +589,16 @@ int lrp_attn_bwd(const void* q, const void* k, const void* v, int64_t ldq, int64
     cudaMemset(dbg_dev, 0, 64 * 16 * sizeof(long long));
     p.dbg = dbg_dev;
   }
-  if (int e = (D == 128 ? launch_bwd<128>(tq, tk, tv, tdo, p, st) : launch_bwd<64>(tq, tk, tv, tdo, p, st))) return e;
+  // dQ tile reductions: bulk tensor reductions through smem by default; LRP_ATTN_DQ=red keeps the per-thread red.global
+  // form for A/B measurements (profiles/r01_attn_bwd_v1_timeline.txt)
+  const char* dqsel = getenv("LRP_ATTN_DQ");
+  const bool tma_dq = !(dqsel != nullptr && !strcmp(dqsel, "red"));
+  CUtensorMap tdq;
+  if (int e = make_tmap_3d_f32(&tdq, dq_acc_ws, uint64_t(HD), S, B, HD, uint64_t(S) * HD, 32, ATT_TILE)) return e;
+  int le;
+  if (D == 128) le = tma_dq ? launch_bwd<128, true>(tq, tk, tv, tdo, tdq, p, st) : launch_bwd<128, false>(tq, tk, tv, tdo, tdq, p, st);
+  else le = tma_dq ? launch_bwd<64, true>(tq, tk, tv, tdo, tdq, p, st) : launch_bwd<64, false>(tq, tk, tv, tdo, tdq, p, st);
+  if (le) return le;
   if (dbg_dev != nullptr) {
     static bool printed = false;
     long long h[64 * 16];

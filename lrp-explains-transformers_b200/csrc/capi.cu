@@ -91,6 +91,28 @@ int make_tmap_3d_bf16(CUtensorMap* out, const void* base, uint64_t dim0, uint64_
   return LRP_OK;
 }
 
+// fp32 [dim2][dim1][dim0] tensor, 128B-swizzled boxes of 32 floats x box1 rows: the destination of the attention
+// backward's dQ tile reductions (cp.reduce.async.bulk.tensor ... .add)
+int make_tmap_3d_f32(CUtensorMap* out, const void* base, uint64_t dim0, uint64_t dim1, uint64_t dim2, uint64_t stride1,
+                     uint64_t stride2, uint32_t box0, uint32_t box1) {
+  PFN_encodeTiled enc = get_encode();
+  if (enc == nullptr) return set_error(LRP_ERR_CUDA, "cuTensorMapEncodeTiled unavailable (no CUDA driver?)");
+  cuuint64_t dims[3] = {dim0, dim1, dim2};
+  cuuint64_t strides[2] = {stride1 * 4, stride2 * 4};
+  cuuint32_t box[3] = {box0, box1, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    char buf[200];
+    snprintf(buf, sizeof(buf), "cuTensorMapEncodeTiled(3d f32) failed (%d): dims=%llu x %llu x %llu", int(r),
+             (unsigned long long)dim0, (unsigned long long)dim1, (unsigned long long)dim2);
+    return set_error(LRP_ERR_CUDA, buf);
+  }
+  return LRP_OK;
+}
+
 }  // namespace lrp
 
 using namespace lrp;

@@ -19,6 +19,8 @@ int make_tmap_2d_bf16(CUtensorMap* out, const void* base, uint64_t dim0, uint64_
 // 3-D variant: dims (dim0 contiguous, dim1, dim2) with element strides stride1/stride2; box = box0 x box1 x 1.
 int make_tmap_3d_bf16(CUtensorMap* out, const void* base, uint64_t dim0, uint64_t dim1, uint64_t dim2,
                       uint64_t stride1, uint64_t stride2, uint32_t box0, uint32_t box1);
+int make_tmap_3d_f32(CUtensorMap* out, const void* base, uint64_t dim0, uint64_t dim1, uint64_t dim2, uint64_t stride1,
+                     uint64_t stride2, uint32_t box0, uint32_t box1);
 
 int gemm_bf16(const void* A, int64_t lda, const void* B, int64_t ldb, int b_layout, int M, int N, int K,
               const lrp_epilogue_t* epi, int force_bn, cudaStream_t stream);
