@@ -339,7 +339,8 @@ def secondary_kernel_rooflines(dims, S, dev, peaks):
     ms_f = timed(lambda: ops.attn_fwd(q, k, v, D ** -0.5))
     ms_b = timed(lambda: ops.attn_bwd(q, k, v, o, d_o, lse, D ** -0.5, dq=dq, dk=dk, dv=dv, dq_acc=acc, delta=dl))
     fl_f = 4.0 * B * H * S * S * D / 2
-    bytes_fb = B * (2 * (S * H * D * 2) * 2 + 2 * (S * Hkv * D * 2) * 2 + S * H * D * 2 + S * H * 4)  # Q,O,dO,dQ + K,V,dK,dV + ... per SURVEY 8d
+    # read Q, K, V, O, dO, LSE; write dQ, dK, dV (bf16; LSE fp32)  -> 84.2 MB per Llama-3-8B layer-sequence
+    bytes_fb = B * (4 * S * H * D * 2 + 4 * S * Hkv * D * 2 + S * H * 4)
     res["flash_attnlrp"] = {"shape": {"B": B, "S": S, "H": H, "Hkv": Hkv, "D": D, "causal": True},
                             "fwd_ms": ms_f, "bwd_ms": ms_b, "fwd_tflops": fl_f / (ms_f * 1e-3) / 1e12,
                             "bwd_tflops": 2.5 * fl_f / (ms_b * 1e-3) / 1e12, "tensor_peak": burst,

@@ -105,6 +105,16 @@ __device__ __forceinline__ void store_row_chunk_sw128(uint8_t* tile, int r, int 
   }
 }
 
+// same, from 16 already packed bf16x2 words
+__device__ __forceinline__ void store_row_chunk_sw128_pk(uint8_t* tile, int r, int c, const uint32_t (&pk)[16]) {
+  uint8_t* rowp = tile + (c >> 1) * 16384 + r * 128;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int chunk = ((c & 1) * 4 + q) ^ (r & 7);
+    *reinterpret_cast<uint4*>(rowp + chunk * 16) = make_uint4(pk[q * 4], pk[q * 4 + 1], pk[q * 4 + 2], pk[q * 4 + 3]);
+  }
+}
+
 // ---- UMMA issue helpers (single thread) -------------------------------------------------------
 // All loops are fully unrolled with compile-time offsets and (lo, hi) descriptor halves: the one issuing thread spends
 // a few instructions per tcgen05.mma (the first version rebuilt both 64-bit descriptors per instruction, ~60 cycles

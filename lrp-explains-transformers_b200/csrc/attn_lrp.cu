@@ -201,15 +201,15 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__
 // =================================================================================================
 // backward
 // =================================================================================================
-// TMA_DQ: the fp32 dQ tile leaves through the (then free) P/dS staging smem as D/32 bulk tensor reductions
-// (cp.reduce.async.bulk.tensor .add, issued by one thread, asynchronous) instead of 16 red.global.add.v4.f32 per thread.
 __device__ __forceinline__ void bar_sync_softmax8() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
-template <int D, bool TMA_DQ>
+// First-generation single kernel (LRP_ATTN_BWD=v1): one tile at a time, dQ leaves as 16 red.global.add.v4.f32 per thread.
+// Kept as the A/B baseline of profiles/r01_attn_bwd_v1_timeline.txt; the default is attn_bwd_pipe_kernel below.
+template <int D>
 __global__ void __launch_bounds__(BWD_THREADS, 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__ CUtensorMap tmk,
                 const __grid_constant__ CUtensorMap tmv, const __grid_constant__ CUtensorMap tmdo,
-                const __grid_constant__ CUtensorMap tmdq, const AttnParams p) {
+                const AttnParams p) {
   constexpr int TILE_BYTES = ATT_TILE * D * 2;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -316,10 +316,6 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__
       mbar_wait(s_full, it & 1);
       if (dbgt) p.dbg[it * 16 + 9] = clock64();
       tc_fence_after();
-      if (TMA_DQ && it > 0) {  // the previous tile's dQ reductions must have read the staging smem (= P/dS) out
-        if (threadIdx.x == 0) tma_store_wait_read<0>();
-        bar_sync_softmax8();
-      }
       int lo, hi;
       row_window(qpos, k0, p.S, p.causal, p.window, lo, hi);
       if (!row_ok) { lo = 1; hi = 0; }  // padded / fully masked query row: everything is masked
@@ -349,28 +345,6 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__
       // dQ tile -> fp32 reductions into the dq workspace.  (Releasing the TMEM columns before issuing the reductions was
       // tried and does not help: the red.global traffic saturates the SM's memory-instruction queue either way, see
       // profiles/r01_attn_bwd_v1_timeline.txt.)
-      if (TMA_DQ) {
-        // MMA2 has retired (dq_full), so P/dS are dead: stage the fp32 tile there as D/32 128B-swizzled [128 x 32] boxes
-#pragma unroll 1
-        for (int c = ch; c < D / 32; c += 2) {
-          uint32_t v[32];
-          tmem_ld32(tmem_S + lane_base + c * 32, v);
-          tmem_ld_wait();
-          uint8_t* rowp = sP + c * 16384 + r * 128;
-#pragma unroll
-          for (int q = 0; q < 8; ++q)
-            *reinterpret_cast<uint4*>(rowp + ((q ^ (r & 7)) * 16)) = make_uint4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
-        }
-        fence_proxy_async_smem();
-        tc_fence_before();
-        mbar_arrive(dq_empty);
-        bar_sync_softmax8();
-        if (threadIdx.x == 0) {
-#pragma unroll
-          for (int c = 0; c < D / 32; ++c) tma_reduce_add_3d(&tmdq, sP + c * 16384, h * D + c * 32, i * ATT_TILE, b);
-          tma_store_commit();
-        }
-      } else {
         float* dqrow = p.dq_acc + ((int64_t(b) * p.S + qpos) * p.H + h) * D;
 #pragma unroll 1
         for (int c = ch; c < D / 32; c += 2) {
@@ -386,10 +360,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__
         }
         tc_fence_before();
         mbar_arrive(dq_empty);
-      }
       if (dbgt) p.dbg[it * 16 + 12] = clock64();
     }
-    if (TMA_DQ && threadIdx.x == 0) tma_store_wait<0>();
     // dK, dV of this key tile
     const int kpos = k0 + r;
     if (n_it > 0) {
@@ -417,6 +389,267 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__
       }
     } else if (kpos < p.S) {
       // key tile attended by nobody (cannot happen with causal / full attention, kept for windowed edge cases)
+      for (int c = ch * 8; c < D; c += 16) {
+        *reinterpret_cast<uint4*>(p.dv + (int64_t(b) * p.S + kpos) * p.lddv + hk * D + c) = make_uint4(0, 0, 0, 0);
+        *reinterpret_cast<uint4*>(p.dk + (int64_t(b) * p.S + kpos) * p.lddk + hk * D + c) = make_uint4(0, 0, 0, 0);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 8) tmem_dealloc(tmem_base, 512);
+}
+
+// -------------------------------------------------------------------------------------------------
+// Software-pipelined form of the kernel above (default).  Same tiles and the same arithmetic, re-ordered so that the
+// tensor pipe, the TMA unit and the soft-max warps overlap across consecutive (head, query-tile) iterations:
+//   * Q is double-buffered (227 KiB budget: K,V,Q0,Q1,dO tiles + P/dS = 224 KiB at D=128); S_{i+1} = Q_{i+1} K^T is
+//     issued right behind MMA2_i, so it runs while the soft-max warps still drain dQ_i;
+//   * dQ_i accumulates in the dP columns (not the S columns), which is what lets S_{i+1} start early;
+//   * the soft-max work is split in two passes: pass A (P = 2^(S*scale_log2 - lse2), the MUFU-heavy half) needs only S
+//     and overlaps the dO_{i+1} load and the dP_{i+1} MMA; pass B (dS = P * (dP*scale - delta*scale)) follows dp_full;
+//   * dQ_i leaves as asynchronous bulk tensor reductions from the P/dS smem (free between MMA2_i and pass A's P store).
+template <int D>
+__global__ void __launch_bounds__(BWD_THREADS, 1)
+attn_bwd_pipe_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__ CUtensorMap tmk,
+                     const __grid_constant__ CUtensorMap tmv, const __grid_constant__ CUtensorMap tmdo,
+                     const __grid_constant__ CUtensorMap tmdq, const AttnParams p) {
+  constexpr int TILE_BYTES = ATT_TILE * D * 2;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sK = smem;
+  uint8_t* sV = sK + TILE_BYTES;
+  uint8_t* sQ0 = sV + TILE_BYTES;          // Q buffer b at sQ0 + b * TILE_BYTES
+  uint8_t* sdO = sQ0 + 2 * TILE_BYTES;
+  uint8_t* sP = sdO + TILE_BYTES;
+  uint8_t* sdS = sP + 32768;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sdS + 32768);
+  uint64_t* kv_full = bars;
+  uint64_t* q_full = bars + 1;   // [2]
+  uint64_t* do_full = bars + 3;
+  uint64_t* s_full = bars + 4;
+  uint64_t* dp_full = bars + 5;
+  uint64_t* p_full = bars + 6;
+  uint64_t* dq_full = bars + 7;
+  uint64_t* dq_empty = bars + 8;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int jt = blockIdx.x, hk = blockIdx.y, b = blockIdx.z;
+  const int G = p.H / p.Hkv;
+  const int k0 = jt * ATT_TILE;
+  const int nq = (p.S + ATT_TILE - 1) / ATT_TILE;
+  const int i_lo = p.causal ? jt : 0;
+  const int i_hi = p.window > 0 ? min(nq - 1, (k0 + ATT_TILE - 1 + p.window - 1) / ATT_TILE) : nq - 1;
+  const int ni = i_hi - i_lo + 1;
+  const int n_it = ni > 0 ? ni * G : 0;
+  const bool dbg_cta = p.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
+
+  if (warp == 8 && lane == 0) {
+    tma_prefetch_desc(&tmq); tma_prefetch_desc(&tmk); tma_prefetch_desc(&tmv); tma_prefetch_desc(&tmdo);
+    tma_prefetch_desc(&tmdq);
+    mbar_init(kv_full, 1);
+    mbar_init(q_full, 1);
+    mbar_init(q_full + 1, 1);
+    mbar_init(do_full, 1);
+    mbar_init(s_full, 1);
+    mbar_init(dp_full, 1);
+    mbar_init(p_full, 256);
+    mbar_init(dq_full, 1);
+    mbar_init(dq_empty, 256);
+    fence_barrier_init();
+  }
+  if (warp == 8) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_S = tmem_base, tmem_dP = tmem_base + 128, tmem_dV = tmem_base + 256, tmem_dK = tmem_base + 256 + D;
+
+  if (warp == 8) {
+    if (lane == 0 && n_it > 0) {
+      auto q_coords = [&](int it, int& h, int& i) { const int g = it / ni; i = i_lo + (it - g * ni); h = hk * G + g; };
+      int h, i;
+      mbar_expect_tx(kv_full, 2 * TILE_BYTES);
+      load_tile<D>(sK, &tmk, kv_full, hk * D, k0, b);
+      load_tile<D>(sV, &tmv, kv_full, hk * D, k0, b);
+      q_coords(0, h, i);
+      mbar_expect_tx(q_full, TILE_BYTES);
+      load_tile<D>(sQ0, &tmq, q_full, h * D, i * ATT_TILE, b);
+      mbar_expect_tx(do_full, TILE_BYTES);
+      load_tile<D>(sdO, &tmdo, do_full, h * D, i * ATT_TILE, b);
+      if (n_it > 1) {
+        q_coords(1, h, i);
+        mbar_expect_tx(q_full + 1, TILE_BYTES);
+        load_tile<D>(sQ0 + TILE_BYTES, &tmq, q_full + 1, h * D, i * ATT_TILE, b);
+      }
+      mbar_wait(kv_full, 0);
+      mbar_wait(q_full, 0);
+      tc_fence_after();
+      mma_kk<128, D>(tmem_S, smem_u32(sQ0), smem_u32(sK), false);      // S_0 = Q_0 K^T
+      tc_commit(s_full);
+      for (int it = 0; it < n_it; ++it) {
+        const bool dbg = dbg_cta && it < 64;
+        const uint32_t sQ = smem_u32(sQ0 + (it & 1) * TILE_BYTES);
+        if (dbg) p.dbg[it * 24 + 0] = clock64();
+        mbar_wait(do_full, it & 1);
+        if (dbg) p.dbg[it * 24 + 1] = clock64();
+        if (it > 0) mbar_wait(dq_empty, (it - 1) & 1);                  // dQ_{it-1} read out of the dP columns
+        if (dbg) p.dbg[it * 24 + 2] = clock64();
+        tc_fence_after();
+        mma_kk<128, D>(tmem_dP, smem_u32(sdO), smem_u32(sV), false);    // dP = dO V^T
+        tc_commit(dp_full);
+        mbar_wait(p_full, it & 1);
+        if (dbg) p.dbg[it * 24 + 3] = clock64();
+        tc_fence_after();
+        mma_mnmn<D>(tmem_dV, smem_u32(sP), smem_u32(sdO), it > 0);      // dV += P^T dO
+        mma_mnmn<D>(tmem_dK, smem_u32(sdS), sQ, it > 0);                // dK += dS^T Q
+        mma_kmn<D>(tmem_dP, smem_u32(sdS), smem_u32(sK), false);        // dQ  = dS K   (into the dP columns)
+        tc_commit(dq_full);
+        if (it + 1 < n_it) {
+          mbar_wait(q_full + ((it + 1) & 1), ((it + 1) >> 1) & 1);
+          tc_fence_after();
+          mma_kk<128, D>(tmem_S, smem_u32(sQ0 + ((it + 1) & 1) * TILE_BYTES), smem_u32(sK), false);   // S_{it+1}
+          tc_commit(s_full);
+        }
+        if (dbg) p.dbg[it * 24 + 4] = clock64();
+        mbar_wait(dq_full, it & 1);                                     // MMA2_it retired: dO, Q[it&1], P, dS reusable
+        if (dbg) p.dbg[it * 24 + 5] = clock64();
+        if (it + 1 < n_it) {
+          q_coords(it + 1, h, i);
+          mbar_expect_tx(do_full, TILE_BYTES);
+          load_tile<D>(sdO, &tmdo, do_full, h * D, i * ATT_TILE, b);
+        }
+        if (it + 2 < n_it) {
+          q_coords(it + 2, h, i);
+          mbar_expect_tx(q_full + (it & 1), TILE_BYTES);
+          load_tile<D>(sQ0 + (it & 1) * TILE_BYTES, &tmq, q_full + (it & 1), h * D, i * ATT_TILE, b);
+        }
+      }
+    }
+    __syncwarp();
+  } else {
+    const int qd = warp & 3, ch = warp >> 2;
+    const int r = qd * 32 + lane;
+    const uint32_t lane_base = uint32_t(qd * 32) << 16;
+    for (int it = 0; it < n_it; ++it) {
+      const int g = it / ni, i = i_lo + (it - g * ni);
+      const int h = hk * G + g;
+      const int qpos = i * ATT_TILE + r;
+      const bool valid = qpos < p.S;
+      float lse2 = 0.f, delta = 0.f;
+      if (valid) {
+        lse2 = p.lse[(int64_t(b) * p.H + h) * p.S + qpos] * LOG2E;
+        delta = p.delta[(int64_t(b) * p.H + h) * p.S + qpos];
+      }
+      const bool row_ok = valid && lse2 != -INFINITY;
+      if (!row_ok) lse2 = 0.f;
+      const bool need_mask = (p.causal && k0 + ATT_TILE - 1 > i * ATT_TILE) || (k0 + ATT_TILE > p.S) ||
+                             (p.window > 0 && i * ATT_TILE + ATT_TILE - 1 - k0 >= p.window);
+      const bool dbgt = dbg_cta && it < 64 && threadIdx.x == 0;
+      if (dbgt) p.dbg[it * 24 + 8] = clock64();
+      mbar_wait(s_full, it & 1);
+      if (dbgt) p.dbg[it * 24 + 9] = clock64();
+      tc_fence_after();
+      int lo, hi;
+      row_window(qpos, k0, p.S, p.causal, p.window, lo, hi);
+      if (!row_ok) { lo = 1; hi = 0; }
+      const bool mask_tile = need_mask || !__all_sync(0xffffffffu, row_ok);
+      const float delta_s = delta * p.scale;
+      // pass A: P for this thread's 64 columns (chunks 2ch, 2ch+1), kept in registers for pass B
+      float pf[2][32];
+#pragma unroll
+      for (int cc = 0; cc < 2; ++cc) {
+        uint32_t vs[32];
+        tmem_ld32(tmem_S + lane_base + (ch * 2 + cc) * 32, vs);
+        tmem_ld_wait();
+        if (mask_tile) chunk_exp<true>(vs, pf[cc], p.scale_log2, lse2, (ch * 2 + cc) * 32, lo, hi);
+        else chunk_exp<false>(vs, pf[cc], p.scale_log2, lse2, (ch * 2 + cc) * 32, lo, hi);
+      }
+      if (dbgt) p.dbg[it * 24 + 10] = clock64();
+      if (it > 0) {  // the previous tile's first dQ reduction group must have read the P half of the staging smem out
+        if (threadIdx.x == 0) tma_store_wait_read<1>();
+        bar_sync_softmax8();
+      }
+      if (dbgt) p.dbg[it * 24 + 11] = clock64();
+#pragma unroll
+      for (int cc = 0; cc < 2; ++cc) store_row_chunk_sw128(sP, r, ch * 2 + cc, pf[cc]);
+      mbar_wait(dp_full, it & 1);
+      if (dbgt) p.dbg[it * 24 + 12] = clock64();
+      tc_fence_after();
+#pragma unroll
+      for (int cc = 0; cc < 2; ++cc) {
+        uint32_t vd[32];
+        float fd[32];
+        tmem_ld32(tmem_dP + lane_base + (ch * 2 + cc) * 32, vd);
+        tmem_ld_wait();
+#pragma unroll
+        for (int e = 0; e < 32; ++e) fd[e] = pf[cc][e] * fmaf(__uint_as_float(vd[e]), p.scale, -delta_s);
+        if (cc == 0 && it > 0) {  // ... and the second group the dS half
+          if (threadIdx.x == 0) tma_store_wait_read<0>();
+          bar_sync_softmax8();
+        }
+        store_row_chunk_sw128(sdS, r, ch * 2 + cc, fd);
+      }
+      fence_proxy_async_smem();
+      tc_fence_before();
+      mbar_arrive(p_full);
+      if (dbgt) p.dbg[it * 24 + 13] = clock64();
+      mbar_wait(dq_full, it & 1);
+      if (dbgt) p.dbg[it * 24 + 14] = clock64();
+      tc_fence_after();
+      // MMA2 has retired, so P/dS are dead: stage the fp32 dQ tile there as D/32 128B-swizzled [128 x 32] boxes
+#pragma unroll 1
+      for (int c = ch; c < D / 32; c += 2) {
+        uint32_t v[32];
+        tmem_ld32(tmem_dP + lane_base + c * 32, v);
+        tmem_ld_wait();
+        uint8_t* rowp = sP + c * 16384 + r * 128;
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+          *reinterpret_cast<uint4*>(rowp + ((q ^ (r & 7)) * 16)) = make_uint4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
+      }
+      fence_proxy_async_smem();
+      tc_fence_before();
+      mbar_arrive(dq_empty);
+      bar_sync_softmax8();
+      if (threadIdx.x == 0) {   // two bulk groups: the boxes staged in sP, then (D=128) the boxes staged in sdS
+#pragma unroll
+        for (int c = 0; c < 2; ++c) tma_reduce_add_3d(&tmdq, sP + c * 16384, h * D + c * 32, i * ATT_TILE, b);
+        tma_store_commit();
+#pragma unroll
+        for (int c = 2; c < D / 32; ++c) tma_reduce_add_3d(&tmdq, sP + c * 16384, h * D + c * 32, i * ATT_TILE, b);
+        tma_store_commit();
+      }
+      if (dbgt) p.dbg[it * 24 + 15] = clock64();
+    }
+    if (threadIdx.x == 0) tma_store_wait<0>();
+    // dK, dV of this key tile
+    const int kpos = k0 + r;
+    if (n_it > 0) {
+#pragma unroll 1
+      for (int which = 0; which < 2; ++which) {
+        const uint32_t src = which == 0 ? tmem_dV : tmem_dK;
+        const float sc = which == 0 ? p.inv_v_div : p.inv_k_div;
+        __nv_bfloat16* dst = which == 0 ? p.dv + (int64_t(b) * p.S + kpos) * p.lddv + hk * D
+                                        : p.dk + (int64_t(b) * p.S + kpos) * p.lddk + hk * D;
+#pragma unroll 1
+        for (int c = ch; c < D / 32; c += 2) {
+          uint32_t v[32];
+          tmem_ld32(src + lane_base + c * 32, v);
+          tmem_ld_wait();
+          if (kpos < p.S) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+              *reinterpret_cast<uint4*>(dst + c * 32 + q * 8) = make_uint4(
+                  pack_bf16x2(__uint_as_float(v[q * 8]) * sc, __uint_as_float(v[q * 8 + 1]) * sc),
+                  pack_bf16x2(__uint_as_float(v[q * 8 + 2]) * sc, __uint_as_float(v[q * 8 + 3]) * sc),
+                  pack_bf16x2(__uint_as_float(v[q * 8 + 4]) * sc, __uint_as_float(v[q * 8 + 5]) * sc),
+                  pack_bf16x2(__uint_as_float(v[q * 8 + 6]) * sc, __uint_as_float(v[q * 8 + 7]) * sc));
+          }
+        }
+      }
+    } else if (kpos < p.S) {
       for (int c = ch * 8; c < D; c += 16) {
         *reinterpret_cast<uint4*>(p.dv + (int64_t(b) * p.S + kpos) * p.lddv + hk * D + c) = make_uint4(0, 0, 0, 0);
         *reinterpret_cast<uint4*>(p.dk + (int64_t(b) * p.S + kpos) * p.lddk + hk * D + c) = make_uint4(0, 0, 0, 0);
@@ -473,6 +706,8 @@ template <int D, int BN>
 static int fwd_smem_bytes() { return ATT_TILE * D * 2 + 4 * BN * D * 2 + ATT_TILE * BN * 2 + 128; }
 template <int D>
 static int bwd_smem_bytes() { return 4 * ATT_TILE * D * 2 + 65536 + 1024 + 256; }
+template <int D>
+static int bwd_pipe_smem_bytes() { return 5 * ATT_TILE * D * 2 + 65536 + 1024 + 256; }
 
 static int check_common(const void* q, const void* k, const void* v, int64_t ldq, int64_t ldk, int64_t ldv, int B, int S,
                         int H, int Hkv, int D) {
@@ -501,10 +736,10 @@ static int launch_fwd(const CUtensorMap& tq, const CUtensorMap& tk, const CUtens
   return LRP_OK;
 }
 
-template <int D, bool TMA_DQ>
+template <int D>
 static int launch_bwd(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const CUtensorMap& tdo,
-                      const CUtensorMap& tdq, const AttnParams& p, cudaStream_t st) {
-  auto kern = attn_bwd_kernel<D, TMA_DQ>;
+                      const AttnParams& p, cudaStream_t st) {
+  auto kern = attn_bwd_kernel<D>;
   static bool done = false;
   if (!done) {
     cudaError_t ce = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bwd_smem_bytes<D>());
@@ -512,7 +747,23 @@ static int launch_bwd(const CUtensorMap& tq, const CUtensorMap& tk, const CUtens
     done = true;
   }
   dim3 grid((p.S + ATT_TILE - 1) / ATT_TILE, p.Hkv, p.B);
-  kern<<<grid, BWD_THREADS, bwd_smem_bytes<D>(), st>>>(tq, tk, tv, tdo, tdq, p);
+  kern<<<grid, BWD_THREADS, bwd_smem_bytes<D>(), st>>>(tq, tk, tv, tdo, p);
+  LRP_CHECK_LAUNCH();
+  return LRP_OK;
+}
+
+template <int D>
+static int launch_bwd_pipe(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const CUtensorMap& tdo,
+                           const CUtensorMap& tdq, const AttnParams& p, cudaStream_t st) {
+  auto kern = attn_bwd_pipe_kernel<D>;
+  static bool done = false;
+  if (!done) {
+    cudaError_t ce = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bwd_pipe_smem_bytes<D>());
+    if (ce != cudaSuccess) return set_error(LRP_ERR_CUDA, cudaGetErrorString(ce));
+    done = true;
+  }
+  dim3 grid((p.S + ATT_TILE - 1) / ATT_TILE, p.Hkv, p.B);
+  kern<<<grid, BWD_THREADS, bwd_pipe_smem_bytes<D>(), st>>>(tq, tk, tv, tdo, tdq, p);
   LRP_CHECK_LAUNCH();
   return LRP_OK;
 }
@@ -585,26 +836,38 @@ int lrp_attn_bwd(const void* q, const void* k, const void* v, int64_t ldq, int64
   p.inv_v_div = v_div > 0.f ? 1.f / v_div : 0.f;
   long long* dbg_dev = nullptr;
   if (getenv("LRP_ATTN_DEBUG") != nullptr && int64_t(B) * S >= 4096) {
-    cudaMalloc(&dbg_dev, 64 * 16 * sizeof(long long));
-    cudaMemset(dbg_dev, 0, 64 * 16 * sizeof(long long));
+    cudaMalloc(&dbg_dev, 64 * 24 * sizeof(long long));
+    cudaMemset(dbg_dev, 0, 64 * 24 * sizeof(long long));
     p.dbg = dbg_dev;
   }
-  // dQ tile reductions: bulk tensor reductions through smem by default; LRP_ATTN_DQ=red keeps the per-thread red.global
-  // form for A/B measurements (profiles/r01_attn_bwd_v1_timeline.txt)
-  const char* dqsel = getenv("LRP_ATTN_DQ");
-  const bool tma_dq = !(dqsel != nullptr && !strcmp(dqsel, "red"));
-  CUtensorMap tdq;
-  if (int e = make_tmap_3d_f32(&tdq, dq_acc_ws, uint64_t(HD), S, B, HD, uint64_t(S) * HD, 32, ATT_TILE)) return e;
+  // default: the software-pipelined kernel with bulk-tensor dQ reductions; LRP_ATTN_BWD=v1 selects the first-generation
+  // kernel (per-thread red.global) for A/B measurements
+  const bool pipe = !(sel != nullptr && !strcmp(sel, "v1"));
   int le;
-  if (D == 128) le = tma_dq ? launch_bwd<128, true>(tq, tk, tv, tdo, tdq, p, st) : launch_bwd<128, false>(tq, tk, tv, tdo, tdq, p, st);
-  else le = tma_dq ? launch_bwd<64, true>(tq, tk, tv, tdo, tdq, p, st) : launch_bwd<64, false>(tq, tk, tv, tdo, tdq, p, st);
+  if (pipe) {
+    CUtensorMap tdq;
+    if (int e = make_tmap_3d_f32(&tdq, dq_acc_ws, uint64_t(HD), S, B, HD, uint64_t(S) * HD, 32, ATT_TILE)) return e;
+    le = D == 128 ? launch_bwd_pipe<128>(tq, tk, tv, tdo, tdq, p, st) : launch_bwd_pipe<64>(tq, tk, tv, tdo, tdq, p, st);
+  } else {
+    le = D == 128 ? launch_bwd<128>(tq, tk, tv, tdo, p, st) : launch_bwd<64>(tq, tk, tv, tdo, p, st);
+  }
   if (le) return le;
   if (dbg_dev != nullptr) {
     static bool printed = false;
-    long long h[64 * 16];
+    long long h[64 * 24];
     cudaDeviceSynchronize();
     cudaMemcpy(h, dbg_dev, sizeof(h), cudaMemcpyDeviceToHost);
     cudaFree(dbg_dev);
+    if (!printed && pipe) {
+      printed = true;
+      printf("pipe it | ctl: do_wait dq_empty dP+p_full mma2+S dq_full | thr: wait_s passA stage_wait storeP+wait_dp passB wait_dq drain | iter\n");
+      for (int it = 1; it < 24; ++it) {
+        const long long* r = h + it * 24;
+        printf("%2d | %5lld %5lld %5lld %5lld %5lld | %5lld %5lld %5lld %5lld %5lld %5lld %5lld | %6lld\n", it, r[1] - r[0], r[2] - r[1],
+               r[3] - r[2], r[4] - r[3], r[5] - r[4], r[9] - r[8], r[10] - r[9], r[11] - r[10], r[12] - r[11], r[13] - r[12],
+               r[14] - r[13], r[15] - r[14], r[0] - (h + (it - 1) * 24)[0]);
+      }
+    }
     if (!printed) {
       printed = true;
       printf("v1 it | ctl: load_wait dq_empty mma1 p_full mma2 dq_full | thr: wait_s compute+store wait_dq drain | iter\n");
