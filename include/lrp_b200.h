@@ -68,7 +68,8 @@ typedef struct lrp_epilogue {
 } lrp_epilogue_t;
 
 /* Generic tcgen05 GEMM, A [M,K] bf16.  b_layout 0: B is [N,K] (NT);  b_layout 1: B is [K,N] (NN).
- * tile_n = 0 lets the library choose (128 or 256). */
+ * tile_n = 0 lets the library choose (one-CTA 128 x 128 / 128 x 256 tiles, or 256 x 256 tiles on CTA pairs with
+ * tcgen05 cta_group::2 when they fill the machine); 128 / 256 force a one-CTA tile, 2 forces the CTA-pair kernel. */
 int lrp_gemm_bf16(const void* A, int64_t lda, const void* B, int64_t ldb, int b_layout, int M, int N, int K,
                   const lrp_epilogue_t* epi, int tile_n, void* stream);
 

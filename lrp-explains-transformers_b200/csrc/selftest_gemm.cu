@@ -257,18 +257,29 @@ int main(int argc, char** argv) {
                            {64, 2048, 512}};
   for (auto& s : shapes)
     for (int layout = 0; layout < 2; ++layout)
-      for (int bn : {128, 256})
+      for (int bn : {128, 256, 2})   // 2 = forced CTA-pair (cta_group::2) kernel
         for (int mode = 0; mode < 2; ++mode) check_case(s[0], s[1], s[2], layout, bn, mode);
   // multi-tile-per-CTA persistent path
   check_case(128 * 40, 256 * 8, 512, 0, 256, 0);
   check_case(128 * 40, 256 * 8, 512, 1, 256, 1);
   check_case(128 * 37, 128 * 9, 192, 1, 128, 0);
+  check_case(256 * 80, 256 * 4, 512, 0, 2, 0);      // CTA pairs, several tiles per pair
+  check_case(256 * 80 + 77, 256 * 4 + 8, 520, 1, 2, 1);
+  check_case(4096, 4096, 1024, 0, 0, 1);            // auto -> CTA pairs
+  check_case(4096, 4096, 1024, 1, 0, 0);
   eps_case(128, 256, 256, false, false);
   eps_case(300, 520, 200, true, false);
   eps_case(1500, 1024, 768, true, false);
   eps_case(4096, 2048, 1024, false, false);
   printf(g_fail ? "SELFTEST FAILED (%d)\n" : "SELFTEST PASSED\n", g_fail);
   if (perf) {
+    perf_case(8192, 4096, 4096, 0, 0, 0);    // auto = CTA pairs
+    perf_case(8192, 4096, 4096, 1, 0, 0);
+    perf_case(16384, 28672, 4096, 0, 0, 0);
+    perf_case(16384, 4096, 14336, 0, 0, 1);
+    perf_case(16384, 4096, 28672, 1, 0, 1);
+    perf_case(16384, 14336, 4096, 1, 0, 0);
+    perf_case(16384, 6144, 4096, 0, 0, 0);
     perf_case(8192, 4096, 4096, 0, 256, 0);
     perf_case(8192, 4096, 4096, 0, 128, 0);
     perf_case(8192, 4096, 4096, 1, 256, 0);
