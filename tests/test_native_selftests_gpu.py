@@ -1,5 +1,5 @@
 """GPU: the native (no Python, no torch) self-tests of liblrp_b200.so through the C ABI: tcgen05 GEMM incl. the fused
-eps-LRP Linear kernel, and flash AttnLRP forward/backward in both backward variants."""
+eps-LRP Linear kernel, and flash AttnLRP forward/backward in all three backward variants (the GEMM self-test covers the one-CTA and the CTA-pair kernels)."""
 import os
 import subprocess
 
@@ -20,6 +20,8 @@ def test_native_gemm_and_fused_eps_linear():
     _run("selftest_gemm")
 
 
-@pytest.mark.parametrize("variant", ["v1", "v2"])
+# "pipe" = the default software-pipelined kernel with bulk-tensor dQ reductions; v1 = first-generation red.global kernel;
+# v2 = two-pass atomic-free kernels (always used for head_dim 256)
+@pytest.mark.parametrize("variant", ["pipe", "v1", "v2"])
 def test_native_flash_attnlrp(variant):
     _run("selftest_attn", {"LRP_ATTN_BWD": variant})
