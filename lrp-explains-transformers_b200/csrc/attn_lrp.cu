@@ -82,7 +82,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__
       load_tile<D, BN>(sV, &tmv, &v_full[0], hk * D, j_lo * BN, b);
       for (int jj = 0; jj < n; ++jj) {
         const int st = jj & 1;
-        if (jj + 1 < n) {
+        if (jj == 0) mbar_wait(q_full, 0);
+        mbar_wait(&k_full[st], (jj >> 1) & 1);
+        tc_fence_after();
+        mma_kk<BN, D, 16384, BN * 128>(tmem_S, smem_u32(sQ), smem_u32(sK + st * KV_BYTES), false);   // S = Q K^T
+        tc_commit(s_full);
+        if (jj + 1 < n) {   // prefetch the next K/V tile (after S has been issued: the wait below is for P.V of tile jj-1)
           const int ns = st ^ 1;
           if (jj >= 1) mbar_wait(&kv_empty[ns], ((jj - 1) >> 1) & 1);
           mbar_expect_tx(&k_full[ns], KV_BYTES);
@@ -90,11 +95,6 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__
           mbar_expect_tx(&v_full[ns], KV_BYTES);
           load_tile<D, BN>(sV + ns * KV_BYTES, &tmv, &v_full[ns], hk * D, (j_lo + jj + 1) * BN, b);
         }
-        if (jj == 0) mbar_wait(q_full, 0);
-        mbar_wait(&k_full[st], (jj >> 1) & 1);
-        tc_fence_after();
-        mma_kk<BN, D, 16384, BN * 128>(tmem_S, smem_u32(sQ), smem_u32(sK + st * KV_BYTES), false);   // S = Q K^T
-        tc_commit(s_full);
         mbar_wait(p_full, jj & 1);
         mbar_wait(&v_full[st], (jj >> 1) & 1);
         tc_fence_after();
@@ -118,14 +118,24 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__
       tc_fence_after();
       int lo, hi;
       row_window(qpos, kbase, p.S, p.causal, p.window, lo, hi);
-      // pass 1: row maximum of the raw scores (scale > 0, so the order is preserved)
+      // pass 1: row maximum of the raw scores (scale > 0, so the order is preserved).  With 64-key tiles the row's 64
+      // scores stay in registers for pass 2 (one TMEM read instead of two).
       float mx = -INFINITY;
-#pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        uint32_t v[32];
-        tmem_ld32(tmem_S + lane_base + c * 32, v);
+      uint32_t sv[BN == 64 ? 2 : 1][32];
+      if constexpr (BN == 64) {
+        tmem_ld32(tmem_S + lane_base, sv[0]);
+        tmem_ld32(tmem_S + lane_base + 32, sv[1]);
         tmem_ld_wait();
-        mx = fmaxf(mx, need_mask ? chunk_max<true>(v, c * 32, lo, hi) : chunk_max<false>(v, c * 32, lo, hi));
+        mx = need_mask ? fmaxf(chunk_max<true>(sv[0], 0, lo, hi), chunk_max<true>(sv[1], 32, lo, hi))
+                       : fmaxf(chunk_max<false>(sv[0], 0, lo, hi), chunk_max<false>(sv[1], 32, lo, hi));
+      } else {
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+          uint32_t v[32];
+          tmem_ld32(tmem_S + lane_base + c * 32, v);
+          tmem_ld_wait();
+          mx = fmaxf(mx, need_mask ? chunk_max<true>(v, c * 32, lo, hi) : chunk_max<false>(v, c * 32, lo, hi));
+        }
       }
       const float m_new = fmaxf(m_used, mx * p.scale_log2);
       float alpha = 1.f;
@@ -155,15 +165,25 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__
       // pass 2: probabilities -> smem (bf16), running sum
       float lsum = 0.f;
       const float msub = (m_used == -INFINITY) ? 0.f : m_used;
+      if constexpr (BN == 64) {
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          float f[32];
+          lsum += need_mask ? chunk_exp<true>(sv[c], f, p.scale_log2, msub, c * 32, lo, hi)
+                            : chunk_exp<false>(sv[c], f, p.scale_log2, msub, c * 32, lo, hi);
+          store_row_chunk_sw128(sP, r, c, f);
+        }
+      } else {
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        uint32_t v[32];
-        float f[32];
-        tmem_ld32(tmem_S + lane_base + c * 32, v);
-        tmem_ld_wait();
-        lsum += need_mask ? chunk_exp<true>(v, f, p.scale_log2, msub, c * 32, lo, hi)
-                          : chunk_exp<false>(v, f, p.scale_log2, msub, c * 32, lo, hi);
-        store_row_chunk_sw128(sP, r, c, f);
+        for (int c = 0; c < BN / 32; ++c) {
+          uint32_t v[32];
+          float f[32];
+          tmem_ld32(tmem_S + lane_base + c * 32, v);
+          tmem_ld_wait();
+          lsum += need_mask ? chunk_exp<true>(v, f, p.scale_log2, msub, c * 32, lo, hi)
+                            : chunk_exp<false>(v, f, p.scale_log2, msub, c * 32, lo, hi);
+          store_row_chunk_sw128(sP, r, c, f);
+        }
       }
       l = l * alpha + lsum;
       fence_proxy_async_smem();
@@ -432,7 +452,10 @@ attn_bwd_pipe_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_const
   uint64_t* p_full = bars + 6;
   uint64_t* dq_full = bars + 7;
   uint64_t* dq_empty = bars + 8;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+  uint64_t* p_ready = bars + 9;
+  uint64_t* dq_ready = bars + 10;
+  uint64_t* dv_done = bars + 11;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int jt = blockIdx.x, hk = blockIdx.y, b = blockIdx.z;
@@ -457,6 +480,9 @@ attn_bwd_pipe_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_const
     mbar_init(p_full, 256);
     mbar_init(dq_full, 1);
     mbar_init(dq_empty, 256);
+    mbar_init(p_ready, 256);
+    mbar_init(dq_ready, 1);
+    mbar_init(dv_done, 1);
     fence_barrier_init();
   }
   if (warp == 8) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
@@ -499,12 +525,25 @@ attn_bwd_pipe_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_const
         tc_fence_after();
         mma_kk<128, D>(tmem_dP, smem_u32(sdO), smem_u32(sV), false);    // dP = dO V^T
         tc_commit(dp_full);
+        mbar_wait(p_ready, it & 1);
+        tc_fence_after();
+        mma_mnmn<D>(tmem_dV, smem_u32(sP), smem_u32(sdO), it > 0);      // dV += P^T dO   (runs under pass B)
+        tc_commit(dv_done);                                             // last reader of the dO tile
         mbar_wait(p_full, it & 1);
         if (dbg) p.dbg[it * 24 + 3] = clock64();
+        if (it + 1 < n_it) {
+          // dO_{it+1}: dV_it (the last reader of the dO tile) retired during pass B.  Issued HERE, ahead of this tile's dQ
+          // reductions: the TMA unit serves its queue in order, and a load queued behind a 32 KiB reduction arrives
+          // ~3k cycles later (profiles/r01_attn_bwd_pipe_timeline.txt).
+          mbar_wait(dv_done, it & 1);
+          q_coords(it + 1, h, i);
+          mbar_expect_tx(do_full, TILE_BYTES);
+          load_tile<D>(sdO, &tmdo, do_full, h * D, i * ATT_TILE, b);
+        }
         tc_fence_after();
-        mma_mnmn<D>(tmem_dV, smem_u32(sP), smem_u32(sdO), it > 0);      // dV += P^T dO
-        mma_mnmn<D>(tmem_dK, smem_u32(sdS), sQ, it > 0);                // dK += dS^T Q
         mma_kmn<D>(tmem_dP, smem_u32(sdS), smem_u32(sK), false);        // dQ  = dS K   (into the dP columns)
+        tc_commit(dq_ready);                                            // dV, dQ retired: P smem and dQ readable
+        mma_mnmn<D>(tmem_dK, smem_u32(sdS), sQ, it > 0);                // dK += dS^T Q   (runs under the first dQ half-drain)
         tc_commit(dq_full);
         if (it + 1 < n_it) {
           mbar_wait(q_full + ((it + 1) & 1), ((it + 1) >> 1) & 1);
@@ -513,13 +552,8 @@ attn_bwd_pipe_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_const
           tc_commit(s_full);
         }
         if (dbg) p.dbg[it * 24 + 4] = clock64();
-        mbar_wait(dq_full, it & 1);                                     // MMA2_it retired: dO, Q[it&1], P, dS reusable
+        mbar_wait(dq_full, it & 1);                                     // MMA2_it retired: Q[it&1], P, dS reusable
         if (dbg) p.dbg[it * 24 + 5] = clock64();
-        if (it + 1 < n_it) {
-          q_coords(it + 1, h, i);
-          mbar_expect_tx(do_full, TILE_BYTES);
-          load_tile<D>(sdO, &tmdo, do_full, h * D, i * ATT_TILE, b);
-        }
         if (it + 2 < n_it) {
           q_coords(it + 2, h, i);
           mbar_expect_tx(q_full + (it & 1), TILE_BYTES);
@@ -532,16 +566,28 @@ attn_bwd_pipe_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_const
     const int qd = warp & 3, ch = warp >> 2;
     const int r = qd * 32 + lane;
     const uint32_t lane_base = uint32_t(qd * 32) << 16;
+    // (lse, delta) of this thread's query row are fetched one tile ahead: the global-load latency hides behind the dQ drain
+    float lse_n = 0.f, delta_n = 0.f;
+    auto fetch_row = [&](int it) {
+      lse_n = 0.f; delta_n = 0.f;
+      if (it < n_it) {
+        const int g = it / ni, i = i_lo + (it - g * ni);
+        const int qpos = i * ATT_TILE + r;
+        if (qpos < p.S) {
+          const int64_t idx = (int64_t(b) * p.H + hk * G + g) * p.S + qpos;
+          lse_n = p.lse[idx];
+          delta_n = p.delta[idx];
+        }
+      }
+    };
+    fetch_row(0);
     for (int it = 0; it < n_it; ++it) {
       const int g = it / ni, i = i_lo + (it - g * ni);
       const int h = hk * G + g;
       const int qpos = i * ATT_TILE + r;
       const bool valid = qpos < p.S;
-      float lse2 = 0.f, delta = 0.f;
-      if (valid) {
-        lse2 = p.lse[(int64_t(b) * p.H + h) * p.S + qpos] * LOG2E;
-        delta = p.delta[(int64_t(b) * p.H + h) * p.S + qpos];
-      }
+      float lse2 = lse_n * LOG2E;
+      const float delta = delta_n;
       const bool row_ok = valid && lse2 != -INFINITY;
       if (!row_ok) lse2 = 0.f;
       const bool need_mask = (p.causal && k0 + ATT_TILE - 1 > i * ATT_TILE) || (k0 + ATT_TILE > p.S) ||
@@ -574,6 +620,8 @@ attn_bwd_pipe_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_const
       if (dbgt) p.dbg[it * 24 + 11] = clock64();
 #pragma unroll
       for (int cc = 0; cc < 2; ++cc) store_row_chunk_sw128(sP, r, ch * 2 + cc, pf[cc]);
+      fence_proxy_async_smem();
+      mbar_arrive(p_ready);
       mbar_wait(dp_full, it & 1);
       if (dbgt) p.dbg[it * 24 + 12] = clock64();
       tc_fence_after();
@@ -595,28 +643,45 @@ attn_bwd_pipe_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_const
       tc_fence_before();
       mbar_arrive(p_full);
       if (dbgt) p.dbg[it * 24 + 13] = clock64();
-      mbar_wait(dq_full, it & 1);
+      fetch_row(it + 1);
+      mbar_wait(dq_ready, it & 1);
       if (dbgt) p.dbg[it * 24 + 14] = clock64();
       tc_fence_after();
-      // MMA2 has retired, so P/dS are dead: stage the fp32 dQ tile there as D/32 128B-swizzled [128 x 32] boxes
-#pragma unroll 1
-      for (int c = ch; c < D / 32; c += 2) {
+      // dV and dQ have retired: P is dead, so the first two [128 x 32] fp32 boxes of the dQ tile are staged in sP (128B-
+      // swizzled) and leave as the first bulk-reduction group while dK += dS^T Q still reads dS
+      {
         uint32_t v[32];
-        tmem_ld32(tmem_dP + lane_base + c * 32, v);
+        tmem_ld32(tmem_dP + lane_base + ch * 32, v);
         tmem_ld_wait();
-        uint8_t* rowp = sP + c * 16384 + r * 128;
+        uint8_t* rowp = sP + ch * 16384 + r * 128;
 #pragma unroll
         for (int q = 0; q < 8; ++q)
           *reinterpret_cast<uint4*>(rowp + ((q ^ (r & 7)) * 16)) = make_uint4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
       }
       fence_proxy_async_smem();
-      tc_fence_before();
-      mbar_arrive(dq_empty);
       bar_sync_softmax8();
-      if (threadIdx.x == 0) {   // two bulk groups: the boxes staged in sP, then (D=128) the boxes staged in sdS
+      if (threadIdx.x == 0) {
 #pragma unroll
         for (int c = 0; c < 2; ++c) tma_reduce_add_3d(&tmdq, sP + c * 16384, h * D + c * 32, i * ATT_TILE, b);
         tma_store_commit();
+      }
+      if (dbgt) p.dbg[it * 24 + 16] = clock64();
+      mbar_wait(dq_full, it & 1);   // dK retired: dS is dead too
+      if (dbgt) p.dbg[it * 24 + 17] = clock64();
+      if (D > 64) {
+        uint32_t v[32];
+        tmem_ld32(tmem_dP + lane_base + (ch + 2) * 32, v);
+        tmem_ld_wait();
+        uint8_t* rowp = sP + (ch + 2) * 16384 + r * 128;
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+          *reinterpret_cast<uint4*>(rowp + ((q ^ (r & 7)) * 16)) = make_uint4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
+        fence_proxy_async_smem();
+      }
+      tc_fence_before();
+      mbar_arrive(dq_empty);
+      bar_sync_softmax8();
+      if (threadIdx.x == 0) {   // second bulk group (empty for D = 64): the boxes staged in sdS
 #pragma unroll
         for (int c = 2; c < D / 32; ++c) tma_reduce_add_3d(&tmdq, sP + c * 16384, h * D + c * 32, i * ATT_TILE, b);
         tma_store_commit();
@@ -860,12 +925,14 @@ int lrp_attn_bwd(const void* q, const void* k, const void* v, int64_t ldq, int64
     cudaFree(dbg_dev);
     if (!printed && pipe) {
       printed = true;
-      printf("pipe it | ctl: do_wait dq_empty dP+p_full mma2+S dq_full | thr: wait_s passA stage_wait storeP+wait_dp passB wait_dq drain | iter\n");
-      for (int it = 1; it < 24; ++it) {
+      printf("pipe: clock64 stamps of one CTA relative to the control thread's iteration start\n"
+             "it | ctl: dO_in dq_empty p_full mma2_issued dq_full | thr: start s_full passA stage P_stored+dp_full passB(p_full) dq_ready drain1 dk_done end | iter\n");
+      for (int it = 2; it < 12; ++it) {
         const long long* r = h + it * 24;
-        printf("%2d | %5lld %5lld %5lld %5lld %5lld | %5lld %5lld %5lld %5lld %5lld %5lld %5lld | %6lld\n", it, r[1] - r[0], r[2] - r[1],
-               r[3] - r[2], r[4] - r[3], r[5] - r[4], r[9] - r[8], r[10] - r[9], r[11] - r[10], r[12] - r[11], r[13] - r[12],
-               r[14] - r[13], r[15] - r[14], r[0] - (h + (it - 1) * 24)[0]);
+        const long long t0 = r[0];
+        printf("%2d | %5lld %5lld %5lld %5lld %5lld | %5lld %5lld %5lld %5lld %5lld %5lld %5lld %5lld %5lld %5lld | %6lld\n", it, r[1] - t0, r[2] - t0,
+               r[3] - t0, r[4] - t0, r[5] - t0, r[8] - t0, r[9] - t0, r[10] - t0, r[11] - t0, r[12] - t0, r[13] - t0, r[14] - t0,
+               r[16] - t0, r[17] - t0, r[15] - t0, r[0] - (h + (it - 1) * 24)[0]);
       }
     }
     if (!printed) {
