@@ -236,12 +236,14 @@ int gemm_bf16(const void* A, int64_t lda, const void* B, int64_t ldb, int b_layo
   p.gated_out = reinterpret_cast<__nv_bfloat16*>(epi->gated_out);
   p.gated_act = epi->gated_act;
   p.gated_cp = epi->gated_cp;
+  bool group_forced = false;
   {
     // 16 m-blocks per group measured best on B200 across the Llama shapes (sweep 8/16/32/64 in
     // profiles/r01_gemm_group_m_sweep.txt): A panels of a group stay L2-resident while B panels stream past them.
     static const int forced = getenv("LRP_GROUP_M") ? atoi(getenv("LRP_GROUP_M")) : 0;
     const int g = forced > 0 ? forced : 16;
     p.group_m = g;
+    group_forced = forced > 0;
   }
   int bn = force_bn;
   if (bn == 0) {
@@ -254,7 +256,11 @@ int gemm_bf16(const void* A, int64_t lda, const void* B, int64_t ldb, int b_layo
     // CTA pairs (gemm2_sm100.cu) when the 256 x 256 tiles still fill the 74 pairs; LRP_GEMM_PAIR=0 keeps the one-CTA kernel
     static const int pair_mode = getenv("LRP_GEMM_PAIR") ? atoi(getenv("LRP_GEMM_PAIR")) : 1;
     const int64_t tiles_pair = int64_t((M + 255) / 256) * ((N + 255) / 256);
-    if (pair_mode != 0 && tiles_pair >= sm_count() / 2) return gemm_bf16_pair(A, lda, B, ldb, b_layout, p, stream);
+    if (pair_mode != 0 && tiles_pair >= sm_count() / 2) {
+      // the pair kernel measured best with 4096-row groups (sweep 8/16/32/64 in units of 128 rows: 15.7 / 16.2 / 16.4 / 15.6 attr/s)
+      if (!group_forced) p.group_m = 32;
+      return gemm_bf16_pair(A, lda, B, ldb, b_layout, p, stream);
+    }
   }
   if (bn == 256) {
     return b_layout == 0 ? launch_gemm<256, false>(A, lda, B, ldb, p, stream)
