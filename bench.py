@@ -269,14 +269,14 @@ def run_b200(args):
                 "d2h_bytes_per_step": int(rel_host.numel() * 4)},
         "gpu_launches": int(launches),
         "clocks": clocks,
-        "roofline": {"bound": "tensor", "kernel": "gemm_bf16_kernel (tcgen05, all Linear fwd + LRP dgrad)",
+        "roofline": {"bound": "tensor", "kernel": "gemm_bf16_pair_kernel (tcgen05 cta_group::2, all Linear fwd + LRP dgrad)",
                      "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / peak_tf,
                      "peak_source": f"{peak_src} bf16_tflops_sustained (kernel timed inside a long step)",
                      "launches": len(prof), "share_of_step": gemm_ms / ms_dev if ms_dev else None,
                      # dram__bytes_read.sum + dram__bytes_write.sum of the largest-share launch shape
-                     # (M=16384 N=28672 K=4096, gate|up forward) from profiles/r01_ncu_summary.md: 2.02 GB + 0.92 GB
-                     # per launch vs 1.31 GB algorithmic (A 134 MB + W 235 MB + C 940 MB): W panels re-streamed 8x via L2
-                     "traffic": 2.94e9, "traffic_note": "bytes/launch, ncu --set full, gate|up fwd shape; algorithmic 1.31e9"},
+                     # (M=16384 N=28672 K=4096, gate|up forward) from profiles/r01_ncu_summary.md: 1.45 GB + 0.92 GB
+                     # per launch vs 1.31 GB algorithmic (A 134 MB + W 235 MB + C 940 MB): W panels re-streamed 4x via L2
+                     "traffic": 2.37e9, "traffic_note": "bytes/launch, ncu --set full, gate|up fwd shape; algorithmic 1.31e9"},
     }
     if args.model == "llama3-8b":
         try:

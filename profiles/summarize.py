@@ -78,5 +78,9 @@ if __name__ == "__main__":
             "Kernel times under ncu are cold-cache and serialised (compare shares, not absolutes).\n"]
     for name in ("gemm", "attn_fwd", "attn_bwd"):
         body += [f"\n## {name}\n"] + full(name)
-    open(f"profiles/{tag}_ncu_summary_tables.md", "w").write("\n".join(body) + "\n")
+    try:   # hand-written interpretation, kept next to the tables
+        body += ["", open(f"profiles/{tag}_ncu_reading.md").read()]
+    except OSError:
+        pass
+    open(f"profiles/{tag}_ncu_summary.md", "w").write("\n".join(body) + "\n")
     print("\n".join(body))
