@@ -726,14 +726,17 @@ attn_bwd_pipe_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_const
   if (warp == 8) tmem_dealloc(tmem_base, 512);
 }
 
-// delta[b,h,s] = sum_d o[b,s,h,d] * dO[b,s,h,d]   (one warp per row)
+// delta[b,h,s] = sum_d o[b,s,h,d] * dO[b,s,h,d]   (one warp per row); the same warp clears its row of the fp32 dQ
+// accumulator (zero_acc != NULL), which saves the separate memset node of the atomic / bulk-reduction kernels
 __global__ void __launch_bounds__(256) attn_delta_kernel(const __nv_bfloat16* __restrict__ o,
                                                          const __nv_bfloat16* __restrict__ d_o, float* __restrict__ delta,
-                                                         int B, int S, int H, int D) {
+                                                         float* __restrict__ zero_acc, int B, int S, int H, int D) {
   const int64_t row = blockIdx.x * int64_t(blockDim.x >> 5) + (threadIdx.x >> 5);
   const int64_t rows = int64_t(B) * S * H;
   if (row >= rows) return;
   const int lane = threadIdx.x & 31;
+  if (zero_acc != nullptr)
+    for (int i = lane * 4; i < D; i += 128) *reinterpret_cast<float4*>(zero_acc + row * D + i) = make_float4(0.f, 0.f, 0.f, 0.f);
   float s = 0.f;
   for (int i = lane * 2; i < D; i += 64) {
     const uint32_t a = *reinterpret_cast<const uint32_t*>(o + row * D + i);
@@ -874,18 +877,17 @@ int lrp_attn_bwd(const void* q, const void* k, const void* v, int64_t ldq, int64
   const int64_t HD = int64_t(H) * D;
   if (int e = make_tmap_3d_bf16(&tdo, d_o, uint64_t(HD), S, B, HD, uint64_t(S) * HD, 64, ATT_TILE)) return e;
   const int64_t rows = int64_t(B) * S * H;
-  attn_delta_kernel<<<unsigned((rows + 7) / 8), 256, 0, st>>>((const __nv_bfloat16*)o, (const __nv_bfloat16*)d_o, delta_ws, B, S, H, D);
+  const char* sel = getenv("LRP_ATTN_BWD");
+  const bool two_pass = D == 256 || (sel != nullptr && !strcmp(sel, "v2"));   // head_dim 256 exists only in the two-pass v2 form
+  attn_delta_kernel<<<unsigned((rows + 7) / 8), 256, 0, st>>>((const __nv_bfloat16*)o, (const __nv_bfloat16*)d_o, delta_ws,
+                                                             two_pass ? nullptr : dq_acc_ws, B, S, H, D);
   LRP_CHECK_LAUNCH();
   // LRP_ATTN_BWD=v2 selects the two-kernel pipelined, atomic-free (bit-reproducible) backward of attn_bwd_v2.cu.
   // Measured on B200 it is on par with / slightly slower than this single-kernel version (its 64-wide MMAs are
   // smem-operand bound and S/dP/exp are recomputed for dQ), so the single kernel stays the default.
-  const char* sel = getenv("LRP_ATTN_BWD");
-  if (D == 256 || (sel != nullptr && !strcmp(sel, "v2")))   // head_dim 256 exists only in the two-pass v2 form
+  if (two_pass)
     return attn_bwd_v2(q, k, v, ldq, ldk, ldv, d_o, lse, delta_ws, dq, dk, dv, lddq, lddk, lddv, B, S, H, Hkv, D, scale, causal,
                        window, q_div, k_div, v_div, st);
-  cudaError_t ce = cudaMemsetAsync(dq_acc_ws, 0, size_t(rows) * D * sizeof(float), st);
-  if (ce != cudaSuccess) return set_error(LRP_ERR_CUDA, cudaGetErrorString(ce));
-  note_launch();  // the memset node
   AttnParams p;
   memset(&p, 0, sizeof(p));
   p.B = B; p.S = S; p.H = H; p.Hkv = Hkv; p.D = D;
