@@ -33,13 +33,16 @@ extern "C" {
 #define LRP_ACT_GELU_TANH 1
 #define LRP_ACT_GELU_ERF 2
 
-/* library ABI version (major*1000 + minor) */
+/* library ABI version (major*1000 + minor).  Library plumbing: the reference has no FFI (its version is lxt/__init__.py / setup.py:5) */
 int lrp_version(void);
-/* thread-local description of the last error returned on this thread ("" if none) */
+/* thread-local description of the last error returned on this thread ("" if none); the reference reports failures as Python
+ * warnings / exceptions (lxt/efficient/core.py:39-44), the Python binding turns a non-zero return code into LrpError */
 const char* lrp_last_error(void);
-/* number of GPU kernels (and memset nodes) this library has enqueued in this process so far */
+/* number of GPU kernels (and memset nodes) this library has enqueued in this process so far (bench.py `gpu_launches`; no
+ * reference counterpart: the reference launches stock torch kernels from autograd, lxt/efficient/rules.py:69-127) */
 int64_t lrp_launch_count(void);
-/* 0 if an sm_100 device is present and usable, LRP_ERR_NO_DEVICE otherwise */
+/* 0 if an sm_100 device is present and usable, LRP_ERR_NO_DEVICE otherwise (the reference runs wherever torch runs:
+ * examples/quantized_llama.py:13-22 `device_map="cuda"`; this library has no CPU fallback by design) */
 int lrp_check_device(void);
 
 /* ------------------------------------------------------------------------------------------------
@@ -94,6 +97,8 @@ int lrp_linear_dgrad_fused(const void* gy, int64_t ldg, const void* W, int64_t l
  * as r_out).  `flags_ws` is an int32 scratch of lrp_linear_eps_flags_count(T) entries, zero on entry. */
 int lrp_linear_eps_bwd(const void* x, const void* W, const float* bias, const void* r_out, int r_is_f32,
                        void* r_in, void* s_ws, int32_t* flags_ws, int T, int N, int K, float eps, void* stream);
+/* number of int32 flags lrp_linear_eps_bwd needs in `flags` (zeroed by the caller) for T rows: the per-op workspace query of
+ * SURVEY.md 8(b); replaces the implicit autograd-saved tensors of lxt/explicit/functional.py:340-346 */
 int64_t lrp_linear_eps_flags_count(int T);
 
 /* ------------------------------------------------------------------------------------------------
@@ -105,14 +110,18 @@ int64_t lrp_linear_eps_flags_count(int T);
  * ---------------------------------------------------------------------------------------------- */
 int lrp_rmsnorm_fwd(const void* x, int x_is_f32, const void* w, float w_offset, float eps, void* y, float* rstd,
                     int T, int d, void* stream);
+/* backward of the line above with the variance detached (identity rule): gx = gy * (w + w_offset) * rstd,
+ * lxt/efficient/patches.py:111-123 (autograd of `hidden_states * rsqrt(variance.detach() + eps)`) */
 int lrp_rmsnorm_bwd(const void* gy, const void* w, float w_offset, const float* rstd, void* gx, int gx_is_f32,
                     int accumulate, int T, int d, void* stream);
 
 /* Gemma layer layout `h = residual + post_norm(branch)`: h[t,:] += rmsnorm(y[t,:]) * (w + w_offset), rstd of y saved
- * (transformers modeling_gemma3.py Gemma3DecoderLayer.forward; the backward of the norm is lrp_rmsnorm_bwd). y,w bf16, h fp32. */
+ * (transformers 5.5 modeling_gemma3.py:425,431 under the norm patch lxt/efficient/models/gemma3.py:11-19; the backward of the norm is
+ * lrp_rmsnorm_bwd). y,w bf16, h fp32. */
 int lrp_rmsnorm_fwd_residual(const void* y, const void* w, float w_offset, float eps, float* h, float* rstd, int T, int d,
                              void* stream);
-/* Per-head RMSNorm over D of the q and k slices of a packed [T, ld] bf16 buffer, in place (Gemma-3 / Qwen3 q_norm, k_norm):
+/* Per-head RMSNorm over D of the q and k slices of a packed [T, ld] bf16 buffer, in place (Gemma-3 / Qwen3 q_norm, k_norm:
+ * transformers 5.5 modeling_gemma3.py:361-362, modeling_qwen3.py:263-264, patched by lxt/efficient/models/gemma3.py:11-12 / qwen3.py):
  * heads [0, n_q_heads) use wq, the next n_k_heads use wk.  backward = 0: normalise and save rstd [T, n_q+n_k];
  * backward = 1: identity rule g <- g * (w + w_offset) * rstd with the saved rstd. */
 int lrp_headnorm_inplace(void* qk, int64_t ld, int n_q_heads, int n_k_heads, int D, const void* wq, const void* wk,
@@ -123,6 +132,7 @@ int lrp_headnorm_inplace(void* qk, int64_t ld, int n_q_heads, int n_k_heads, int
  *   fwd: y = (x-mean)/sqrt(var+eps) * w + b ; saves mean,rstd.  bwd: g_x = (g_y*w*rstd) - mean_d(g_y*w*rstd) */
 int lrp_layernorm_fwd(const void* x, const void* w, const void* b, float eps, void* y, float* mean, float* rstd,
                       int T, int d, int is_f32, void* stream);
+/* backward with the std detached (formula above), lxt/efficient/patches.py:126-142 */
 int lrp_layernorm_bwd(const void* gy, const void* w, const float* rstd, void* gx, int T, int d, int is_f32,
                       void* stream);
 
@@ -140,12 +150,15 @@ int lrp_rope_inplace(void* qk, int64_t ld, int n_heads_total, int D, const float
  *        (fp32 arithmetic on the bf16 inputs, one rounding per output)
  *   cp_variant = 1 is CP-LRP (`cp_gated_mlp_forward`, patches.py:272-280): g_gate = 0, g_up = g_a * act(gate). */
 int lrp_gated_act_fwd(const void* gu, void* a, int T, int I, int act, void* stream);
+/* LRP backward of the gated product: identity rule on act(gate) (lxt/efficient/rules.py:88-100), uniform rule /2 on the product
+ * (rules.py:125-127 via patches.py:154); cp_variant = CP-LRP gate detached (patches.py:228-246) */
 int lrp_gated_act_bwd(const void* ga, const void* gu, void* ggu, int T, int I, int act, int cp_variant, void* stream);
 
 /* Identity rule on a plain element-wise non-linearity (lxt/efficient/rules.py:88-100,
  * lxt/efficient/patches.py:159-169 `mlp_forward`, :206-211 `non_linear_forward`):
  *   fwd: y = act(x);   bwd: g_x = g_y * act(x)/(x + 1e-10) */
 int lrp_act_identity_fwd(const void* x, void* y, int64_t n, int act, int is_f32, void* stream);
+/* gx = gy * act(x) / (x + 1e-10): lxt/efficient/rules.py:96-100 */
 int lrp_act_identity_bwd(const void* gy, const void* x, void* gx, int64_t n, int act, int is_f32, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
@@ -161,6 +174,8 @@ int lrp_act_identity_bwd(const void* gy, const void* x, void* gx, int64_t n, int
 int lrp_attn_fwd(const void* q, const void* k, const void* v, int64_t ldq, int64_t ldk, int64_t ldv, void* o,
                  float* lse, int B, int S, int H, int Hkv, int D, float scale, int causal, int window,
                  void* stream);
+/* LRP backward: plain flash-attention backward with dQ/q_div, dK/k_div, dV/v_div = (4,4,2) for AttnLRP
+ * (lxt/efficient/patches.py:193-203), (0,0,1) for CP-LRP (patches.py:249-258; a divisor 0 means "detached": zeros) */
 int lrp_attn_bwd(const void* q, const void* k, const void* v, int64_t ldq, int64_t ldk, int64_t ldv,
                  const void* o, const void* d_o, const float* lse, void* dq, void* dk, void* dv, int64_t lddq,
                  int64_t lddk, int64_t lddv, float* dq_acc_ws, float* delta_ws, int B, int S, int H, int Hkv, int D,
@@ -172,12 +187,17 @@ int lrp_attn_bwd(const void* q, const void* k, const void* v, int64_t ldq, int64
 /* h[t,:] = float(emb[ids[t],:]) * scale   (ids int64 on device; emb bf16 [V,d]; h fp32 [T,d]) */
 int lrp_embed_gather(const int64_t* ids, const void* emb, float scale, float* h, int T, int d, void* stream);
 /* argmax over logits[b,:] (fp32 [B,V]) -> idx[b] (int32), val[b] */
+/* arg-max logit per prompt: `output_logits[0, -1, :].max()` examples/quantized_llama.py:40 */
 int lrp_argmax_rows(const float* logits, int32_t* idx, float* val, int B, int V, void* stream);
 /* relevance[t] = sum_d x[t,d] * g[t,d]  (x,g fp32) — `(emb * emb.grad).float().sum(-1)` */
+/* rel[t] = sum_d x[t,d] * g[t,d]: `(input_embeds * input_embeds.grad).float().sum(-1)` examples/quantized_llama.py:47 */
 int lrp_gxi_reduce(const float* x, const float* g, float* rel, int T, int d, void* stream);
 /* bf16 variant of the same reduction (x, g bf16) */
+/* same for bf16 x / g (the dtype the reference's example runs in, examples/quantized_llama.py:13-19,47) */
 int lrp_gxi_reduce_bf16(const void* x, const void* g, float* rel, int T, int d, void* stream);
 /* out_bf16 = bf16(in_f32), n elements */
+/* fp32 -> bf16 rounding of an activation / gradient stream (the reference's `.to(input_dtype)` casts,
+ * lxt/efficient/patches.py:118-123) */
 int lrp_cast_f32_to_bf16(const float* in, void* out, int64_t n, void* stream);
 
 /* ------------------------------------------------------------------------------------------------

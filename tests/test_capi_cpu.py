@@ -48,3 +48,17 @@ def test_no_device_is_reported_not_faked():
     assert b"CUDA" in _capi.lib().lrp_last_error() or b"device" in _capi.lib().lrp_last_error()
     with pytest.raises(_capi.LrpError):
         _capi.require_device()
+
+
+def test_every_entry_point_cites_the_reference_code_it_replaces():
+    """include/lrp_b200.h: the comment in front of each declaration names a reference (or call-site) file:line"""
+    import re
+    hdr = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include", "lrp_b200.h")).read()
+    decls = list(re.finditer(r"^(?:int|int64_t|const char\*)\s+(lrp_[a-z0-9_]+)\s*\(", hdr, re.M))
+    assert len(decls) == 33
+    prev, missing = 0, []
+    for m in decls:
+        if not re.search(r"[A-Za-z0-9_/\.]+\.py:\d+", hdr[prev:m.start()]):
+            missing.append(m.group(1))
+        prev = m.end()
+    assert not missing, missing
