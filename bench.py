@@ -37,7 +37,10 @@ def parse():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--per-gpu-batch", type=int, default=32)
+    ap.add_argument("--scaling", default="strong", choices=["strong", "weak"],
+                    help="strong (default, BASELINE config 3): a fixed global batch split over the GPUs; weak: --per-gpu-batch prompts per GPU")
+    ap.add_argument("--global-batch", type=int, default=32, help="prompts per step over all GPUs (strong scaling)")
+    ap.add_argument("--per-gpu-batch", type=int, default=0, help="prompts per GPU per step (implies --scaling weak)")
     ap.add_argument("--micro-batch", type=int, default=8)
     ap.add_argument("--seq", type=int, default=2048)
     ap.add_argument("--model", default="llama3-8b", choices=["llama3-8b", "tinyllama-1.1b", "gemma3-4b", "llama-test"])
@@ -105,10 +108,130 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------ CPU reference arm
-def cpu_reference_sample(dims, seq, threads=None):
-    """Time the oracle port (oracle/attnlrp_oracle.py, the CPU restatement of lxt.efficient + HF Llama) on the host
-    cores on a bounded sample: ONE decoder layer at the full model width, batch 1, bf16, and extrapolate to L layers.
-    Returns (attributions_per_s, cores, sample_description, seconds_per_layer)."""
+def _import_reference():
+    """Import the UNMODIFIED reference (`lxt` 2.1): `baseline/_ref` (pip --target install, travels to the GPU box) or,
+    in the build container, /root/reference.  Returns the `lxt.efficient.monkey_patch` callable or None."""
+    for cand in (os.path.join(ROOT, "baseline", "_ref"), "/root/reference"):
+        if os.path.isdir(os.path.join(cand, "lxt")):
+            if cand not in sys.path:
+                sys.path.insert(0, cand)
+            try:
+                import warnings
+                with warnings.catch_warnings():
+                    warnings.simplefilter("ignore")
+                    from lxt.efficient import monkey_patch  # noqa: F401  (the reference, not lxt_b200)
+                import lxt
+                if "lxt_b200" in (lxt.__file__ or ""):
+                    return None
+                return monkey_patch
+            except Exception:
+                continue
+    return None
+
+
+class ReferenceCpuArm:
+    """The reference's own CPU implementation of the path: `lxt.efficient.monkey_patch(modeling_llama)` on a HuggingFace
+    `LlamaForCausalLM` of the benchmark's width (bf16, sdpa, real vocabulary, logits at ALL positions as HF computes them),
+    workload of examples/quantized_llama.py:35-47 (embed -> forward -> max logit at the last position -> backward ->
+    (emb * emb.grad).sum(-1)).  A full 32-layer attribution takes minutes on host cores, so a step is a bounded COMPLETE
+    attribution of the same model truncated to 2 and to 1 decoder layers (same weights): t_layer = t(2) - t(1),
+    t_fixed = t(1) - t_layer (embedding, final norm, lm_head over all positions, their backward), and the full-depth
+    rate is 1 / (t_fixed + L * t_layer).  What was timed and the extrapolation are reported separately."""
+
+    SAMPLE_LAYERS = 2
+
+    def __init__(self, dims, seq, monkey_patch, threads=None):
+        import warnings
+        from transformers import LlamaConfig, LlamaForCausalLM
+        from transformers.models.llama import modeling_llama
+        self.dims, self.seq = dims, seq
+        self.cores = threads or best_thread_count()
+        torch.set_num_threads(self.cores)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            monkey_patch(modeling_llama, verbose=False)
+        cfg = LlamaConfig(hidden_size=dims.d, intermediate_size=dims.I, num_attention_heads=dims.H, num_key_value_heads=dims.Hkv,
+                          head_dim=dims.D, num_hidden_layers=self.SAMPLE_LAYERS, vocab_size=dims.V, rms_norm_eps=dims.eps,
+                          rope_theta=dims.theta, max_position_embeddings=max(seq, 2048), tie_word_embeddings=False,
+                          attn_implementation="sdpa")
+        t0 = time.perf_counter()
+        torch.set_default_dtype(torch.bfloat16)
+        try:
+            try:   # skip HF's single-threaded normal_ init of 2.3 G parameters (a minute): weights are filled below
+                from transformers.initialization import no_init_weights
+                with no_init_weights():
+                    model = LlamaForCausalLM(cfg)
+                skipped = True
+            except Exception:
+                torch.manual_seed(0)
+                model = LlamaForCausalLM(cfg)
+                skipped = False
+        finally:
+            torch.set_default_dtype(torch.float32)
+        if skipped:   # N(0, 0.02) values tiled from one seeded 8 Mi block (synthetic weights; timing does not depend on them)
+            g = torch.Generator().manual_seed(0)
+            block = (torch.randn(1 << 23, generator=g) * 0.02).to(torch.bfloat16)
+            with torch.no_grad():
+                for k, (name, prm) in enumerate(model.named_parameters()):
+                    if prm.dim() >= 2:
+                        flat = prm.data.view(-1)
+                        rolled = torch.roll(block, shifts=7919 * (k + 1))
+                        for off in range(0, flat.numel(), block.numel()):
+                            n = min(block.numel(), flat.numel() - off)
+                            flat[off:off + n] = rolled[:n]
+                    else:
+                        prm.data.fill_(1.0)
+        model.eval()
+        for prm in model.parameters():
+            prm.requires_grad_(False)
+        self.model = model
+        self.build_s = time.perf_counter() - t0
+        self.ids = torch.randint(0, dims.V, (1, seq), generator=torch.Generator().manual_seed(1))
+
+    def attribution(self, n_layers):
+        import warnings
+        m = self.model
+        layers = m.model.layers
+        m.model.layers = layers[:n_layers]
+        try:
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                emb = m.get_input_embeddings()(self.ids).requires_grad_(True)
+                logits = m(inputs_embeds=emb, use_cache=False).logits
+                mx, _ = torch.max(logits[0, -1, :], dim=-1)
+                mx.backward()
+                return (emb * emb.grad).float().sum(-1)
+        finally:
+            m.model.layers = layers
+
+    def step(self):
+        """one timed step: a complete 2-layer attribution and a complete 1-layer attribution; returns (t2, t1) seconds"""
+        t0 = time.perf_counter()
+        self.attribution(2)
+        t1 = time.perf_counter()
+        self.attribution(1)
+        t2 = time.perf_counter()
+        return t1 - t0, t2 - t1
+
+    def summarize(self, samples):
+        t2 = sum(s[0] for s in samples) / len(samples)
+        t1 = sum(s[1] for s in samples) / len(samples)
+        t_layer = max(t2 - t1, 1e-6)
+        t_fixed = max(t1 - t_layer, 0.0)
+        L = self.dims.L
+        per_attr = t_fixed + L * t_layer
+        desc = (f"UNMODIFIED reference lxt.efficient.monkey_patch(modeling_llama) on HF LlamaForCausalLM (torch CPU bf16, sdpa, "
+                f"{self.cores} threads, d={self.dims.d}, I={self.dims.I}, H={self.dims.H}/{self.dims.Hkv}, V={self.dims.V}, all-position "
+                f"logits), S={self.seq}, B=1: complete attributions at 2 layers ({t2:.2f} s) and 1 layer ({t1:.2f} s) per step")
+        extra = {"formula": "attributions/s = 1 / (t_fixed + L * t_layer), t_layer = t(2 layers) - t(1 layer), t_fixed = t(1 layer) - t_layer",
+                 "L": L, "t_layer_s": t_layer, "t_fixed_s": t_fixed, "t_2layer_s": t2, "t_1layer_s": t1,
+                 "seconds_per_full_attribution_est": per_attr}
+        return 1.0 / per_attr, desc, extra, (t2 + t1)
+
+
+def cpu_port_sample(dims, seq, threads=None):
+    """Fallback when the reference cannot be imported: time the oracle port (oracle/attnlrp_oracle.py) on ONE decoder layer at
+    the full model width, batch 1, bf16, and extrapolate to L layers.  Returns (attributions_per_s, cores, description, s)."""
     from oracle import attnlrp_oracle as O
     cores = threads or best_thread_count()
     torch.set_num_threads(cores)
@@ -120,8 +243,8 @@ def cpu_reference_sample(dims, seq, threads=None):
     O.llama_attnlrp(w, ids, cfg, dtype=torch.bfloat16)
     dt = time.perf_counter() - t0
     per_attr = dt * dims.L
-    desc = (f"oracle port (torch CPU bf16, {cores} threads): 1 of {dims.L} decoder layers at full width "
-            f"(d={dims.d}, I={dims.I}, H={dims.H}/{dims.Hkv}), S={seq}, B=1, fwd + LRP bwd = {dt:.2f} s; x{dims.L} layers")
+    desc = (f"oracle PORT (reference not importable; torch CPU bf16, {cores} threads): 1 of {dims.L} decoder layers at full width "
+            f"(d={dims.d}, I={dims.I}, H={dims.H}/{dims.Hkv}), V=2048, S={seq}, B=1, fwd + LRP bwd = {dt:.2f} s; x{dims.L} layers")
     return 1.0 / per_attr, cores, desc, dt
 
 
@@ -145,26 +268,59 @@ def best_thread_count():
     return best
 
 
+def cpu_baseline_block(dims, seq, warmup=1, steps=1, budget_s=150.0):
+    """CPU leg shared by `--impl reference` and by our arm's `cpu_baseline` (rank 0, N=1): the imported reference when
+    available (kind "reference"), else the oracle port (kind "port").  Returns (value, block, ms_per_step, steps_run, extra)."""
+    mp = _import_reference()
+    llama_like = getattr(dims, "act", "silu") == "silu" and not getattr(dims, "post_norms", False) and not getattr(dims, "qk_norm", False)
+    if mp is not None and llama_like:
+        arm = ReferenceCpuArm(dims, seq, mp)
+        t_start = time.perf_counter()
+        samples, n_w = [], 0
+        for i in range(warmup + steps):
+            t = arm.step()
+            if i >= warmup:
+                samples.append(t)
+            else:
+                n_w += 1
+            elapsed = time.perf_counter() - t_start
+            per = elapsed / (i + 1)
+            if elapsed + per > budget_s and samples:   # keep the whole arm within a few minutes; report the steps actually run
+                break
+        v, desc, extra, step_s = arm.summarize(samples)
+        extra.update(model_build_s=arm.build_s, warmup_steps_run=n_w)
+        blk = {"value": v, "unit": UNIT, "cores": arm.cores, "kind": "reference", "sample": desc}
+        return v, blk, step_s * 1e3, len(samples), extra
+    vals, dts = [], []
+    for i in range(steps):
+        v, cores, desc, dt = cpu_port_sample(dims, seq)
+        vals.append(v)
+        dts.append(dt)
+        if sum(dts) * 2 > budget_s:
+            break
+    v = sum(vals) / len(vals)
+    blk = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc}
+    extra = {"formula": "attributions/s = 1 / (L * t_one_layer)", "L": dims.L, "t_layer_s": sum(dts) / len(dts)}
+    return v, blk, 2e3 * sum(dts) / len(dts), len(vals), extra
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     dims = model_dims(args.model, args.layers)
-    vals = []
-    for i in range(args.warmup + args.steps):
-        v, cores, desc, dt = cpu_reference_sample(dims, args.seq)
-        if i >= args.warmup:
-            vals.append(v)
-        if dt * (args.warmup + args.steps) > 240:  # keep the whole arm within a few minutes
-            vals = vals or [v]
-            break
-    v = sum(vals) / len(vals)
+    v, blk, ms_step, steps_run, extra = cpu_baseline_block(dims, args.seq, warmup=args.warmup, steps=args.steps, budget_s=200.0)
     print(json.dumps({
-        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1000.0 / v, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": f"{args.model} random-init bf16, seq {args.seq}, CPU sample", "seq_len": args.seq},
-        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc},
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": steps_run,
+        "steps_requested": args.steps, "warmup": extra.get("warmup_steps_run", args.warmup),
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": f"{args.model} random-init bf16, seq {args.seq}, host CPU; a step is a bounded sample "
+                               f"(see cpu_baseline.sample), value is the full-depth rate it implies (see extrapolation)",
+                   "seq_len": args.seq, "layers": dims.L},
+        "timed": {"ms_per_step": ms_step, "what": blk["sample"]},
+        "extrapolation": extra,
+        "cpu_baseline": blk,
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
@@ -174,17 +330,27 @@ def run_b200(args):
     from lxt_b200 import dist as ldist, ops
     from lxt_b200.engine import LlamaAttnLRPEngine
 
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        # keep the communicator set-up lines (nranks, NVLS / P2P transport) in stderr as evidence of the one collective
+        os.environ.setdefault("NCCL_DEBUG", "INFO")
+        os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
     rank, world, local = ldist.init_from_env("nccl")
     if world != args.gpus and world > 1:
         args.gpus = world
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     dims = model_dims(args.model, args.layers)
-    S, Bg = args.seq, args.per_gpu_batch
-    eng = LlamaAttnLRPEngine.random_init(dims, device=dev, seed=0, micro_batch=args.micro_batch)
-    N_total = Bg * world
-    ids_all = torch.randint(0, dims.V, (N_total, S), generator=torch.Generator().manual_seed(1))
+    S = args.seq
+    if args.per_gpu_batch > 0:
+        args.scaling = "weak"
+    N_total = args.per_gpu_batch * world if args.scaling == "weak" else args.global_batch
+    if N_total < world:
+        raise SystemExit(f"global batch {N_total} smaller than the number of GPUs {world}")
     lo, hi = ldist.shard_range(N_total, rank, world)
+    Bg = hi - lo
+    micro = max(1, min(args.micro_batch, Bg))
+    eng = LlamaAttnLRPEngine.random_init(dims, device=dev, seed=0, micro_batch=micro)
+    ids_all = torch.randint(0, dims.V, (N_total, S), generator=torch.Generator().manual_seed(1))
     ids_host = ids_all[lo:hi].contiguous().pin_memory()
     ids_dev = ids_host.to(dev)
     rel_host = torch.empty((hi - lo, S), dtype=torch.float32, pin_memory=True)
@@ -259,10 +425,10 @@ def run_b200(args):
     metric = METRIC if (args.model == "llama3-8b" and S == 2048 and not args.layers) else f"attributions/sec (seq{S}) {args.model} [non-headline workload]"
     out = {
         "metric": metric, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-        "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
         "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": f"{args.model} random-init bf16, seq {S}, {Bg} prompts per GPU per step "
-                               f"(micro-batch {args.micro_batch}), batch-sharded over {world} GPU(s), 1 NCCL gather",
+        "config": {"workload": f"{args.model} random-init bf16, seq {S}, global batch {N_total} per step = {Bg} prompts per GPU "
+                               f"(micro-batch {micro}), batch-sharded over {world} GPU(s), 1 NCCL gather",
                    "global_batch": N_total, "seq_len": S, "layers": dims.L, "parallelism": f"dp{world}",
                    "l2": "inputs larger than L2 (16 GB weights + activation store streamed every step)"},
         "e2e": {"value": e2e_v, "unit": UNIT, "h2d_bytes_per_step": int(ids_host.numel() * 8),
@@ -285,8 +451,9 @@ def run_b200(args):
             out["kernels"] = {"error": str(ex)}
     if not args.no_cpu_baseline and world == 1:   # reported on rank 0 at N=1 only
         try:
-            v, cores, desc, _ = cpu_reference_sample(dims, S)
-            out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc}
+            v, blk, ms_step, steps_run, extra = cpu_baseline_block(dims, S, warmup=1, steps=1, budget_s=60.0)
+            blk["extrapolation"] = extra
+            out["cpu_baseline"] = blk
         except Exception as ex:  # pragma: no cover
             out["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {ex}"}
     print(json.dumps(out))

@@ -220,6 +220,48 @@ int lrp_softmax_dt_bwd(const void* x, const void* p, const void* r, void* out, i
 int lrp_add2_bwd(const void* a, const void* b, const void* r, void* ra, void* rb, int64_t n, float eps, int is_f32,
                  void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Validation-precision mode (fp32 activations): the same rule kernels with the activation dtype selectable, the two-term
+ * bf16 split that feeds fp32 activations to the bf16 tcgen05 GEMM (out = hi W + lo W, fp32 accumulation), and an fp32
+ * CUDA-core flash AttnLRP.  Purpose: show that the bf16 path's distance to the reference's fp32 run is storage rounding
+ * (the reference itself runs in whatever dtype the HF model has; fp32: tests of lxt/explicit, bf16: examples/quantized_llama.py:13-19).
+ * `*_is_f32` = 1 selects fp32, 0 bf16, for the named tensor; weights stay bf16.
+ * ---------------------------------------------------------------------------------------------- */
+/* lrp_rmsnorm_fwd with a selectable output dtype (lxt/efficient/patches.py:111-123) */
+int lrp_rmsnorm_fwd_t(const void* x, int x_is_f32, const void* w, float w_offset, float eps, void* y, int y_is_f32, float* rstd,
+                      int T, int d, void* stream);
+/* lrp_rmsnorm_bwd with a selectable input dtype (identity rule, lxt/efficient/patches.py:111-123) */
+int lrp_rmsnorm_bwd_t(const void* gy, int gy_is_f32, const void* w, float w_offset, const float* rstd, void* gx, int gx_is_f32,
+                      int accumulate, int T, int d, void* stream);
+/* lrp_rmsnorm_fwd_residual with a selectable branch dtype (lxt/efficient/models/gemma3.py:11-19) */
+int lrp_rmsnorm_fwd_residual_t(const void* y, int y_is_f32, const void* w, float w_offset, float eps, float* h, float* rstd, int T,
+                               int d, void* stream);
+/* lrp_headnorm_inplace on a bf16 or fp32 packed buffer (lxt/efficient/models/gemma3.py:11-12) */
+int lrp_headnorm_inplace_t(void* qk, int is_f32, int64_t ld, int n_q_heads, int n_k_heads, int D, const void* wq, const void* wk,
+                           float w_offset, float eps, float* rstd, int T, int backward, void* stream);
+/* lrp_rope_inplace on a bf16 or fp32 packed buffer (RoPE is left unpatched by the reference: transformers modeling_llama.py:146-168,
+ * SURVEY 0 table; explicit form lxt/explicit/models/llama.py:226-260) */
+int lrp_rope_inplace_t(void* qk, int is_f32, int64_t ld, int n_heads_total, int D, const float* cos_t, const float* sin_t, int T,
+                       int S, int inverse, void* stream);
+/* lrp_gated_act_fwd on bf16 or fp32 tensors (lxt/efficient/patches.py:145-157) */
+int lrp_gated_act_fwd_t(const void* gu, void* a, int is_f32, int T, int I, int act, void* stream);
+/* lrp_gated_act_bwd on bf16 or fp32 tensors (lxt/efficient/rules.py:88-127) */
+int lrp_gated_act_bwd_t(const void* ga, const void* gu, void* ggu, int is_f32, int T, int I, int act, int cp_variant, void* stream);
+/* x (fp32, n elements) -> hi = bf16(x), lo = bf16(x - hi): operands of the split GEMM that replaces the fp32 `F.linear` of an fp32
+ * model (transformers modeling_llama.py:183,262-264,288 executed in fp32, as in the reference's own tests/test_functional.py:57-76) */
+int lrp_split_bf16x2(const float* x, void* hi, void* lo, int64_t n, void* stream);
+/* fp32 flash AttnLRP forward (same contract as lrp_attn_fwd, all tensors fp32; lxt/efficient/patches.py:193-203) */
+int lrp_attn_fwd_f32(const float* q, const float* k, const float* v, int64_t ldq, int64_t ldk, int64_t ldv, float* o, float* lse,
+                     int B, int S, int H, int Hkv, int D, float scale, int causal, int window, void* stream);
+/* fp32 flash AttnLRP backward (same contract as lrp_attn_bwd; delta_ws fp32 [B,H,S]; lxt/efficient/patches.py:193-203) */
+int lrp_attn_bwd_f32(const float* q, const float* k, const float* v, int64_t ldq, int64_t ldk, int64_t ldv, const float* o,
+                     const float* d_o, const float* lse, float* dq, float* dk, float* dv, int64_t lddq, int64_t lddk,
+                     int64_t lddv, float* delta_ws, int B, int S, int H, int Hkv, int D, float scale, int causal, int window,
+                     float q_div, float k_div, float v_div, void* stream);
+/* workspace query of lrp_attn_bwd (SURVEY.md 8(b) "a *_workspace_bytes query per op"): bytes of `dq_acc_ws` and `delta_ws` for this
+ * shape; replaces the tensors autograd saves / allocates in the reference's SDPA backward (lxt/efficient/patches.py:193-203) */
+int lrp_attn_bwd_workspace_bytes(int B, int S, int H, int D, int64_t* dq_acc_bytes, int64_t* delta_bytes);
+
 #ifdef __cplusplus
 }
 #endif

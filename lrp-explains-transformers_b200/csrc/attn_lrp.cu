@@ -842,10 +842,23 @@ using namespace lrp;
 
 extern "C" {
 
+int lrp_attn_bwd_workspace_bytes(int B, int S, int H, int D, int64_t* dq_acc_bytes, int64_t* delta_bytes) {
+  if (B <= 0 || S <= 0 || H <= 0 || D <= 0) return set_error(LRP_ERR_ARG, "attn_bwd_workspace_bytes: bad shape");
+  if (dq_acc_bytes != nullptr) *dq_acc_bytes = int64_t(B) * S * H * D * 4;   // fp32 [B,S,H,D] dQ accumulator
+  if (delta_bytes != nullptr) *delta_bytes = int64_t(B) * H * S * 4;         // fp32 [B,H,S] row sums of o * dO
+  return LRP_OK;
+}
+
 int lrp_attn_fwd(const void* q, const void* k, const void* v, int64_t ldq, int64_t ldk, int64_t ldv, void* o, float* lse,
                  int B, int S, int H, int Hkv, int D, float scale, int causal, int window, void* stream) {
   if (int e = check_common(q, k, v, ldq, ldk, ldv, B, S, H, Hkv, D)) return e;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  {
+    // head_dim 128 without a sliding window: the persistent two-tile kernel of attn_fwd_ws.cu (LRP_ATTN_FWD=v1 keeps the
+    // first-generation kernel below for A/B measurements)
+    static const bool v1 = getenv("LRP_ATTN_FWD") != nullptr && !strcmp(getenv("LRP_ATTN_FWD"), "v1");
+    if (D == 128 && window <= 0 && !v1) return attn_fwd_ws(q, k, v, ldq, ldk, ldv, o, lse, B, S, H, Hkv, scale, causal, st);
+  }
   // key tile: 64 keys for D=128, 128 keys for D=64 -> 112 KiB of smem per CTA either way (2 CTAs per SM)
   const int BN = D == 64 ? 128 : 64;   // head_dim 256: 208 KiB, one CTA per SM, 320 TMEM columns
   CUtensorMap tq, tk, tv;

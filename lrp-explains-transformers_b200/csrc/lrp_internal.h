@@ -30,6 +30,9 @@ int attn_bwd_v2(const void* q, const void* k, const void* v, int64_t ldq, int64_
                 int B, int S, int H, int Hkv, int D, float scale, int causal, int window, float q_div, float k_div, float v_div,
                 cudaStream_t st);
 
+int attn_fwd_ws(const void* q, const void* k, const void* v, int64_t ldq, int64_t ldk, int64_t ldv, void* o, float* lse, int B,
+                int S, int H, int Hkv, float scale, int causal, cudaStream_t st);
+
 int linear_eps_bwd(const void* x, const void* W, const float* bias, const void* r_out, int r_is_f32, void* r_in,
                    void* s_ws, int32_t* flags_ws, int T, int N, int K, float eps, cudaStream_t stream);
 

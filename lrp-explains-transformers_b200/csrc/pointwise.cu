@@ -54,11 +54,11 @@ constexpr int NORM_THREADS = 256;
 // y = bf16( (x * rstd) * (w_offset + w) ), all arithmetic in fp32 with one final rounding.
 //   Llama: w_offset = 0 (patches.py:111-123; the reference's intermediate bf16 downcast before `weight *` is a
 //   storage artefact of its bf16 tensors, not part of the rule);  Gemma: w_offset = 1 (gemma3.py:11-12).
-template <typename TIn>
+template <typename TIn, typename TOut>
 __global__ void __launch_bounds__(NORM_THREADS) rmsnorm_fwd_kernel(const TIn* __restrict__ x,
                                                                    const __nv_bfloat16* __restrict__ w,
                                                                    float w_offset, float eps,
-                                                                   __nv_bfloat16* __restrict__ y,
+                                                                   TOut* __restrict__ y,
                                                                    float* __restrict__ rstd_out, int d) {
   __shared__ float red[NORM_THREADS / 32];
   const int64_t row = blockIdx.x;
@@ -73,7 +73,7 @@ __global__ void __launch_bounds__(NORM_THREADS) rmsnorm_fwd_kernel(const TIn* __
   ss = block_sum<NORM_THREADS>(ss, red);
   const float rstd = rsqrtf(ss / float(d) + eps);
   if (threadIdx.x == 0 && rstd_out != nullptr) rstd_out[row] = rstd;
-  __nv_bfloat16* yr = y + row * d;
+  TOut* yr = y + row * d;
   for (int i = threadIdx.x * 8; i < d; i += NORM_THREADS * 8) {
     float f[8], wf[8], o[8];
     load8(xr + i, f);
@@ -87,8 +87,8 @@ __global__ void __launch_bounds__(NORM_THREADS) rmsnorm_fwd_kernel(const TIn* __
 }
 
 // GxI backward: g_x = g_y * (w + w_offset) * rstd  (variance path detached = identity rule)
-template <typename TOut>
-__global__ void __launch_bounds__(NORM_THREADS) rmsnorm_bwd_kernel(const __nv_bfloat16* __restrict__ gy,
+template <typename TIn, typename TOut>
+__global__ void __launch_bounds__(NORM_THREADS) rmsnorm_bwd_kernel(const TIn* __restrict__ gy,
                                                                    const __nv_bfloat16* __restrict__ w,
                                                                    float w_offset,
                                                                    const float* __restrict__ rstd,
@@ -111,13 +111,14 @@ __global__ void __launch_bounds__(NORM_THREADS) rmsnorm_bwd_kernel(const __nv_bf
 
 // h[t,:] += (y[t,:] * rsqrt(mean(y^2)+eps)) * (w_offset + w)   — Gemma's post-branch RMSNorm fused with the residual add
 // (HF Gemma3DecoderLayer: hidden = residual + post_norm(branch)); rstd of the branch output saved for the backward.
-__global__ void __launch_bounds__(NORM_THREADS) rmsnorm_fwd_residual_kernel(const __nv_bfloat16* __restrict__ y,
+template <typename TY>
+__global__ void __launch_bounds__(NORM_THREADS) rmsnorm_fwd_residual_kernel(const TY* __restrict__ y,
                                                                             const __nv_bfloat16* __restrict__ w,
                                                                             float w_offset, float eps, float* __restrict__ h,
                                                                             float* __restrict__ rstd_out, int d) {
   __shared__ float red[NORM_THREADS / 32];
   const int64_t row = blockIdx.x;
-  const __nv_bfloat16* yr = y + row * d;
+  const TY* yr = y + row * d;
   float ss = 0.f;
   for (int i = threadIdx.x * 8; i < d; i += NORM_THREADS * 8) {
     float f[8];
@@ -142,7 +143,8 @@ __global__ void __launch_bounds__(NORM_THREADS) rmsnorm_fwd_residual_kernel(cons
 // Per-head RMSNorm over D on the q and k slices of a packed qkv buffer, in place (Gemma-3 / Qwen3 q_norm, k_norm), one
 // warp per (token, head).  backward = 0: x <- x * rstd * (off + w), rstd saved [T, n_heads];
 // backward = 1 (identity rule): g <- g * (off + w) * rstd with the saved rstd.
-__global__ void __launch_bounds__(256) headnorm_kernel(__nv_bfloat16* __restrict__ qk, int64_t ld, int n_q, int n_heads, int D,
+template <typename TQ>
+__global__ void __launch_bounds__(256) headnorm_kernel(TQ* __restrict__ qk, int64_t ld, int n_q, int n_heads, int D,
                                                        const __nv_bfloat16* __restrict__ wq, const __nv_bfloat16* __restrict__ wk,
                                                        float w_offset, float eps, float* __restrict__ rstd, int64_t T, int backward) {
   const int64_t row = blockIdx.x * int64_t(blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -150,7 +152,7 @@ __global__ void __launch_bounds__(256) headnorm_kernel(__nv_bfloat16* __restrict
   const int lane = threadIdx.x & 31;
   const int64_t t = row / n_heads;
   const int hd = int(row - t * n_heads);
-  __nv_bfloat16* p = qk + t * ld + int64_t(hd) * D;
+  TQ* p = qk + t * ld + int64_t(hd) * D;
   const __nv_bfloat16* w = hd < n_q ? wq : wk;
   float r;
   if (!backward) {
@@ -259,7 +261,8 @@ __global__ void __launch_bounds__(NORM_THREADS) layernorm_bwd_kernel(const T* __
 // RoPE in place on packed heads (rotate_half convention)
 // ------------------------------------------------------------------------------------------------
 // one thread handles 8 consecutive "pair" indices i..i+7 of one head: x1 = x[i], x2 = x[i + D/2]
-__global__ void __launch_bounds__(256) rope_kernel(__nv_bfloat16* __restrict__ qk, int64_t ld, int n_heads, int D,
+template <typename TQ>
+__global__ void __launch_bounds__(256) rope_kernel(TQ* __restrict__ qk, int64_t ld, int n_heads, int D,
                                                    const float* __restrict__ cos_t, const float* __restrict__ sin_t,
                                                    int64_t T, int S, int inverse) {
   const int half = D >> 1;
@@ -272,7 +275,7 @@ __global__ void __launch_bounds__(256) rope_kernel(__nv_bfloat16* __restrict__ q
     const int h = int(r % n_heads);
     const int64_t t = r / n_heads;
     const int pos = int(t % S);
-    __nv_bfloat16* p = qk + t * ld + int64_t(h) * D + c * 8;
+    TQ* p = qk + t * ld + int64_t(h) * D + c * 8;
     float x1[8], x2[8], cs[8], sn[8], y1[8], y2[8];
     load8(p, x1);
     load8(p + half, x2);
@@ -302,8 +305,9 @@ __device__ __forceinline__ float act_eval(float x, int act) {
 }
 
 // a = bf16( act(gate) * up )
-__global__ void __launch_bounds__(256) gated_act_fwd_kernel(const __nv_bfloat16* __restrict__ gu,
-                                                            __nv_bfloat16* __restrict__ a, int64_t T, int I, int act) {
+template <typename TA>
+__global__ void __launch_bounds__(256) gated_act_fwd_kernel(const TA* __restrict__ gu,
+                                                            TA* __restrict__ a, int64_t T, int I, int act) {
   const int chunks = I >> 3;
   const int64_t total = T * chunks;
   for (int64_t idx = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; idx < total;
@@ -323,9 +327,10 @@ __global__ void __launch_bounds__(256) gated_act_fwd_kernel(const __nv_bfloat16*
 // g_up   = g_half * s                        s = act(gate)
 // g_gate = (s / (gate + 1e-10)) * (g_half * up)                      (identity rule, rules.py:88-100)
 // fp32 arithmetic on the bf16 inputs, one rounding on each output.
-__global__ void __launch_bounds__(256) gated_act_bwd_kernel(const __nv_bfloat16* __restrict__ ga,
-                                                            const __nv_bfloat16* __restrict__ gu,
-                                                            __nv_bfloat16* __restrict__ ggu, int64_t T, int I, int act,
+template <typename TA>
+__global__ void __launch_bounds__(256) gated_act_bwd_kernel(const TA* __restrict__ ga,
+                                                            const TA* __restrict__ gu,
+                                                            TA* __restrict__ ggu, int64_t T, int I, int act,
                                                             int cp_variant) {
   const int chunks = I >> 3;
   const int64_t total = T * chunks;
@@ -461,6 +466,23 @@ __global__ void __launch_bounds__(256) cast_f32_bf16_kernel(const float* __restr
   }
 }
 
+// x (fp32) = hi + lo with hi = bf16(x), lo = bf16(x - hi): the two-term bf16 split that lets the bf16 tcgen05 GEMM
+// contract an fp32 activation with ~16 mantissa bits (validation-precision mode: out = hi W + lo W, fp32 accumulation)
+__global__ void __launch_bounds__(256) split_bf16x2_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ hi,
+                                                           __nv_bfloat16* __restrict__ lo, int64_t n8) {
+  for (int64_t idx = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; idx < n8; idx += int64_t(gridDim.x) * blockDim.x) {
+    float f[8], h[8], l[8];
+    load8(in + idx * 8, f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      h[j] = round_bf16(f[j]);
+      l[j] = f[j] - h[j];
+    }
+    store8(hi + idx * 8, h);
+    store8(lo + idx * 8, l);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // generic element-wise rule kernels (explicit / efficient rule API on arbitrary tensors); scalar tail handled
 // ------------------------------------------------------------------------------------------------
@@ -538,48 +560,84 @@ typedef __nv_bfloat16 bf16;
 
 extern "C" {
 
-int lrp_rmsnorm_fwd(const void* x, int x_is_f32, const void* w, float w_offset, float eps, void* y, float* rstd,
-                    int T, int d, void* stream) {
+int lrp_rmsnorm_fwd_t(const void* x, int x_is_f32, const void* w, float w_offset, float eps, void* y, int y_is_f32, float* rstd,
+                      int T, int d, void* stream) {
   if (T <= 0 || d <= 0 || (d % 8) != 0) return set_error(LRP_ERR_ARG, "rmsnorm_fwd: d must be a positive multiple of 8");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (x_is_f32)
-    rmsnorm_fwd_kernel<float><<<T, NORM_THREADS, 0, st>>>((const float*)x, (const bf16*)w, w_offset, eps, (bf16*)y, rstd, d);
+  if (x_is_f32 && y_is_f32)
+    rmsnorm_fwd_kernel<float, float><<<T, NORM_THREADS, 0, st>>>((const float*)x, (const bf16*)w, w_offset, eps, (float*)y, rstd, d);
+  else if (x_is_f32)
+    rmsnorm_fwd_kernel<float, bf16><<<T, NORM_THREADS, 0, st>>>((const float*)x, (const bf16*)w, w_offset, eps, (bf16*)y, rstd, d);
+  else if (y_is_f32)
+    rmsnorm_fwd_kernel<bf16, float><<<T, NORM_THREADS, 0, st>>>((const bf16*)x, (const bf16*)w, w_offset, eps, (float*)y, rstd, d);
   else
-    rmsnorm_fwd_kernel<bf16><<<T, NORM_THREADS, 0, st>>>((const bf16*)x, (const bf16*)w, w_offset, eps, (bf16*)y, rstd, d);
+    rmsnorm_fwd_kernel<bf16, bf16><<<T, NORM_THREADS, 0, st>>>((const bf16*)x, (const bf16*)w, w_offset, eps, (bf16*)y, rstd, d);
+  LRP_CHECK_LAUNCH();
+  return LRP_OK;
+}
+
+int lrp_rmsnorm_fwd(const void* x, int x_is_f32, const void* w, float w_offset, float eps, void* y, float* rstd,
+                    int T, int d, void* stream) {
+  return lrp_rmsnorm_fwd_t(x, x_is_f32, w, w_offset, eps, y, 0, rstd, T, d, stream);
+}
+
+int lrp_rmsnorm_bwd_t(const void* gy, int gy_is_f32, const void* w, float w_offset, const float* rstd, void* gx, int gx_is_f32,
+                      int accumulate, int T, int d, void* stream) {
+  if (T <= 0 || d <= 0 || (d % 8) != 0) return set_error(LRP_ERR_ARG, "rmsnorm_bwd: d must be a positive multiple of 8");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (gy_is_f32 && gx_is_f32)
+    rmsnorm_bwd_kernel<float, float><<<T, NORM_THREADS, 0, st>>>((const float*)gy, (const bf16*)w, w_offset, rstd, (float*)gx, accumulate, d);
+  else if (gy_is_f32)
+    rmsnorm_bwd_kernel<float, bf16><<<T, NORM_THREADS, 0, st>>>((const float*)gy, (const bf16*)w, w_offset, rstd, (bf16*)gx, accumulate, d);
+  else if (gx_is_f32)
+    rmsnorm_bwd_kernel<bf16, float><<<T, NORM_THREADS, 0, st>>>((const bf16*)gy, (const bf16*)w, w_offset, rstd, (float*)gx, accumulate, d);
+  else
+    rmsnorm_bwd_kernel<bf16, bf16><<<T, NORM_THREADS, 0, st>>>((const bf16*)gy, (const bf16*)w, w_offset, rstd, (bf16*)gx, accumulate, d);
   LRP_CHECK_LAUNCH();
   return LRP_OK;
 }
 
 int lrp_rmsnorm_bwd(const void* gy, const void* w, float w_offset, const float* rstd, void* gx, int gx_is_f32,
                     int accumulate, int T, int d, void* stream) {
-  if (T <= 0 || d <= 0 || (d % 8) != 0) return set_error(LRP_ERR_ARG, "rmsnorm_bwd: d must be a positive multiple of 8");
+  return lrp_rmsnorm_bwd_t(gy, 0, w, w_offset, rstd, gx, gx_is_f32, accumulate, T, d, stream);
+}
+
+int lrp_rmsnorm_fwd_residual_t(const void* y, int y_is_f32, const void* w, float w_offset, float eps, float* h, float* rstd, int T,
+                               int d, void* stream) {
+  if (T <= 0 || d <= 0 || (d % 8) != 0) return set_error(LRP_ERR_ARG, "rmsnorm_fwd_residual: d must be a positive multiple of 8");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (gx_is_f32)
-    rmsnorm_bwd_kernel<float><<<T, NORM_THREADS, 0, st>>>((const bf16*)gy, (const bf16*)w, w_offset, rstd, (float*)gx, accumulate, d);
+  if (y_is_f32)
+    rmsnorm_fwd_residual_kernel<float><<<T, NORM_THREADS, 0, st>>>((const float*)y, (const bf16*)w, w_offset, eps, h, rstd, d);
   else
-    rmsnorm_bwd_kernel<bf16><<<T, NORM_THREADS, 0, st>>>((const bf16*)gy, (const bf16*)w, w_offset, rstd, (bf16*)gx, accumulate, d);
+    rmsnorm_fwd_residual_kernel<bf16><<<T, NORM_THREADS, 0, st>>>((const bf16*)y, (const bf16*)w, w_offset, eps, h, rstd, d);
   LRP_CHECK_LAUNCH();
   return LRP_OK;
 }
 
 int lrp_rmsnorm_fwd_residual(const void* y, const void* w, float w_offset, float eps, float* h, float* rstd, int T, int d,
                              void* stream) {
-  if (T <= 0 || d <= 0 || (d % 8) != 0) return set_error(LRP_ERR_ARG, "rmsnorm_fwd_residual: d must be a positive multiple of 8");
-  rmsnorm_fwd_residual_kernel<<<T, NORM_THREADS, 0, static_cast<cudaStream_t>(stream)>>>((const bf16*)y, (const bf16*)w, w_offset,
-                                                                                        eps, h, rstd, d);
+  return lrp_rmsnorm_fwd_residual_t(y, 0, w, w_offset, eps, h, rstd, T, d, stream);
+}
+
+int lrp_headnorm_inplace_t(void* qk, int is_f32, int64_t ld, int n_q_heads, int n_k_heads, int D, const void* wq, const void* wk,
+                           float w_offset, float eps, float* rstd, int T, int backward, void* stream) {
+  if (T <= 0 || n_q_heads < 0 || n_k_heads < 0 || n_q_heads + n_k_heads <= 0 || D <= 0 || (D % 8) != 0 || (ld % 8) != 0)
+    return set_error(LRP_ERR_ARG, "headnorm: D and ld must be multiples of 8");
+  const int64_t rows = int64_t(T) * (n_q_heads + n_k_heads);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (is_f32)
+    headnorm_kernel<float><<<unsigned((rows + 7) / 8), 256, 0, st>>>((float*)qk, ld, n_q_heads, n_q_heads + n_k_heads, D, (const bf16*)wq,
+                                                                    (const bf16*)wk, w_offset, eps, rstd, T, backward);
+  else
+    headnorm_kernel<bf16><<<unsigned((rows + 7) / 8), 256, 0, st>>>((bf16*)qk, ld, n_q_heads, n_q_heads + n_k_heads, D, (const bf16*)wq,
+                                                                   (const bf16*)wk, w_offset, eps, rstd, T, backward);
   LRP_CHECK_LAUNCH();
   return LRP_OK;
 }
 
 int lrp_headnorm_inplace(void* qk, int64_t ld, int n_q_heads, int n_k_heads, int D, const void* wq, const void* wk,
                          float w_offset, float eps, float* rstd, int T, int backward, void* stream) {
-  if (T <= 0 || n_q_heads < 0 || n_k_heads < 0 || n_q_heads + n_k_heads <= 0 || D <= 0 || (D % 8) != 0 || (ld % 8) != 0)
-    return set_error(LRP_ERR_ARG, "headnorm: D and ld must be multiples of 8");
-  const int64_t rows = int64_t(T) * (n_q_heads + n_k_heads);
-  headnorm_kernel<<<unsigned((rows + 7) / 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      (bf16*)qk, ld, n_q_heads, n_q_heads + n_k_heads, D, (const bf16*)wq, (const bf16*)wk, w_offset, eps, rstd, T, backward);
-  LRP_CHECK_LAUNCH();
-  return LRP_OK;
+  return lrp_headnorm_inplace_t(qk, 0, ld, n_q_heads, n_k_heads, D, wq, wk, w_offset, eps, rstd, T, backward, stream);
 }
 
 int lrp_layernorm_fwd(const void* x, const void* w, const void* b, float eps, void* y, float* mean, float* rstd, int T,
@@ -606,32 +664,60 @@ int lrp_layernorm_bwd(const void* gy, const void* w, const float* rstd, void* gx
   return LRP_OK;
 }
 
-int lrp_rope_inplace(void* qk, int64_t ld, int n_heads_total, int D, const float* cos_t, const float* sin_t, int T,
-                     int S, int inverse, void* stream) {
+int lrp_rope_inplace_t(void* qk, int is_f32, int64_t ld, int n_heads_total, int D, const float* cos_t, const float* sin_t, int T,
+                       int S, int inverse, void* stream) {
   if (T <= 0 || n_heads_total <= 0 || D <= 0 || (D % 16) != 0 || (ld % 8) != 0 || S <= 0)
     return set_error(LRP_ERR_ARG, "rope: D must be a multiple of 16 and ld a multiple of 8");
   const int64_t total = int64_t(T) * n_heads_total * (D / 16);
-  rope_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>((bf16*)qk, ld, n_heads_total, D, cos_t,
-                                                                                  sin_t, T, S, inverse);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (is_f32)
+    rope_kernel<float><<<grid_for(total, 256), 256, 0, st>>>((float*)qk, ld, n_heads_total, D, cos_t, sin_t, T, S, inverse);
+  else
+    rope_kernel<bf16><<<grid_for(total, 256), 256, 0, st>>>((bf16*)qk, ld, n_heads_total, D, cos_t, sin_t, T, S, inverse);
+  LRP_CHECK_LAUNCH();
+  return LRP_OK;
+}
+
+int lrp_rope_inplace(void* qk, int64_t ld, int n_heads_total, int D, const float* cos_t, const float* sin_t, int T,
+                     int S, int inverse, void* stream) {
+  return lrp_rope_inplace_t(qk, 0, ld, n_heads_total, D, cos_t, sin_t, T, S, inverse, stream);
+}
+
+int lrp_gated_act_fwd_t(const void* gu, void* a, int is_f32, int T, int I, int act, void* stream) {
+  if (T <= 0 || I <= 0 || (I % 8) != 0) return set_error(LRP_ERR_ARG, "gated_act_fwd: I must be a positive multiple of 8");
+  if (act < 0 || act > 2) return set_error(LRP_ERR_ARG, "gated_act_fwd: unknown activation");
+  const int64_t total = int64_t(T) * (I / 8);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (is_f32) gated_act_fwd_kernel<float><<<grid_for(total, 256), 256, 0, st>>>((const float*)gu, (float*)a, T, I, act);
+  else gated_act_fwd_kernel<bf16><<<grid_for(total, 256), 256, 0, st>>>((const bf16*)gu, (bf16*)a, T, I, act);
   LRP_CHECK_LAUNCH();
   return LRP_OK;
 }
 
 int lrp_gated_act_fwd(const void* gu, void* a, int T, int I, int act, void* stream) {
-  if (T <= 0 || I <= 0 || (I % 8) != 0) return set_error(LRP_ERR_ARG, "gated_act_fwd: I must be a positive multiple of 8");
-  if (act < 0 || act > 2) return set_error(LRP_ERR_ARG, "gated_act_fwd: unknown activation");
+  return lrp_gated_act_fwd_t(gu, a, 0, T, I, act, stream);
+}
+
+int lrp_gated_act_bwd_t(const void* ga, const void* gu, void* ggu, int is_f32, int T, int I, int act, int cp_variant, void* stream) {
+  if (T <= 0 || I <= 0 || (I % 8) != 0) return set_error(LRP_ERR_ARG, "gated_act_bwd: I must be a positive multiple of 8");
+  if (act < 0 || act > 2) return set_error(LRP_ERR_ARG, "gated_act_bwd: unknown activation");
   const int64_t total = int64_t(T) * (I / 8);
-  gated_act_fwd_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>((const bf16*)gu, (bf16*)a, T, I, act);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (is_f32)
+    gated_act_bwd_kernel<float><<<grid_for(total, 256), 256, 0, st>>>((const float*)ga, (const float*)gu, (float*)ggu, T, I, act, cp_variant);
+  else
+    gated_act_bwd_kernel<bf16><<<grid_for(total, 256), 256, 0, st>>>((const bf16*)ga, (const bf16*)gu, (bf16*)ggu, T, I, act, cp_variant);
   LRP_CHECK_LAUNCH();
   return LRP_OK;
 }
 
 int lrp_gated_act_bwd(const void* ga, const void* gu, void* ggu, int T, int I, int act, int cp_variant, void* stream) {
-  if (T <= 0 || I <= 0 || (I % 8) != 0) return set_error(LRP_ERR_ARG, "gated_act_bwd: I must be a positive multiple of 8");
-  if (act < 0 || act > 2) return set_error(LRP_ERR_ARG, "gated_act_bwd: unknown activation");
-  const int64_t total = int64_t(T) * (I / 8);
-  gated_act_bwd_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>((const bf16*)ga, (const bf16*)gu,
-                                                                                          (bf16*)ggu, T, I, act, cp_variant);
+  return lrp_gated_act_bwd_t(ga, gu, ggu, 0, T, I, act, cp_variant, stream);
+}
+
+int lrp_split_bf16x2(const float* x, void* hi, void* lo, int64_t n, void* stream) {
+  if (n <= 0 || (n % 8) != 0) return set_error(LRP_ERR_ARG, "split_bf16x2: n must be a positive multiple of 8");
+  split_bf16x2_kernel<<<grid_for(n / 8, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, (bf16*)hi, (bf16*)lo, n / 8);
   LRP_CHECK_LAUNCH();
   return LRP_OK;
 }

@@ -224,6 +224,10 @@ int main(int argc, char** argv) {
   run_case(1, 128, 1, 1, 128, 1, 0, false);
   run_case(1, 256, 2, 1, 128, 1, 0, false);
   run_case(2, 300, 4, 2, 128, 1, 0, true);
+  run_case(1, 384, 2, 2, 128, 1, 0, false);     // odd number of query tiles: the second tile of the last pair is absent
+  run_case(2, 1000, 8, 2, 128, 1, 0, true);     // ragged tail, several work items per CTA
+  run_case(1, 2048, 40, 8, 128, 1, 0, true);    // more work items than SMs: persistent loop, phases across items
+  run_case(2, 333, 4, 4, 128, 0, 0, false);     // full (non-causal) attention
   run_case(2, 300, 4, 2, 64, 1, 0, true);
   run_case(2, 197, 4, 4, 64, 0, 0, false);
   run_case(1, 520, 4, 1, 128, 1, 200, true);
@@ -235,6 +239,7 @@ int main(int argc, char** argv) {
   printf(g_fail ? "SELFTEST FAILED (%d)\n" : "SELFTEST PASSED\n", g_fail);
   if (perf) {
     perf_case(4, 2048, 32, 8, 128);
+    perf_case(8, 2048, 32, 8, 128);
     perf_case(1, 512, 32, 4, 64);
     perf_case(1, 8192, 8, 4, 256);
   }

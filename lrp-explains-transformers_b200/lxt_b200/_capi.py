@@ -79,6 +79,22 @@ SIGNATURES = {
     "lrp_identity_rule_bwd": (_i, [_vp, _vp, _vp, _vp, _i64, _i, _vp]),
     "lrp_softmax_dt_bwd": (_i, [_vp, _vp, _vp, _vp, _i64, _i, _i, _vp]),
     "lrp_add2_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _i64, _f, _i, _vp]),
+    # validation-precision mode (fp32 activations)
+    "lrp_rmsnorm_fwd_t": (_i, [_vp, _i, _vp, _f, _f, _vp, _i, _vp, _i, _i, _vp]),
+    "lrp_rmsnorm_bwd_t": (_i, [_vp, _i, _vp, _f, _vp, _vp, _i, _i, _i, _i, _vp]),
+    "lrp_rmsnorm_fwd_residual_t": (_i, [_vp, _i, _vp, _f, _f, _vp, _vp, _i, _i, _vp]),
+    "lrp_headnorm_inplace_t": (_i, [_vp, _i, _i64, _i, _i, _i, _vp, _vp, _f, _f, _vp, _i, _i, _vp]),
+    "lrp_rope_inplace_t": (_i, [_vp, _i, _i64, _i, _i, _vp, _vp, _i, _i, _i, _vp]),
+    "lrp_gated_act_fwd_t": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
+    "lrp_gated_act_bwd_t": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    "lrp_split_bf16x2": (_i, [_vp, _vp, _vp, _i64, _vp]),
+    "lrp_attn_fwd_f32": (_i, [_vp, _vp, _vp, _i64, _i64, _i64, _vp, _vp, _i, _i, _i, _i, _i, _f, _i, _i, _vp]),
+    "lrp_attn_bwd_f32": (
+        _i,
+        [_vp, _vp, _vp, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _vp,
+         _i, _i, _i, _i, _i, _f, _i, _i, _f, _f, _f, _vp],
+    ),
+    "lrp_attn_bwd_workspace_bytes": (_i, [_i, _i, _i, _i, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
 }
 
 _lib = None

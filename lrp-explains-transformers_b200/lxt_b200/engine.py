@@ -98,7 +98,7 @@ class LlamaAttnLRPEngine:
     """B200-native AttnLRP engine.  Construct with `from_weights`, `from_hf` or `random_init`."""
 
     def __init__(self, dims: LlamaDims, device: torch.device, weights: Dict, micro_batch: int = 8, store: str = "all",
-                 rule: str = "attnlrp", cuda_graph: bool = False):
+                 rule: str = "attnlrp", cuda_graph: bool = False, precision: str = "bf16"):
         if device.type != "cuda":
             raise RuntimeError("LlamaAttnLRPEngine runs on a CUDA (B200) device only; there is no CPU path")
         ops._capi.require_device()
@@ -106,10 +106,18 @@ class LlamaAttnLRPEngine:
         if rule not in ("attnlrp", "cp"):
             raise ValueError("rule must be 'attnlrp' (lxt attnLRP map) or 'cp' (lxt cp_LRP map)")
         self.cp = rule == "cp"  # CP-LRP: q,k and the MLP gate detached (lxt/efficient/models/llama.py:16-21)
+        # precision="high" is the VALIDATION mode: every activation / gradient tensor is stored in fp32, every GEMM runs as a
+        # two-term bf16 split (x = hi + lo) on the same tcgen05 kernel, the point-wise kernels are the fp32 instantiations of
+        # the same templates and attention runs on the fp32 CUDA-core kernel (attn_f32.cu).  It exists to show that the bf16
+        # mode's distance to the reference's fp32 run is storage rounding, not a defect; it is ~5-10x slower.
+        if precision not in ("bf16", "high"):
+            raise ValueError("precision must be 'bf16' (production) or 'high' (fp32-activation validation mode)")
+        self.hp = precision == "high"
+        self.adt = torch.float32 if self.hp else torch.bfloat16
         import os
         # fusing the gated-MLP backward rules into the down-dgrad epilogue was measured SLOWER on B200 (16.2 vs 16.9
         # attributions/s: the exp/div epilogue outlasts the K=4096 mainloop), so it is opt-in
-        self.fuse_gated = os.environ.get("LRP_FUSE_GATED", "0") == "1"
+        self.fuse_gated = os.environ.get("LRP_FUSE_GATED", "0") == "1" and not self.hp
         bf = lambda t: t.to(device=device, dtype=torch.bfloat16).contiguous()
         f32 = lambda t: t.to(device=device, dtype=torch.float32).contiguous()
         self.emb = bf(weights["emb"])
@@ -223,7 +231,7 @@ class LlamaAttnLRPEngine:
         self._ws = None  # release the previous workspace before allocating the new one
         m, dev = self.dims, self.device
         T = B * S
-        e = lambda *s, dt=torch.bfloat16: torch.empty(*s, dtype=dt, device=dev)
+        e = lambda *s, dt=self.adt: torch.empty(*s, dtype=dt, device=dev)
         ws = {}
         n_store = m.L if self.store_policy == "all" else self._segment_len()
         stores = []
@@ -241,7 +249,7 @@ class LlamaAttnLRPEngine:
             ws["h_ckpt"] = [e(T, m.d, dt=torch.float32) for _ in range(math.ceil(m.L / self._segment_len()))]
         ws["h"] = e(T, m.d, dt=torch.float32)
         ws["g_h"] = e(T, m.d, dt=torch.float32)
-        ws["g_hb"] = e(T, m.d)
+        ws["g_hb"] = ws["g_h"] if self.hp else e(T, m.d)   # GEMM A operand: bf16 shadow (fp32 stream itself in validation mode)
         ws["xn"] = e(T, m.d)
         if m.post_norms:
             ws["y"] = e(T, m.d)      # branch output before its post-norm (forward) / gradient after it (backward)
@@ -249,7 +257,7 @@ class LlamaAttnLRPEngine:
         ws["g_gu"] = e(T, 2 * m.I)
         ws["g_o"] = e(T, m.H * m.D)
         ws["g_qkv"] = e(T, m.qkv_width)
-        ws["dq_acc"] = e(B, S, m.H, m.D, dt=torch.float32)
+        ws["dq_acc"] = None if self.hp else e(B, S, m.H, m.D, dt=torch.float32)
         ws["delta"] = e(B, m.H, S, dt=torch.float32)
         ws["logits"] = e(B, m.V, dt=torch.float32)
         ws["last_rows"] = (torch.arange(B, device=dev, dtype=torch.int64) + 1) * S - 1
@@ -277,30 +285,36 @@ class LlamaAttnLRPEngine:
         scale = m.attn_scale or 1.0 / math.sqrt(m.D)
         off, win = m.norm_offset, m.window(l)
         lib, C = ops._capi.lib(), ops._capi
-        C.check(lib.lrp_rmsnorm_fwd(h.data_ptr(), 1, lw["ln1"].data_ptr(), off, m.eps, ws["xn"].data_ptr(), st.rstd1.data_ptr(),
-                                    T, m.d, ops._stream()), "rmsnorm_fwd")
+        f = int(self.hp)   # activation dtype flag of the typed entry points: 0 = bf16 (production), 1 = fp32 (validation mode)
+        C.check(lib.lrp_rmsnorm_fwd_t(h.data_ptr(), 1, lw["ln1"].data_ptr(), off, m.eps, ws["xn"].data_ptr(), f, st.rstd1.data_ptr(),
+                                      T, m.d, ops._stream()), "rmsnorm_fwd")
         ops.linear_fwd(ws["xn"], lw["wqkv"], st.qkv, bias=lw.get("bqkv"))
         if m.qk_norm:
-            C.check(lib.lrp_headnorm_inplace(st.qkv.data_ptr(), m.qkv_width, m.H, m.Hkv, m.D, lw["qn"].data_ptr(), lw["kn"].data_ptr(),
-                                             off, m.eps, st.rstd_qk.data_ptr(), T, 0, ops._stream()), "headnorm_fwd")
+            C.check(lib.lrp_headnorm_inplace_t(st.qkv.data_ptr(), f, m.qkv_width, m.H, m.Hkv, m.D, lw["qn"].data_ptr(), lw["kn"].data_ptr(),
+                                               off, m.eps, st.rstd_qk.data_ptr(), T, 0, ops._stream()), "headnorm_fwd")
         ops.rope_inplace(st.qkv, m.H + m.Hkv, m.D, cos, sin, S)
         q, k, v = self._qkv_views(st.qkv, B, S)
-        C.check(lib.lrp_attn_fwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), m.qkv_width, m.qkv_width, m.qkv_width,
-                                 st.o.data_ptr(), st.lse.data_ptr(), B, S, m.H, m.Hkv, m.D, scale, 1, win, ops._stream()), "attn_fwd")
+        if self.hp:
+            C.check(lib.lrp_attn_fwd_f32(q.data_ptr(), k.data_ptr(), v.data_ptr(), m.qkv_width, m.qkv_width, m.qkv_width,
+                                         st.o.data_ptr(), st.lse.data_ptr(), B, S, m.H, m.Hkv, m.D, scale, 1, win, ops._stream()),
+                    "attn_fwd_f32")
+        else:
+            C.check(lib.lrp_attn_fwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), m.qkv_width, m.qkv_width, m.qkv_width,
+                                     st.o.data_ptr(), st.lse.data_ptr(), B, S, m.H, m.Hkv, m.D, scale, 1, win, ops._stream()), "attn_fwd")
         if m.post_norms:
             ops.linear_fwd(st.o, lw["wo"], ws["y"])
-            C.check(lib.lrp_rmsnorm_fwd_residual(ws["y"].data_ptr(), lw["ln_post_attn"].data_ptr(), off, m.eps, h.data_ptr(),
-                                                 st.rstd_pa.data_ptr(), T, m.d, ops._stream()), "rmsnorm_fwd_residual")
+            C.check(lib.lrp_rmsnorm_fwd_residual_t(ws["y"].data_ptr(), f, lw["ln_post_attn"].data_ptr(), off, m.eps, h.data_ptr(),
+                                                   st.rstd_pa.data_ptr(), T, m.d, ops._stream()), "rmsnorm_fwd_residual")
         else:
             ops.linear_fwd(st.o, lw["wo"], h, resid=h)
-        C.check(lib.lrp_rmsnorm_fwd(h.data_ptr(), 1, lw["ln2"].data_ptr(), off, m.eps, ws["xn"].data_ptr(), st.rstd2.data_ptr(),
-                                    T, m.d, ops._stream()), "rmsnorm_fwd")
+        C.check(lib.lrp_rmsnorm_fwd_t(h.data_ptr(), 1, lw["ln2"].data_ptr(), off, m.eps, ws["xn"].data_ptr(), f, st.rstd2.data_ptr(),
+                                      T, m.d, ops._stream()), "rmsnorm_fwd")
         ops.linear_fwd(ws["xn"], lw["wgu"], st.gu)
-        C.check(lib.lrp_gated_act_fwd(st.gu.data_ptr(), ws["a"].data_ptr(), T, m.I, m.act_code, ops._stream()), "gated_act_fwd")
+        C.check(lib.lrp_gated_act_fwd_t(st.gu.data_ptr(), ws["a"].data_ptr(), f, T, m.I, m.act_code, ops._stream()), "gated_act_fwd")
         if m.post_norms:
             ops.linear_fwd(ws["a"], lw["wd"], ws["y"])
-            C.check(lib.lrp_rmsnorm_fwd_residual(ws["y"].data_ptr(), lw["ln_post_ff"].data_ptr(), off, m.eps, h.data_ptr(),
-                                                 st.rstd_pf.data_ptr(), T, m.d, ops._stream()), "rmsnorm_fwd_residual")
+            C.check(lib.lrp_rmsnorm_fwd_residual_t(ws["y"].data_ptr(), f, lw["ln_post_ff"].data_ptr(), off, m.eps, h.data_ptr(),
+                                                   st.rstd_pf.data_ptr(), T, m.d, ops._stream()), "rmsnorm_fwd_residual")
         else:
             ops.linear_fwd(ws["a"], lw["wd"], h, resid=h)
 
@@ -312,6 +326,8 @@ class LlamaAttnLRPEngine:
         off, win = m.norm_offset, m.window(l)
         lib, C = ops._capi.lib(), ops._capi
         g_h, g_hb = ws["g_h"], ws["g_hb"]
+        f = int(self.hp)
+        shadow = None if self.hp else g_hb
         # ---- gated MLP
         src = g_hb
         if m.post_norms:   # identity rule through the post-feed-forward norm: g * (off + w) * rstd of the branch output
@@ -321,9 +337,9 @@ class LlamaAttnLRPEngine:
             ops.linear_dgrad_gated_bwd(src, lw["wd"], st.gu, ws["g_gu"], m.act_code, self.cp)
         else:
             ops.linear_dgrad(src, lw["wd"], ws["a"])                               # g_a [T, I]
-            C.check(lib.lrp_gated_act_bwd(ws["a"].data_ptr(), st.gu.data_ptr(), ws["g_gu"].data_ptr(), T, m.I, m.act_code,
-                                          int(self.cp), ops._stream()), "gated_act_bwd")
-        ops.linear_dgrad(ws["g_gu"], lw["wgu"], g_h, resid=g_h, rowscale=st.rstd2, colscale=lw["ln2_f"], shadow=g_hb)
+            C.check(lib.lrp_gated_act_bwd_t(ws["a"].data_ptr(), st.gu.data_ptr(), ws["g_gu"].data_ptr(), f, T, m.I, m.act_code,
+                                            int(self.cp), ops._stream()), "gated_act_bwd")
+        ops.linear_dgrad(ws["g_gu"], lw["wgu"], g_h, resid=g_h, rowscale=st.rstd2, colscale=lw["ln2_f"], shadow=shadow)
         # ---- attention
         src = g_hb
         if m.post_norms:
@@ -331,17 +347,23 @@ class LlamaAttnLRPEngine:
         ops.linear_dgrad(src, lw["wo"], ws["g_o"])                                 # g_o [T, H D]
         q, k, v = self._qkv_views(st.qkv, B, S)
         dq, dk, dv = self._qkv_views(ws["g_qkv"], B, S)
-        C.check(lib.lrp_attn_bwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), m.qkv_width, m.qkv_width, m.qkv_width,
-                                 st.o.data_ptr(), ws["g_o"].data_ptr(), st.lse.data_ptr(), dq.data_ptr(), dk.data_ptr(),
-                                 dv.data_ptr(), m.qkv_width, m.qkv_width, m.qkv_width, ws["dq_acc"].data_ptr(),
-                                 ws["delta"].data_ptr(), B, S, m.H, m.Hkv, m.D, scale, 1, win, *((0.0, 0.0, 1.0) if self.cp else (4.0, 4.0, 2.0)),
-                                 ops._stream()),
-                "attn_bwd")
+        divs = (0.0, 0.0, 1.0) if self.cp else (4.0, 4.0, 2.0)
+        if self.hp:
+            C.check(lib.lrp_attn_bwd_f32(q.data_ptr(), k.data_ptr(), v.data_ptr(), m.qkv_width, m.qkv_width, m.qkv_width,
+                                         st.o.data_ptr(), ws["g_o"].data_ptr(), st.lse.data_ptr(), dq.data_ptr(), dk.data_ptr(),
+                                         dv.data_ptr(), m.qkv_width, m.qkv_width, m.qkv_width, ws["delta"].data_ptr(), B, S, m.H,
+                                         m.Hkv, m.D, scale, 1, win, *divs, ops._stream()), "attn_bwd_f32")
+        else:
+            C.check(lib.lrp_attn_bwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), m.qkv_width, m.qkv_width, m.qkv_width,
+                                     st.o.data_ptr(), ws["g_o"].data_ptr(), st.lse.data_ptr(), dq.data_ptr(), dk.data_ptr(),
+                                     dv.data_ptr(), m.qkv_width, m.qkv_width, m.qkv_width, ws["dq_acc"].data_ptr(),
+                                     ws["delta"].data_ptr(), B, S, m.H, m.Hkv, m.D, scale, 1, win, *divs, ops._stream()),
+                    "attn_bwd")
         ops.rope_inplace(ws["g_qkv"], m.H + m.Hkv, m.D, cos, sin, S, inverse=True)
         if m.qk_norm:
-            C.check(lib.lrp_headnorm_inplace(ws["g_qkv"].data_ptr(), m.qkv_width, m.H, m.Hkv, m.D, lw["qn"].data_ptr(),
-                                             lw["kn"].data_ptr(), off, m.eps, st.rstd_qk.data_ptr(), T, 1, ops._stream()), "headnorm_bwd")
-        ops.linear_dgrad(ws["g_qkv"], lw["wqkv"], g_h, resid=g_h, rowscale=st.rstd1, colscale=lw["ln1_f"], shadow=g_hb)
+            C.check(lib.lrp_headnorm_inplace_t(ws["g_qkv"].data_ptr(), f, m.qkv_width, m.H, m.Hkv, m.D, lw["qn"].data_ptr(),
+                                               lw["kn"].data_ptr(), off, m.eps, st.rstd_qk.data_ptr(), T, 1, ops._stream()), "headnorm_bwd")
+        ops.linear_dgrad(ws["g_qkv"], lw["wqkv"], g_h, resid=g_h, rowscale=st.rstd1, colscale=lw["ln1_f"], shadow=shadow)
 
     def _qkv_views(self, buf, B, S):
         m = self.dims
@@ -384,7 +406,7 @@ class LlamaAttnLRPEngine:
 
         # ---- head: only the last position is read (examples/quantized_llama.py:40)
         h_last = h.index_select(0, ws["last_rows"])
-        xn_last, rstd_last = ops.rmsnorm_fwd(h_last, self.norm_w, m.eps, w_offset=m.norm_offset)
+        xn_last, rstd_last = ops.rmsnorm_fwd(h_last, self.norm_w, m.eps, w_offset=m.norm_offset, out_dtype=self.adt)
         ops.linear_fwd(xn_last, self.lm_head, ws["logits"])
         idx, _ = ops.argmax_rows(ws["logits"])
         # seed: d(max logit)/d(xn_last) = lm_head[idx]; through the final norm with the identity rule
@@ -392,7 +414,8 @@ class LlamaAttnLRPEngine:
         g_last = ops.rmsnorm_bwd(g_xn_last, self.norm_w, rstd_last, w_offset=m.norm_offset, out_dtype=torch.float32)
         g_h.zero_()
         g_h.index_copy_(0, ws["last_rows"], g_last)
-        ops.cast_bf16(g_h, g_hb)
+        if not self.hp:
+            ops.cast_bf16(g_h, g_hb)
 
         if self.store_policy == "all":
             layer_rel = [None] * m.L

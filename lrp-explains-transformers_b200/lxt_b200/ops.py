@@ -73,8 +73,31 @@ def make_epilogue(out: torch.Tensor, *, resid: Optional[torch.Tensor] = None, ro
     return e
 
 
+def split_bf16x2(x: torch.Tensor):
+    """fp32 x -> (hi, lo) bf16 with x ~= hi + lo to ~16 mantissa bits (validation-precision GEMM operands)"""
+    _need(x, torch.float32, "x")
+    x = x.contiguous()
+    if x.numel() % 8:
+        raise _capi.LrpError("split_bf16x2: element count must be a multiple of 8")
+    hi = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
+    lo = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
+    check(_capi.lib().lrp_split_bf16x2(x.data_ptr(), hi.data_ptr(), lo.data_ptr(), x.numel(), _stream()), "lrp_split_bf16x2")
+    return hi, lo
+
+
 def gemm(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor, *, b_layout: int, tile_n: int = 0, **epi) -> torch.Tensor:
-    """out = epilogue(a @ b.T) for b_layout 0 (b is [N,K]) or epilogue(a @ b) for b_layout 1 (b is [K,N])."""
+    """out = epilogue(a @ b.T) for b_layout 0 (b is [N,K]) or epilogue(a @ b) for b_layout 1 (b is [K,N]).
+    An fp32 `a` selects the validation-precision form: a = hi + lo (two bf16 terms), out = epilogue(hi b) then
+    out += alpha * rowscale * colscale * (lo b), both on the same bf16 tcgen05 kernel with fp32 accumulation; `out` must be fp32."""
+    if a.dtype == torch.float32:
+        if out.dtype != torch.float32:
+            raise _capi.LrpError("gemm: an fp32 A operand (validation precision) needs an fp32 output")
+        if epi.get("shadow") is not None:
+            raise _capi.LrpError("gemm: no bf16 shadow in validation precision")
+        hi, lo = split_bf16x2(a)
+        gemm(hi, b, out, b_layout=b_layout, tile_n=tile_n, **epi)
+        epi2 = {k: v for k, v in epi.items() if k in ("rowscale", "colscale", "alpha")}
+        return gemm(lo, b, out, b_layout=b_layout, tile_n=tile_n, resid=out, **epi2)
     _need(a, torch.bfloat16, "a")
     _need(b, torch.bfloat16, "b")
     lda, ldb = _rowmajor2d(a, "a"), _rowmajor2d(b, "b")
@@ -136,8 +159,9 @@ def linear_dgrad(gy: torch.Tensor, w: torch.Tensor, out: torch.Tensor, **epi) ->
     return gemm(gy, w, out, b_layout=1, **epi)
 
 
-def rmsnorm_fwd(x: torch.Tensor, w: torch.Tensor, eps: float, *, w_offset: float = 0.0, want_rstd: bool = True):
-    """x [T,d] (bf16 or fp32) -> (y bf16 [T,d], rstd fp32 [T])"""
+def rmsnorm_fwd(x: torch.Tensor, w: torch.Tensor, eps: float, *, w_offset: float = 0.0, want_rstd: bool = True,
+                out_dtype=torch.bfloat16, out: Optional[torch.Tensor] = None, rstd: Optional[torch.Tensor] = None):
+    """x [T,d] (bf16 or fp32) -> (y [T,d] bf16 (default) or fp32, rstd fp32 [T])"""
     if x.dtype not in (torch.float32, torch.bfloat16):
         raise _capi.LrpError("rmsnorm_fwd: x must be bf16 or fp32")
     _need(x, x.dtype, "x")
@@ -145,16 +169,21 @@ def rmsnorm_fwd(x: torch.Tensor, w: torch.Tensor, eps: float, *, w_offset: float
     T, d = x.shape
     if not x.is_contiguous():
         raise _capi.LrpError("rmsnorm_fwd: x must be contiguous")
-    y = torch.empty((T, d), dtype=torch.bfloat16, device=x.device)
-    rstd = torch.empty((T,), dtype=torch.float32, device=x.device) if want_rstd else None
-    check(_capi.lib().lrp_rmsnorm_fwd(x.data_ptr(), int(x.dtype == torch.float32), w.data_ptr(), w_offset, eps,
-                                      y.data_ptr(), _p(rstd), T, d, _stream()), "lrp_rmsnorm_fwd")
+    y = out if out is not None else torch.empty((T, d), dtype=out_dtype, device=x.device)
+    if y.dtype not in (torch.float32, torch.bfloat16) or not y.is_contiguous():
+        raise _capi.LrpError("rmsnorm_fwd: y must be a contiguous bf16 or fp32 tensor")
+    if rstd is None and want_rstd:
+        rstd = torch.empty((T,), dtype=torch.float32, device=x.device)
+    check(_capi.lib().lrp_rmsnorm_fwd_t(x.data_ptr(), int(x.dtype == torch.float32), w.data_ptr(), w_offset, eps,
+                                        y.data_ptr(), int(y.dtype == torch.float32), _p(rstd), T, d, _stream()), "lrp_rmsnorm_fwd")
     return y, rstd
 
 
 def rmsnorm_bwd(gy: torch.Tensor, w: torch.Tensor, rstd: torch.Tensor, *, w_offset: float = 0.0,
                 out: Optional[torch.Tensor] = None, out_dtype=torch.bfloat16, accumulate: bool = False) -> torch.Tensor:
-    _need(gy, torch.bfloat16, "gy")
+    if gy.dtype not in (torch.float32, torch.bfloat16):
+        raise _capi.LrpError("rmsnorm_bwd: gy must be bf16 or fp32")
+    _need(gy, gy.dtype, "gy")
     _need(w, torch.bfloat16, "w")
     _need(rstd, torch.float32, "rstd")
     T, d = gy.shape
@@ -162,8 +191,9 @@ def rmsnorm_bwd(gy: torch.Tensor, w: torch.Tensor, rstd: torch.Tensor, *, w_offs
         raise _capi.LrpError("rmsnorm_bwd: gy must be contiguous")
     if out is None:
         out = torch.empty((T, d), dtype=out_dtype, device=gy.device)
-    check(_capi.lib().lrp_rmsnorm_bwd(gy.data_ptr(), w.data_ptr(), w_offset, rstd.data_ptr(), out.data_ptr(),
-                                      int(out.dtype == torch.float32), int(accumulate), T, d, _stream()), "lrp_rmsnorm_bwd")
+    check(_capi.lib().lrp_rmsnorm_bwd_t(gy.data_ptr(), int(gy.dtype == torch.float32), w.data_ptr(), w_offset, rstd.data_ptr(),
+                                        out.data_ptr(), int(out.dtype == torch.float32), int(accumulate), T, d, _stream()),
+          "lrp_rmsnorm_bwd")
     return out
 
 
@@ -191,35 +221,46 @@ def layernorm_bwd(gy: torch.Tensor, w: Optional[torch.Tensor], rstd: torch.Tenso
 
 def rope_inplace(qk: torch.Tensor, n_heads: int, D: int, cos: torch.Tensor, sin: torch.Tensor, S: int, *, inverse: bool = False):
     """rotate the first n_heads*D columns of qk [T, ld] in place; cos/sin fp32 [S, D/2]."""
-    _need(qk, torch.bfloat16, "qk")
+    if qk.dtype not in (torch.float32, torch.bfloat16):
+        raise _capi.LrpError("rope_inplace: qk must be bf16 or fp32")
+    _need(qk, qk.dtype, "qk")
     _need(cos, torch.float32, "cos")
     _need(sin, torch.float32, "sin")
     ld = _rowmajor2d(qk, "qk")
-    check(_capi.lib().lrp_rope_inplace(qk.data_ptr(), ld, n_heads, D, cos.data_ptr(), sin.data_ptr(), qk.shape[0], S,
-                                       int(inverse), _stream()), "lrp_rope_inplace")
+    check(_capi.lib().lrp_rope_inplace_t(qk.data_ptr(), int(qk.dtype == torch.float32), ld, n_heads, D, cos.data_ptr(),
+                                         sin.data_ptr(), qk.shape[0], S, int(inverse), _stream()), "lrp_rope_inplace")
     return qk
 
 
-def gated_act_fwd(gu: torch.Tensor, act: int = ACT_SILU) -> torch.Tensor:
-    _need(gu, torch.bfloat16, "gu")
+def gated_act_fwd(gu: torch.Tensor, act: int = ACT_SILU, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    if gu.dtype not in (torch.float32, torch.bfloat16):
+        raise _capi.LrpError("gated_act_fwd: gu must be bf16 or fp32")
+    _need(gu, gu.dtype, "gu")
     T, I2 = gu.shape
     if not gu.is_contiguous():
         raise _capi.LrpError("gated_act_fwd: gu must be contiguous")
-    a = torch.empty((T, I2 // 2), dtype=torch.bfloat16, device=gu.device)
-    check(_capi.lib().lrp_gated_act_fwd(gu.data_ptr(), a.data_ptr(), T, I2 // 2, act, _stream()), "lrp_gated_act_fwd")
+    a = out if out is not None else torch.empty((T, I2 // 2), dtype=gu.dtype, device=gu.device)
+    if a.dtype != gu.dtype or not a.is_contiguous():
+        raise _capi.LrpError("gated_act_fwd: output must be contiguous and share gu's dtype")
+    check(_capi.lib().lrp_gated_act_fwd_t(gu.data_ptr(), a.data_ptr(), int(gu.dtype == torch.float32), T, I2 // 2, act, _stream()),
+          "lrp_gated_act_fwd")
     return a
 
 
 def gated_act_bwd(ga: torch.Tensor, gu: torch.Tensor, act: int = ACT_SILU, out: Optional[torch.Tensor] = None, cp: bool = False) -> torch.Tensor:
-    _need(ga, torch.bfloat16, "ga")
-    _need(gu, torch.bfloat16, "gu")
+    if gu.dtype not in (torch.float32, torch.bfloat16):
+        raise _capi.LrpError("gated_act_bwd: gu must be bf16 or fp32")
+    _need(ga, gu.dtype, "ga")
+    _need(gu, gu.dtype, "gu")
     T, I2 = gu.shape
     if not (ga.is_contiguous() and gu.is_contiguous()):
         raise _capi.LrpError("gated_act_bwd: inputs must be contiguous")
     if out is None:
         out = torch.empty_like(gu)
-    check(_capi.lib().lrp_gated_act_bwd(ga.data_ptr(), gu.data_ptr(), out.data_ptr(), T, I2 // 2, act, int(cp), _stream()),
-          "lrp_gated_act_bwd")
+    if out.dtype != gu.dtype or not out.is_contiguous():
+        raise _capi.LrpError("gated_act_bwd: output must be contiguous and share gu's dtype")
+    check(_capi.lib().lrp_gated_act_bwd_t(ga.data_ptr(), gu.data_ptr(), out.data_ptr(), int(gu.dtype == torch.float32), T, I2 // 2,
+                                          act, int(cp), _stream()), "lrp_gated_act_bwd")
     return out
 
 
@@ -241,9 +282,9 @@ def act_identity_bwd(gy: torch.Tensor, x: torch.Tensor, act: int) -> torch.Tenso
     return gx
 
 
-def _bshd(t: torch.Tensor, name: str):
+def _bshd(t: torch.Tensor, name: str, dtype=torch.bfloat16):
     """accept [B,S,H,D] tensors whose last dim is contiguous, head stride D, batch stride S*token stride"""
-    _need(t, torch.bfloat16, name)
+    _need(t, dtype, name)
     B, S, H, D = t.shape
     if t.stride(3) != 1 or (H > 1 and t.stride(2) != D) or (B > 1 and t.stride(0) != S * t.stride(1)):
         raise _capi.LrpError(f"{name}: expected [B,S,H,D] with strides (S*ld, ld, D, 1), got {t.stride()}")
@@ -252,11 +293,18 @@ def _bshd(t: torch.Tensor, name: str):
 
 def attn_fwd(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, scale: float, *, causal: bool = True, window: int = 0):
     """q [B,S,H,D], k/v [B,S,Hkv,D] (views into a packed buffer are fine) -> (o [B,S,H,D] bf16, lse fp32 [B,H,S])"""
-    ldq, ldk, ldv = _bshd(q, "q"), _bshd(k, "k"), _bshd(v, "v")
+    dt = q.dtype
+    if dt not in (torch.float32, torch.bfloat16):
+        raise _capi.LrpError("attn_fwd: q must be bf16 or fp32")
+    ldq, ldk, ldv = _bshd(q, "q", dt), _bshd(k, "k", dt), _bshd(v, "v", dt)
     B, S, H, D = q.shape
     Hkv = k.shape[2]
-    o = torch.empty((B, S, H, D), dtype=torch.bfloat16, device=q.device)
+    o = torch.empty((B, S, H, D), dtype=dt, device=q.device)
     lse = torch.empty((B, H, S), dtype=torch.float32, device=q.device)
+    if dt == torch.float32:   # validation precision: fp32 CUDA-core kernel
+        check(_capi.lib().lrp_attn_fwd_f32(q.data_ptr(), k.data_ptr(), v.data_ptr(), ldq, ldk, ldv, o.data_ptr(), lse.data_ptr(),
+                                           B, S, H, Hkv, D, scale, int(causal), window, _stream()), "lrp_attn_fwd_f32")
+        return o, lse
     check(_capi.lib().lrp_attn_fwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), ldq, ldk, ldv, o.data_ptr(), lse.data_ptr(),
                                    B, S, H, Hkv, D, scale, int(causal), window, _stream()), "lrp_attn_fwd")
     return o, lse
@@ -265,20 +313,31 @@ def attn_fwd(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, scale: float, *,
 def attn_bwd(q, k, v, o, d_o, lse, scale: float, *, causal: bool = True, window: int = 0, q_div: float = 4.0,
              k_div: float = 4.0, v_div: float = 2.0, dq=None, dk=None, dv=None, dq_acc=None, delta=None):
     """LRP backward of attention: returns (dq, dk, dv) already divided by (q_div, k_div, v_div)."""
-    ldq, ldk, ldv = _bshd(q, "q"), _bshd(k, "k"), _bshd(v, "v")
+    dt = q.dtype
+    if dt not in (torch.float32, torch.bfloat16):
+        raise _capi.LrpError("attn_bwd: q must be bf16 or fp32")
+    ldq, ldk, ldv = _bshd(q, "q", dt), _bshd(k, "k", dt), _bshd(v, "v", dt)
     B, S, H, D = q.shape
     Hkv = k.shape[2]
-    _need(o, torch.bfloat16, "o")
-    _need(d_o, torch.bfloat16, "d_o")
+    _need(o, dt, "o")
+    _need(d_o, dt, "d_o")
     if not (o.is_contiguous() and d_o.is_contiguous()):
         raise _capi.LrpError("attn_bwd: o and d_o must be contiguous [B,S,H,D]")
     if dq is None:
-        dq = torch.empty((B, S, H, D), dtype=torch.bfloat16, device=q.device)
+        dq = torch.empty((B, S, H, D), dtype=dt, device=q.device)
     if dk is None:
-        dk = torch.empty((B, S, Hkv, D), dtype=torch.bfloat16, device=q.device)
+        dk = torch.empty((B, S, Hkv, D), dtype=dt, device=q.device)
     if dv is None:
-        dv = torch.empty((B, S, Hkv, D), dtype=torch.bfloat16, device=q.device)
-    lddq, lddk, lddv = _bshd(dq, "dq"), _bshd(dk, "dk"), _bshd(dv, "dv")
+        dv = torch.empty((B, S, Hkv, D), dtype=dt, device=q.device)
+    lddq, lddk, lddv = _bshd(dq, "dq", dt), _bshd(dk, "dk", dt), _bshd(dv, "dv", dt)
+    if dt == torch.float32:   # validation precision: fp32 CUDA-core kernels (dQ pass + key-major dK/dV pass)
+        if delta is None:
+            delta = torch.empty((B, H, S), dtype=torch.float32, device=q.device)
+        check(_capi.lib().lrp_attn_bwd_f32(q.data_ptr(), k.data_ptr(), v.data_ptr(), ldq, ldk, ldv, o.data_ptr(), d_o.data_ptr(),
+                                           lse.data_ptr(), dq.data_ptr(), dk.data_ptr(), dv.data_ptr(), lddq, lddk, lddv,
+                                           delta.data_ptr(), B, S, H, Hkv, D, scale, int(causal), window, q_div, k_div, v_div,
+                                           _stream()), "lrp_attn_bwd_f32")
+        return dq, dk, dv
     if dq_acc is None:
         dq_acc = torch.empty((B, S, H, D), dtype=torch.float32, device=q.device)
     if delta is None:
