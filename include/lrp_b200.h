@@ -68,6 +68,11 @@ typedef struct lrp_epilogue {
   void* gated_out;        /* bf16 [M, 2I] */
   int32_t gated_act;      /* LRP_ACT_* */
   int32_t gated_cp;       /* 1 = CP-LRP variant */
+  /* Optional fused gated-MLP FORWARD (lxt/efficient/patches.py:145-157): when `act_out` is set, this GEMM is the packed gate|up
+   * projection with its weight rows interleaved in blocks of 32 (32 gate rows, then the 32 matching up rows); `out` (bf16
+   * [M, 2I], same interleaved column order) is written as usual and act_out[m, i] = act(gate[m, i]) * up[m, i] (bf16 [M, I],
+   * gated_act selects the activation) — bit-identical to lrp_gated_act_fwd on the stored bf16 values. */
+  void* act_out;
 } lrp_epilogue_t;
 
 /* Generic tcgen05 GEMM, A [M,K] bf16.  b_layout 0: B is [N,K] (NT);  b_layout 1: B is [K,N] (NN).
@@ -181,6 +186,20 @@ int lrp_attn_bwd(const void* q, const void* k, const void* v, int64_t ldq, int64
                  int64_t lddk, int64_t lddv, float* dq_acc_ws, float* delta_ws, int B, int S, int H, int Hkv, int D,
                  float scale, int causal, int window, float q_div, float k_div, float v_div, void* stream);
 
+/* Batches of prompts of different lengths (the HF `attention_mask` of a padded batch, which the reference passes through to the
+ * wrapped HF attention function untouched: lxt/efficient/patches.py:193-203): `kv_range` is a DEVICE int32 [B,2] array, keys
+ * outside [kv_range[2b], kv_range[2b+1]) are masked for every query of sequence b (left or right padding); NULL = no padding.
+ * Query rows that see no key produce o = 0, lse = -inf and receive / contribute zero gradient. */
+int lrp_attn_fwd_varlen(const void* q, const void* k, const void* v, int64_t ldq, int64_t ldk, int64_t ldv, void* o,
+                        float* lse, const int32_t* kv_range, int B, int S, int H, int Hkv, int D, float scale, int causal,
+                        int window, void* stream);
+/* backward of lrp_attn_fwd_varlen (same rule and workspaces as lrp_attn_bwd; lxt/efficient/patches.py:193-203) */
+int lrp_attn_bwd_varlen(const void* q, const void* k, const void* v, int64_t ldq, int64_t ldk, int64_t ldv,
+                        const void* o, const void* d_o, const float* lse, void* dq, void* dk, void* dv, int64_t lddq,
+                        int64_t lddk, int64_t lddv, float* dq_acc_ws, float* delta_ws, const int32_t* kv_range, int B, int S,
+                        int H, int Hkv, int D, float scale, int causal, int window, float q_div, float k_div, float v_div,
+                        void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Ends of the path (examples/quantized_llama.py:35-47)
  * ---------------------------------------------------------------------------------------------- */
@@ -243,21 +262,23 @@ int lrp_headnorm_inplace_t(void* qk, int is_f32, int64_t ld, int n_q_heads, int 
  * SURVEY 0 table; explicit form lxt/explicit/models/llama.py:226-260) */
 int lrp_rope_inplace_t(void* qk, int is_f32, int64_t ld, int n_heads_total, int D, const float* cos_t, const float* sin_t, int T,
                        int S, int inverse, void* stream);
-/* lrp_gated_act_fwd on bf16 or fp32 tensors (lxt/efficient/patches.py:145-157) */
-int lrp_gated_act_fwd_t(const void* gu, void* a, int is_f32, int T, int I, int act, void* stream);
-/* lrp_gated_act_bwd on bf16 or fp32 tensors (lxt/efficient/rules.py:88-127) */
-int lrp_gated_act_bwd_t(const void* ga, const void* gu, void* ggu, int is_f32, int T, int I, int act, int cp_variant, void* stream);
+/* lrp_gated_act_fwd on bf16 or fp32 tensors (lxt/efficient/patches.py:145-157); layout 0: gu = (gate | up) halves, layout 1:
+ * blocks of 32 interleaved (32 gate columns, the 32 matching up columns, ...) as the fused gate|up GEMM epilogue writes them */
+int lrp_gated_act_fwd_t(const void* gu, void* a, int is_f32, int layout, int T, int I, int act, void* stream);
+/* lrp_gated_act_bwd on bf16 or fp32 tensors, same layouts for gu and ggu (lxt/efficient/rules.py:88-127) */
+int lrp_gated_act_bwd_t(const void* ga, const void* gu, void* ggu, int is_f32, int layout, int T, int I, int act, int cp_variant,
+                        void* stream);
 /* x (fp32, n elements) -> hi = bf16(x), lo = bf16(x - hi): operands of the split GEMM that replaces the fp32 `F.linear` of an fp32
  * model (transformers modeling_llama.py:183,262-264,288 executed in fp32, as in the reference's own tests/test_functional.py:57-76) */
 int lrp_split_bf16x2(const float* x, void* hi, void* lo, int64_t n, void* stream);
-/* fp32 flash AttnLRP forward (same contract as lrp_attn_fwd, all tensors fp32; lxt/efficient/patches.py:193-203) */
+/* fp32 flash AttnLRP forward (same contract as lrp_attn_fwd_varlen, all tensors fp32; lxt/efficient/patches.py:193-203) */
 int lrp_attn_fwd_f32(const float* q, const float* k, const float* v, int64_t ldq, int64_t ldk, int64_t ldv, float* o, float* lse,
-                     int B, int S, int H, int Hkv, int D, float scale, int causal, int window, void* stream);
-/* fp32 flash AttnLRP backward (same contract as lrp_attn_bwd; delta_ws fp32 [B,H,S]; lxt/efficient/patches.py:193-203) */
+                     const int32_t* kv_range, int B, int S, int H, int Hkv, int D, float scale, int causal, int window, void* stream);
+/* fp32 flash AttnLRP backward (same contract as lrp_attn_bwd_varlen; delta_ws fp32 [B,H,S]; lxt/efficient/patches.py:193-203) */
 int lrp_attn_bwd_f32(const float* q, const float* k, const float* v, int64_t ldq, int64_t ldk, int64_t ldv, const float* o,
                      const float* d_o, const float* lse, float* dq, float* dk, float* dv, int64_t lddq, int64_t lddk,
-                     int64_t lddv, float* delta_ws, int B, int S, int H, int Hkv, int D, float scale, int causal, int window,
-                     float q_div, float k_div, float v_div, void* stream);
+                     int64_t lddv, float* delta_ws, const int32_t* kv_range, int B, int S, int H, int Hkv, int D, float scale,
+                     int causal, int window, float q_div, float k_div, float v_div, void* stream);
 /* workspace query of lrp_attn_bwd (SURVEY.md 8(b) "a *_workspace_bytes query per op"): bytes of `dq_acc_ws` and `delta_ws` for this
  * shape; replaces the tensors autograd saves / allocates in the reference's SDPA backward (lxt/efficient/patches.py:193-203) */
 int lrp_attn_bwd_workspace_bytes(int B, int S, int H, int D, int64_t* dq_acc_bytes, int64_t* delta_bytes);

@@ -90,6 +90,8 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_const
   const int i_hi = p.window > 0 ? min(nq - 1, (k0 + ATT_TILE - 1 + p.window - 1) / QT) : nq - 1;
   const int ni = max(i_hi - i_lo + 1, 0);
   const int n_it = ni * G;
+  int kvlo, kvhi;
+  kv_bounds(p, b, kvlo, kvhi);
 
   if (warp == 8 && lane == 0) {
     tma_prefetch_desc(&tmq); tma_prefetch_desc(&tmk); tma_prefetch_desc(&tmv); tma_prefetch_desc(&tmdo);
@@ -190,8 +192,8 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_const
       // visible query columns for this key: lo <= c <= hi (tile-relative)
       int lo = p.causal ? key - q0 : 0;
       int hi = min(p.S - 1, p.window > 0 ? key + p.window - 1 : p.S - 1) - q0;
-      if (key >= p.S) { lo = 1; hi = 0; }
-      const bool need_mask = (p.causal && q0 < k0 + ATT_TILE - 1) || (q0 + QT > p.S) || (k0 + ATT_TILE > p.S) ||
+      if (key >= kvhi || key < kvlo) { lo = 1; hi = 0; }   // padded (or out-of-range) key: attended by nobody
+      const bool need_mask = (p.causal && q0 < k0 + ATT_TILE - 1) || (q0 + QT > p.S) || (k0 + ATT_TILE > kvhi) || (k0 < kvlo) ||
                              (p.window > 0 && q0 + QT - 1 - k0 >= p.window);
       const bool dbgt = p.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && it < 64 && sid == 0;
       if (dbgt) p.dbg[it * 16 + 8] = clock64();
@@ -307,6 +309,8 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constan
   const int j_hi = p.causal ? min((q0 + ATT_TILE - 1) / QT, nkv - 1) : nkv - 1;
   const int j_lo = p.window > 0 ? max(0, q0 - p.window + 1) / QT : 0;
   const int n = j_hi - j_lo + 1;
+  int kvlo, kvhi;
+  kv_bounds(p, b, kvlo, kvhi);
 
   if (warp == 8 && lane == 0) {
     tma_prefetch_desc(&tmq); tma_prefetch_desc(&tmk); tma_prefetch_desc(&tmv); tma_prefetch_desc(&tmdo);
@@ -391,9 +395,9 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constan
     for (int jj = 0; jj < n; ++jj) {
       const int kbase = (j_lo + jj) * QT, tb = jj & 1;
       int lo, hi;
-      row_window(qpos, kbase, p.S, p.causal, p.window, lo, hi);
+      row_window(qpos, kbase, kvlo, kvhi, p.causal, p.window, lo, hi);
       if (!row_ok) { lo = 1; hi = 0; }
-      const bool need_mask = (p.causal && kbase + QT - 1 > q0) || (kbase + QT > p.S) || (q0 + ATT_TILE > p.S) ||
+      const bool need_mask = (p.causal && kbase + QT - 1 > q0) || (kbase + QT > kvhi) || (kbase < kvlo) || (q0 + ATT_TILE > p.S) ||
                              (p.window > 0 && q0 + ATT_TILE - 1 - kbase >= p.window);
       mbar_wait(&st_full[tb], (jj >> 1) & 1);
       tc_fence_after();
@@ -497,8 +501,8 @@ static int launch_v2(const CUtensorMap& tq128, const CUtensorMap& tk128, const C
 // host entry used by lrp_attn_bwd (attn_lrp.cu)
 int attn_bwd_v2(const void* q, const void* k, const void* v, int64_t ldq, int64_t ldk, int64_t ldv, const void* d_o,
                 const float* lse, const float* delta, void* dq, void* dk, void* dv, int64_t lddq, int64_t lddk, int64_t lddv,
-                int B, int S, int H, int Hkv, int D, float scale, int causal, int window, float q_div, float k_div, float v_div,
-                cudaStream_t st) {
+                const int32_t* kv_range, int B, int S, int H, int Hkv, int D, float scale, int causal, int window, float q_div,
+                float k_div, float v_div, cudaStream_t st) {
   CUtensorMap tq128, tk128, tv128, tdo128, tq64, tk64, tv64, tdo64;
   const int64_t HD = int64_t(H) * D;
   struct { CUtensorMap* m; const void* ptr; uint64_t width; int64_t ld; uint32_t rows; } maps[] = {
@@ -520,6 +524,7 @@ int attn_bwd_v2(const void* q, const void* k, const void* v, int64_t ldq, int64_
   p.lddk = lddk; p.lddv = lddv;
   p.inv_k_div = k_div > 0.f ? 1.f / k_div : 0.f;
   p.inv_v_div = v_div > 0.f ? 1.f / v_div : 0.f;
+  p.kv_range = kv_range;
   static const bool want_dbg = getenv("LRP_ATTN_DEBUG") != nullptr;
   long long* dbg_dev = nullptr;
   if (want_dbg && B * S >= 4096) {

@@ -29,7 +29,19 @@ struct AttnParams {
   int64_t lddk, lddv;
   float inv_k_div, inv_v_div;
   long long* dbg;  // optional timeline buffer (debug builds of the pipeline analysis), NULL otherwise
+  // optional per-sequence range of VALID keys [kv_range[2b], kv_range[2b+1]) (left / right padding of a batch of prompts of
+  // different lengths): keys outside it are masked for every query.  NULL = all S keys valid.
+  const int* kv_range;
 };
+
+__device__ __forceinline__ void kv_bounds(const AttnParams& p, int b, int& kvlo, int& kvhi) {
+  kvlo = 0;
+  kvhi = p.S;
+  if (p.kv_range != nullptr) {
+    kvlo = max(0, p.kv_range[2 * b]);
+    kvhi = min(p.S, p.kv_range[2 * b + 1]);
+  }
+}
 
 __device__ __forceinline__ bool is_masked(int qpos, int kpos, int S, int causal, int window) {
   if (kpos >= S) return true;
@@ -46,10 +58,12 @@ __device__ __forceinline__ float ex2_approx(float x) {
 
 // Per-row column window [lo, hi] (tile-relative) of keys that are NOT masked:
 //   key (kbase + c) is visible iff lo <= c <= hi.
-__device__ __forceinline__ void row_window(int qpos, int kbase, int S, int causal, int window, int& lo, int& hi) {
-  hi = S - 1 - kbase;
+// kvlo / kvhi: range of valid keys of this sequence (0 / S without padding)
+__device__ __forceinline__ void row_window(int qpos, int kbase, int kvlo, int kvhi, int causal, int window, int& lo, int& hi) {
+  hi = kvhi - 1 - kbase;
   if (causal) hi = min(hi, qpos - kbase);
-  lo = window > 0 ? qpos - window + 1 - kbase : 0;
+  lo = kvlo - kbase;
+  if (window > 0) lo = max(lo, qpos - window + 1 - kbase);
 }
 
 template <bool MASK>

@@ -32,7 +32,7 @@ template <int E>
 __global__ void __launch_bounds__(F32_WARPS * 32)
 attn_f32_fwd_kernel(const float* __restrict__ q, const float* __restrict__ k, const float* __restrict__ v, int64_t ldq,
                     int64_t ldk, int64_t ldv, float* __restrict__ o, float* __restrict__ lse, int B, int S, int H, int Hkv,
-                    float scale, int causal, int window) {
+                    float scale, int causal, int window, const int* __restrict__ kv_range) {
   constexpr int D = E * 32;
   const int64_t row = blockIdx.x * int64_t(F32_WARPS) + (threadIdx.x >> 5);
   if (row >= int64_t(B) * H * S) return;
@@ -43,8 +43,9 @@ attn_f32_fwd_kernel(const float* __restrict__ q, const float* __restrict__ k, co
   float qv[E], acc[E];
 #pragma unroll
   for (int e = 0; e < E; ++e) { qv[e] = qr[lane + 32 * e]; acc[e] = 0.f; }
-  const int j_lo = window > 0 ? max(0, qi - window + 1) : 0;
-  const int j_hi = causal ? qi : S - 1;
+  const int kvlo = kv_range ? max(0, kv_range[2 * b]) : 0, kvhi = kv_range ? min(S, kv_range[2 * b + 1]) : S;
+  const int j_lo = max(kvlo, window > 0 ? max(0, qi - window + 1) : 0);
+  const int j_hi = min(kvhi - 1, causal ? qi : S - 1);
   float m = -INFINITY, l = 0.f;
   for (int j = j_lo; j <= j_hi; ++j) {
     const float* kr = k + (int64_t(b) * S + j) * ldk + hk * D;
@@ -74,7 +75,7 @@ __global__ void __launch_bounds__(F32_WARPS * 32)
 attn_f32_dq_kernel(const float* __restrict__ q, const float* __restrict__ k, const float* __restrict__ v, int64_t ldq,
                    int64_t ldk, int64_t ldv, const float* __restrict__ o, const float* __restrict__ d_o,
                    const float* __restrict__ lse, float* __restrict__ delta, float* __restrict__ dq, int64_t lddq, int B, int S,
-                   int H, int Hkv, float scale, int causal, int window, float inv_q_div) {
+                   int H, int Hkv, float scale, int causal, int window, float inv_q_div, const int* __restrict__ kv_range) {
   constexpr int D = E * 32;
   const int64_t row = blockIdx.x * int64_t(F32_WARPS) + (threadIdx.x >> 5);
   if (row >= int64_t(B) * H * S) return;
@@ -96,8 +97,9 @@ attn_f32_dq_kernel(const float* __restrict__ q, const float* __restrict__ k, con
   dl = wsum(dl);
   const float ls = lse[(int64_t(b) * H + h) * S + qi];
   if (lane == 0) delta[(int64_t(b) * H + h) * S + qi] = dl;
-  const int j_lo = window > 0 ? max(0, qi - window + 1) : 0;
-  const int j_hi = causal ? qi : S - 1;
+  const int kvlo = kv_range ? max(0, kv_range[2 * b]) : 0, kvhi = kv_range ? min(S, kv_range[2 * b + 1]) : S;
+  const int j_lo = max(kvlo, window > 0 ? max(0, qi - window + 1) : 0);
+  const int j_hi = min(kvhi - 1, causal ? qi : S - 1);
   if (ls != -INFINITY) {
     for (int j = j_lo; j <= j_hi; ++j) {
       const float* kr = k + (int64_t(b) * S + j) * ldk + hk * D;
@@ -126,7 +128,8 @@ __global__ void __launch_bounds__(F32_WARPS * 32)
 attn_f32_dkv_kernel(const float* __restrict__ q, const float* __restrict__ k, const float* __restrict__ v, int64_t ldq,
                     int64_t ldk, int64_t ldv, const float* __restrict__ d_o, const float* __restrict__ lse,
                     const float* __restrict__ delta, float* __restrict__ dk, float* __restrict__ dv, int64_t lddk, int64_t lddv,
-                    int B, int S, int H, int Hkv, float scale, int causal, int window, float inv_k_div, float inv_v_div) {
+                    int B, int S, int H, int Hkv, float scale, int causal, int window, float inv_k_div, float inv_v_div,
+                    const int* __restrict__ kv_range) {
   constexpr int D = E * 32;
   const int64_t row = blockIdx.x * int64_t(F32_WARPS) + (threadIdx.x >> 5);
   if (row >= int64_t(B) * Hkv * S) return;
@@ -138,8 +141,9 @@ attn_f32_dkv_kernel(const float* __restrict__ q, const float* __restrict__ k, co
   float kv[E], vv[E], ak[E], av[E];
 #pragma unroll
   for (int e = 0; e < E; ++e) { kv[e] = kr[lane + 32 * e]; vv[e] = vr[lane + 32 * e]; ak[e] = 0.f; av[e] = 0.f; }
+  const int kvlo = kv_range ? max(0, kv_range[2 * b]) : 0, kvhi = kv_range ? min(S, kv_range[2 * b + 1]) : S;
   const int i_lo = causal ? j : 0;
-  const int i_hi = window > 0 ? min(S - 1, j + window - 1) : S - 1;
+  const int i_hi = (j < kvlo || j >= kvhi) ? -1 : (window > 0 ? min(S - 1, j + window - 1) : S - 1);   // a padded key is attended by nobody
   for (int g = 0; g < G; ++g) {
     const int h = hk * G + g;
     for (int i = i_lo; i <= i_hi; ++i) {
@@ -188,12 +192,12 @@ using namespace lrp;
 extern "C" {
 
 int lrp_attn_fwd_f32(const float* q, const float* k, const float* v, int64_t ldq, int64_t ldk, int64_t ldv, float* o, float* lse,
-                     int B, int S, int H, int Hkv, int D, float scale, int causal, int window, void* stream) {
+                     const int32_t* kv_range, int B, int S, int H, int Hkv, int D, float scale, int causal, int window, void* stream) {
   if (int e = check_f32(B, S, H, Hkv, D)) return e;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int64_t rows = int64_t(B) * H * S;
   const unsigned grid = unsigned((rows + F32_WARPS - 1) / F32_WARPS);
-#define LRP_F32_FWD(E) attn_f32_fwd_kernel<E><<<grid, F32_WARPS * 32, 0, st>>>(q, k, v, ldq, ldk, ldv, o, lse, B, S, H, Hkv, scale, causal, window)
+#define LRP_F32_FWD(E) attn_f32_fwd_kernel<E><<<grid, F32_WARPS * 32, 0, st>>>(q, k, v, ldq, ldk, ldv, o, lse, B, S, H, Hkv, scale, causal, window, kv_range)
   if (D == 32) LRP_F32_FWD(1); else if (D == 64) LRP_F32_FWD(2); else if (D == 128) LRP_F32_FWD(4); else LRP_F32_FWD(8);
 #undef LRP_F32_FWD
   LRP_CHECK_LAUNCH();
@@ -202,8 +206,8 @@ int lrp_attn_fwd_f32(const float* q, const float* k, const float* v, int64_t ldq
 
 int lrp_attn_bwd_f32(const float* q, const float* k, const float* v, int64_t ldq, int64_t ldk, int64_t ldv, const float* o,
                      const float* d_o, const float* lse, float* dq, float* dk, float* dv, int64_t lddq, int64_t lddk,
-                     int64_t lddv, float* delta_ws, int B, int S, int H, int Hkv, int D, float scale, int causal, int window,
-                     float q_div, float k_div, float v_div, void* stream) {
+                     int64_t lddv, float* delta_ws, const int32_t* kv_range, int B, int S, int H, int Hkv, int D, float scale, int causal,
+                     int window, float q_div, float k_div, float v_div, void* stream) {
   if (int e = check_f32(B, S, H, Hkv, D)) return e;
   if (delta_ws == nullptr) return set_error(LRP_ERR_ARG, "attn_bwd_f32: missing delta workspace");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -213,9 +217,9 @@ int lrp_attn_bwd_f32(const float* q, const float* k, const float* v, int64_t ldq
 #define LRP_F32_BWD(E)                                                                                                          \
   do {                                                                                                                          \
     attn_f32_dq_kernel<E><<<g1, F32_WARPS * 32, 0, st>>>(q, k, v, ldq, ldk, ldv, o, d_o, lse, delta_ws, dq, lddq, B, S, H, Hkv,  \
-                                                          scale, causal, window, iq);                                           \
+                                                          scale, causal, window, iq, kv_range);                                         \
     attn_f32_dkv_kernel<E><<<g2, F32_WARPS * 32, 0, st>>>(q, k, v, ldq, ldk, ldv, d_o, lse, delta_ws, dk, dv, lddk, lddv, B, S,  \
-                                                           H, Hkv, scale, causal, window, ik, iv);                              \
+                                                           H, Hkv, scale, causal, window, ik, iv, kv_range);                    \
   } while (0)
   if (D == 32) LRP_F32_BWD(1); else if (D == 64) LRP_F32_BWD(2); else if (D == 128) LRP_F32_BWD(4); else LRP_F32_BWD(8);
 #undef LRP_F32_BWD

@@ -225,10 +225,12 @@ attn_fwd_ws_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constan
       if (n == 0) continue;
       const int q0i = it.q0 + i * ATT_TILE;
       const int qpos = q0i + r;
+      int kvlo, kvhi;
+      kv_bounds(p, it.b, kvlo, kvhi);
       float m_used = -INFINITY, l = 0.f;
       for (int j = 0; j < n; ++j) {
         const int k0 = j * ATT_TILE;
-        const bool need_mask = (p.causal && k0 + ATT_TILE - 1 > q0i) || (k0 + ATT_TILE > p.S);
+        const bool need_mask = (p.causal && k0 + ATT_TILE - 1 > q0i) || (k0 + ATT_TILE > kvhi) || (k0 < kvlo);
         mbar_wait(&s_full[i], s_cnt & 1);
         ++s_cnt;
         tc_fence_after();
@@ -237,13 +239,14 @@ attn_fwd_ws_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constan
         for (int c = 0; c < 4; ++c) tmem_ld32(tS + c * 32, s[c]);
         tmem_ld_wait();
         if (need_mask) {
-          int hi = p.S - 1 - k0;
+          int hi = kvhi - 1 - k0;
           if (p.causal) hi = min(hi, qpos - k0);
+          const int lo = kvlo - k0;
 #pragma unroll
           for (int c = 0; c < 4; ++c)
 #pragma unroll
             for (int e = 0; e < 32; ++e)
-              if (c * 32 + e > hi) s[c][e] = 0xff800000u;   // -inf
+              if (c * 32 + e > hi || c * 32 + e < lo) s[c][e] = 0xff800000u;   // -inf
         }
         float mx0 = __uint_as_float(s[0][0]), mx1 = __uint_as_float(s[0][1]);
 #pragma unroll
@@ -333,8 +336,8 @@ attn_fwd_ws_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constan
 }
 
 // host entry: head_dim 128, causal or full attention, no sliding window (the first-generation kernel handles the rest)
-int attn_fwd_ws(const void* q, const void* k, const void* v, int64_t ldq, int64_t ldk, int64_t ldv, void* o, float* lse, int B,
-                int S, int H, int Hkv, float scale, int causal, cudaStream_t st) {
+int attn_fwd_ws(const void* q, const void* k, const void* v, int64_t ldq, int64_t ldk, int64_t ldv, void* o, float* lse,
+                const int32_t* kv_range, int B, int S, int H, int Hkv, float scale, int causal, cudaStream_t st) {
   CUtensorMap tq, tk, tv, to;
   const int64_t HD = int64_t(H) * WS_D;
   if (int e = make_tmap_3d_bf16(&tq, q, uint64_t(HD), S, B, ldq, uint64_t(S) * ldq, 64, ATT_TILE)) return e;
@@ -348,6 +351,7 @@ int attn_fwd_ws(const void* q, const void* k, const void* v, int64_t ldq, int64_
   p.causal = causal; p.window = 0;
   p.o = reinterpret_cast<__nv_bfloat16*>(o);
   p.lse = lse;
+  p.kv_range = kv_range;
   static bool done = false;
   if (!done) {
     cudaError_t ce = cudaFuncSetAttribute(attn_fwd_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WS_SMEM_BYTES);

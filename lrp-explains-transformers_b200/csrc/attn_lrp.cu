@@ -55,6 +55,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__
   const int j_hi = p.causal ? min((q0 + ATT_TILE - 1) / BN, nkv - 1) : nkv - 1;
   const int j_lo = p.window > 0 ? max(0, q0 - p.window + 1) / BN : 0;
   const int n = j_hi - j_lo + 1;
+  int kvlo, kvhi;
+  kv_bounds(p, b, kvlo, kvhi);
 
   if (warp == 4 && lane == 0) {
     tma_prefetch_desc(&tmq); tma_prefetch_desc(&tmk); tma_prefetch_desc(&tmv);
@@ -112,12 +114,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__
     for (int jj = 0; jj < n; ++jj) {
       const int j = j_lo + jj;
       const int kbase = j * BN;
-      const bool need_mask = (p.causal && kbase + BN - 1 > q0) || (kbase + BN > p.S) ||
+      const bool need_mask = (p.causal && kbase + BN - 1 > q0) || (kbase + BN > kvhi) || (kbase < kvlo) ||
                              (p.window > 0 && q0 + ATT_TILE - 1 - kbase >= p.window);
       mbar_wait(s_full, jj & 1);
       tc_fence_after();
       int lo, hi;
-      row_window(qpos, kbase, p.S, p.causal, p.window, lo, hi);
+      row_window(qpos, kbase, kvlo, kvhi, p.causal, p.window, lo, hi);
       // pass 1: row maximum of the raw scores (scale > 0, so the order is preserved).  With 64-key tiles the row's 64
       // scores stay in registers for pass 2 (one TMEM read instead of two).
       float mx = -INFINITY;
@@ -257,6 +259,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__
   const int i_hi = p.window > 0 ? min(nq - 1, (k0 + ATT_TILE - 1 + p.window - 1) / ATT_TILE) : nq - 1;
   const int ni = i_hi - i_lo + 1;
   const int n_it = ni > 0 ? ni * G : 0;
+  int kvlo, kvhi;
+  kv_bounds(p, b, kvlo, kvhi);
 
   if (warp == 8 && lane == 0) {
     tma_prefetch_desc(&tmq); tma_prefetch_desc(&tmk); tma_prefetch_desc(&tmv); tma_prefetch_desc(&tmdo);
@@ -329,7 +333,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__
       }
       const bool row_ok = valid && lse2 != -INFINITY;
       if (!row_ok) lse2 = 0.f;
-      const bool need_mask = (p.causal && k0 + ATT_TILE - 1 > i * ATT_TILE) || (k0 + ATT_TILE > p.S) ||
+      const bool need_mask = (p.causal && k0 + ATT_TILE - 1 > i * ATT_TILE) || (k0 + ATT_TILE > kvhi) || (k0 < kvlo) ||
                              (p.window > 0 && i * ATT_TILE + ATT_TILE - 1 - k0 >= p.window);
       const bool dbgt = p.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && it < 64 && threadIdx.x == 0;
       if (dbgt) p.dbg[it * 16 + 8] = clock64();
@@ -337,7 +341,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__
       if (dbgt) p.dbg[it * 16 + 9] = clock64();
       tc_fence_after();
       int lo, hi;
-      row_window(qpos, k0, p.S, p.causal, p.window, lo, hi);
+      row_window(qpos, k0, kvlo, kvhi, p.causal, p.window, lo, hi);
       if (!row_ok) { lo = 1; hi = 0; }  // padded / fully masked query row: everything is masked
       const bool mask_tile = need_mask || !__all_sync(0xffffffffu, row_ok);
       const float delta_s = delta * p.scale;
@@ -467,6 +471,8 @@ attn_bwd_pipe_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_const
   const int ni = i_hi - i_lo + 1;
   const int n_it = ni > 0 ? ni * G : 0;
   const bool dbg_cta = p.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
+  int kvlo, kvhi;
+  kv_bounds(p, b, kvlo, kvhi);
 
   if (warp == 8 && lane == 0) {
     tma_prefetch_desc(&tmq); tma_prefetch_desc(&tmk); tma_prefetch_desc(&tmv); tma_prefetch_desc(&tmdo);
@@ -590,7 +596,7 @@ attn_bwd_pipe_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_const
       const float delta = delta_n;
       const bool row_ok = valid && lse2 != -INFINITY;
       if (!row_ok) lse2 = 0.f;
-      const bool need_mask = (p.causal && k0 + ATT_TILE - 1 > i * ATT_TILE) || (k0 + ATT_TILE > p.S) ||
+      const bool need_mask = (p.causal && k0 + ATT_TILE - 1 > i * ATT_TILE) || (k0 + ATT_TILE > kvhi) || (k0 < kvlo) ||
                              (p.window > 0 && i * ATT_TILE + ATT_TILE - 1 - k0 >= p.window);
       const bool dbgt = dbg_cta && it < 64 && threadIdx.x == 0;
       if (dbgt) p.dbg[it * 24 + 8] = clock64();
@@ -598,7 +604,7 @@ attn_bwd_pipe_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_const
       if (dbgt) p.dbg[it * 24 + 9] = clock64();
       tc_fence_after();
       int lo, hi;
-      row_window(qpos, k0, p.S, p.causal, p.window, lo, hi);
+      row_window(qpos, k0, kvlo, kvhi, p.causal, p.window, lo, hi);
       if (!row_ok) { lo = 1; hi = 0; }
       const bool mask_tile = need_mask || !__all_sync(0xffffffffu, row_ok);
       const float delta_s = delta * p.scale;
@@ -851,13 +857,19 @@ int lrp_attn_bwd_workspace_bytes(int B, int S, int H, int D, int64_t* dq_acc_byt
 
 int lrp_attn_fwd(const void* q, const void* k, const void* v, int64_t ldq, int64_t ldk, int64_t ldv, void* o, float* lse,
                  int B, int S, int H, int Hkv, int D, float scale, int causal, int window, void* stream) {
+  return lrp_attn_fwd_varlen(q, k, v, ldq, ldk, ldv, o, lse, nullptr, B, S, H, Hkv, D, scale, causal, window, stream);
+}
+
+int lrp_attn_fwd_varlen(const void* q, const void* k, const void* v, int64_t ldq, int64_t ldk, int64_t ldv, void* o, float* lse,
+                        const int32_t* kv_range, int B, int S, int H, int Hkv, int D, float scale, int causal, int window,
+                        void* stream) {
   if (int e = check_common(q, k, v, ldq, ldk, ldv, B, S, H, Hkv, D)) return e;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   {
     // head_dim 128 without a sliding window: the persistent two-tile kernel of attn_fwd_ws.cu (LRP_ATTN_FWD=v1 keeps the
     // first-generation kernel below for A/B measurements)
     static const bool v1 = getenv("LRP_ATTN_FWD") != nullptr && !strcmp(getenv("LRP_ATTN_FWD"), "v1");
-    if (D == 128 && window <= 0 && !v1) return attn_fwd_ws(q, k, v, ldq, ldk, ldv, o, lse, B, S, H, Hkv, scale, causal, st);
+    if (D == 128 && window <= 0 && !v1) return attn_fwd_ws(q, k, v, ldq, ldk, ldv, o, lse, kv_range, B, S, H, Hkv, scale, causal, st);
   }
   // key tile: 64 keys for D=128, 128 keys for D=64 -> 112 KiB of smem per CTA either way (2 CTAs per SM)
   const int BN = D == 64 ? 128 : 64;   // head_dim 256: 208 KiB, one CTA per SM, 320 TMEM columns
@@ -872,6 +884,7 @@ int lrp_attn_fwd(const void* q, const void* k, const void* v, int64_t ldq, int64
   p.causal = causal; p.window = window;
   p.o = reinterpret_cast<__nv_bfloat16*>(o);
   p.lse = lse;
+  p.kv_range = kv_range;
   return D == 256 ? launch_fwd<256, 64>(tq, tk, tv, p, st) : D == 128 ? launch_fwd<128, 64>(tq, tk, tv, p, st) : launch_fwd<64, 128>(tq, tk, tv, p, st);
 }
 
@@ -879,6 +892,14 @@ int lrp_attn_bwd(const void* q, const void* k, const void* v, int64_t ldq, int64
                  const void* d_o, const float* lse, void* dq, void* dk, void* dv, int64_t lddq, int64_t lddk, int64_t lddv,
                  float* dq_acc_ws, float* delta_ws, int B, int S, int H, int Hkv, int D, float scale, int causal, int window,
                  float q_div, float k_div, float v_div, void* stream) {
+  return lrp_attn_bwd_varlen(q, k, v, ldq, ldk, ldv, o, d_o, lse, dq, dk, dv, lddq, lddk, lddv, dq_acc_ws, delta_ws, nullptr, B, S, H,
+                             Hkv, D, scale, causal, window, q_div, k_div, v_div, stream);
+}
+
+int lrp_attn_bwd_varlen(const void* q, const void* k, const void* v, int64_t ldq, int64_t ldk, int64_t ldv, const void* o,
+                        const void* d_o, const float* lse, void* dq, void* dk, void* dv, int64_t lddq, int64_t lddk, int64_t lddv,
+                        float* dq_acc_ws, float* delta_ws, const int32_t* kv_range, int B, int S, int H, int Hkv, int D, float scale,
+                        int causal, int window, float q_div, float k_div, float v_div, void* stream) {
   if (int e = check_common(q, k, v, ldq, ldk, ldv, B, S, H, Hkv, D)) return e;
   if ((lddq % 8) || (lddk % 8) || (lddv % 8)) return set_error(LRP_ERR_ARG, "attn_bwd: gradient strides must be multiples of 8");
   if (dq_acc_ws == nullptr || delta_ws == nullptr) return set_error(LRP_ERR_ARG, "attn_bwd: missing workspace");
@@ -899,8 +920,8 @@ int lrp_attn_bwd(const void* q, const void* k, const void* v, int64_t ldq, int64
   // Measured on B200 it is on par with / slightly slower than this single-kernel version (its 64-wide MMAs are
   // smem-operand bound and S/dP/exp are recomputed for dQ), so the single kernel stays the default.
   if (two_pass)
-    return attn_bwd_v2(q, k, v, ldq, ldk, ldv, d_o, lse, delta_ws, dq, dk, dv, lddq, lddk, lddv, B, S, H, Hkv, D, scale, causal,
-                       window, q_div, k_div, v_div, st);
+    return attn_bwd_v2(q, k, v, ldq, ldk, ldv, d_o, lse, delta_ws, dq, dk, dv, lddq, lddk, lddv, kv_range, B, S, H, Hkv, D, scale,
+                       causal, window, q_div, k_div, v_div, st);
   AttnParams p;
   memset(&p, 0, sizeof(p));
   p.B = B; p.S = S; p.H = H; p.Hkv = Hkv; p.D = D;
@@ -914,6 +935,7 @@ int lrp_attn_bwd(const void* q, const void* k, const void* v, int64_t ldq, int64
   p.lddk = lddk; p.lddv = lddv;
   p.inv_k_div = k_div > 0.f ? 1.f / k_div : 0.f;
   p.inv_v_div = v_div > 0.f ? 1.f / v_div : 0.f;
+  p.kv_range = kv_range;
   long long* dbg_dev = nullptr;
   if (getenv("LRP_ATTN_DEBUG") != nullptr && int64_t(B) * S >= 4096) {
     cudaMalloc(&dbg_dev, 64 * 24 * sizeof(long long));

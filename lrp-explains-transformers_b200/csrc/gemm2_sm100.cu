@@ -156,13 +156,30 @@ gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_co
       const float rs = (p.rowscale != nullptr && row_ok) ? p.rowscale[m] * p.alpha : p.alpha;
       const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + acc * P_BN;
       const int64_t row_off = int64_t(m) * p.ldc;
+      if (p.act_out != nullptr) {
+        // gate|up forward with act(gate) * up fused: 64-column (gate block, up block) pairs
 #pragma unroll 1
-      for (int c = 0; c < P_BN / 32; ++c) {
-        uint32_t v[32];
-        tmem_ld32(taddr + c * 32, v);
-        tmem_ld_wait();
-        const int n0 = n_blk * P_BN + c * 32;
-        if (row_ok && n0 < p.N) gemm_epilogue_chunk(p, v, m, rs, row_off, n0);
+        for (int c = 0; c < P_BN / 64; ++c) {
+          uint32_t vg[32], vu[32];
+          tmem_ld32(taddr + c * 64, vg);
+          tmem_ld32(taddr + c * 64 + 32, vu);
+          tmem_ld_wait();
+          const int n0 = n_blk * P_BN + c * 64;
+          if (row_ok && n0 < p.N) {
+            gemm_epilogue_chunk(p, vg, m, rs, row_off, n0);
+            gemm_epilogue_chunk(p, vu, m, rs, row_off, n0 + 32);
+            gemm_epilogue_act_pair(p, vg, vu, m, rs, n0);
+          }
+        }
+      } else {
+#pragma unroll 1
+        for (int c = 0; c < P_BN / 32; ++c) {
+          uint32_t v[32];
+          tmem_ld32(taddr + c * 32, v);
+          tmem_ld_wait();
+          const int n0 = n_blk * P_BN + c * 32;
+          if (row_ok && n0 < p.N) gemm_epilogue_chunk(p, v, m, rs, row_off, n0);
+        }
       }
       tc_fence_before();
       __syncwarp();

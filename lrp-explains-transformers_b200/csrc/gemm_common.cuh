@@ -21,6 +21,7 @@ struct GemmParams {
   const __nv_bfloat16* gated_gu;
   __nv_bfloat16* gated_out;
   int gated_act, gated_cp;
+  __nv_bfloat16* act_out;   // fused gated-MLP forward: a[m, n/2] = act(gate) * up from 32-interleaved (gate | up) column blocks
   int group_m;  // rasterisation: `group_m` m-blocks share each streamed B panel through L2
 };
 
@@ -41,6 +42,28 @@ __device__ __forceinline__ void tile_coords(int t, int num_m, int num_n, int gro
   const int in_group = t - group * tiles_per_group;
   m_blk = first_m + in_group % gsize;
   n_blk = in_group / gsize;
+}
+
+// Fused gated-MLP forward (lxt/efficient/patches.py:145-157): the weight rows are interleaved in blocks of 32 (gate rows
+// 32k..32k+31, then up rows 32k..32k+31), so columns [n0, n0+32) of the accumulator are a gate block and [n0+32, n0+64) the
+// matching up block.  a = act(bf16(gate)) * bf16(up), i.e. exactly what lrp_gated_act_fwd computes from the stored bf16 gu.
+__device__ __forceinline__ void gemm_epilogue_act_pair(const GemmParams& p, const uint32_t (&vg)[32], const uint32_t (&vu)[32], int m,
+                                                       float rs, int n0) {
+  __nv_bfloat16* arow = p.act_out + int64_t(m) * (p.N >> 1) + (n0 >> 1);
+#pragma unroll
+  for (int j8 = 0; j8 < 4; ++j8) {
+    float a[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float g = __uint_as_float(vg[j8 * 8 + j]) * rs, u = __uint_as_float(vu[j8 * 8 + j]) * rs;
+      if (p.bias != nullptr) { g += p.bias[n0 + j8 * 8 + j]; u += p.bias[n0 + 32 + j8 * 8 + j]; }
+      g = __bfloat162float(__float2bfloat16_rn(g));
+      u = __bfloat162float(__float2bfloat16_rn(u));
+      a[j] = gemm_act_eval(g, p.gated_act) * u;
+    }
+    *reinterpret_cast<uint4*>(arow + j8 * 8) =
+        make_uint4(pack_bf16x2(a[0], a[1]), pack_bf16x2(a[2], a[3]), pack_bf16x2(a[4], a[5]), pack_bf16x2(a[6], a[7]));
+  }
 }
 
 // v[32] = fp32 accumulators of row m, columns [n0, n0+32); rs = alpha * rowscale[m]

@@ -157,13 +157,30 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
       const float rs = (p.rowscale != nullptr && row_ok) ? p.rowscale[m] * p.alpha : p.alpha;
       const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + acc * BN;
       const int64_t row_off = int64_t(m) * p.ldc;
+      if (p.act_out != nullptr) {
+        // gate|up forward with act(gate) * up fused: 64-column (gate block, up block) pairs
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        uint32_t v[32];
-        tmem_ld32(taddr + c * 32, v);
-        tmem_ld_wait();
-        const int n0 = n_blk * BN + c * 32;
-        if (row_ok && n0 < p.N) gemm_epilogue_chunk(p, v, m, rs, row_off, n0);
+        for (int c = 0; c < BN / 64; ++c) {
+          uint32_t vg[32], vu[32];
+          tmem_ld32(taddr + c * 64, vg);
+          tmem_ld32(taddr + c * 64 + 32, vu);
+          tmem_ld_wait();
+          const int n0 = n_blk * BN + c * 64;
+          if (row_ok && n0 < p.N) {
+            gemm_epilogue_chunk(p, vg, m, rs, row_off, n0);
+            gemm_epilogue_chunk(p, vu, m, rs, row_off, n0 + 32);
+            gemm_epilogue_act_pair(p, vg, vu, m, rs, n0);
+          }
+        }
+      } else {
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+          uint32_t v[32];
+          tmem_ld32(taddr + c * 32, v);
+          tmem_ld_wait();
+          const int n0 = n_blk * BN + c * 32;
+          if (row_ok && n0 < p.N) gemm_epilogue_chunk(p, v, m, rs, row_off, n0);
+        }
       }
       tc_fence_before();
       __syncwarp();
@@ -236,6 +253,12 @@ int gemm_bf16(const void* A, int64_t lda, const void* B, int64_t ldb, int b_layo
   p.gated_out = reinterpret_cast<__nv_bfloat16*>(epi->gated_out);
   p.gated_act = epi->gated_act;
   p.gated_cp = epi->gated_cp;
+  p.act_out = reinterpret_cast<__nv_bfloat16*>(epi->act_out);
+  if (p.act_out != nullptr) {
+    if ((N % 64) != 0 || epi->out == nullptr || epi->out_is_f32 || epi->gated_gu != nullptr || epi->gated_act < 0 || epi->gated_act > 2 ||
+        epi->colscale != nullptr || epi->resid_f32 != nullptr)
+      return set_error(LRP_ERR_ARG, "gemm: the fused gated forward needs a bf16 output, N % 64 == 0 and no colscale / resid term");
+  }
   bool group_forced = false;
   {
     // 16 m-blocks per group measured best on B200 across the Llama shapes (sweep 8/16/32/64 in

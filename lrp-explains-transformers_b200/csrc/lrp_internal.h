@@ -27,11 +27,11 @@ int gemm_bf16(const void* A, int64_t lda, const void* B, int64_t ldb, int b_layo
 
 int attn_bwd_v2(const void* q, const void* k, const void* v, int64_t ldq, int64_t ldk, int64_t ldv, const void* d_o,
                 const float* lse, const float* delta, void* dq, void* dk, void* dv, int64_t lddq, int64_t lddk, int64_t lddv,
-                int B, int S, int H, int Hkv, int D, float scale, int causal, int window, float q_div, float k_div, float v_div,
-                cudaStream_t st);
+                const int32_t* kv_range, int B, int S, int H, int Hkv, int D, float scale, int causal, int window, float q_div,
+                float k_div, float v_div, cudaStream_t st);
 
-int attn_fwd_ws(const void* q, const void* k, const void* v, int64_t ldq, int64_t ldk, int64_t ldv, void* o, float* lse, int B,
-                int S, int H, int Hkv, float scale, int causal, cudaStream_t st);
+int attn_fwd_ws(const void* q, const void* k, const void* v, int64_t ldq, int64_t ldk, int64_t ldv, void* o, float* lse,
+                const int32_t* kv_range, int B, int S, int H, int Hkv, float scale, int causal, cudaStream_t st);
 
 int linear_eps_bwd(const void* x, const void* W, const float* bias, const void* r_out, int r_is_f32, void* r_in,
                    void* s_ws, int32_t* flags_ws, int T, int N, int K, float eps, cudaStream_t stream);

@@ -305,9 +305,14 @@ __device__ __forceinline__ float act_eval(float x, int act) {
 }
 
 // a = bf16( act(gate) * up )
+// column of gate element c / distance to the matching up element in a [T, 2I] gate|up row:
+//   layout 0: halves (gate | up);  layout 1: blocks of 32 interleaved (32 gate, 32 up, ...) as the fused GEMM epilogue writes them
+__device__ __forceinline__ int gu_col(int c, int layout) { return layout ? ((c >> 5) << 6) + (c & 31) : c; }
+__device__ __forceinline__ int gu_up(int I, int layout) { return layout ? 32 : I; }
+
 template <typename TA>
 __global__ void __launch_bounds__(256) gated_act_fwd_kernel(const TA* __restrict__ gu,
-                                                            TA* __restrict__ a, int64_t T, int I, int act) {
+                                                            TA* __restrict__ a, int64_t T, int I, int act, int layout) {
   const int chunks = I >> 3;
   const int64_t total = T * chunks;
   for (int64_t idx = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; idx < total;
@@ -315,8 +320,8 @@ __global__ void __launch_bounds__(256) gated_act_fwd_kernel(const TA* __restrict
     const int64_t t = idx / chunks;
     const int c = int(idx - t * chunks) * 8;
     float g[8], u[8], o[8];
-    load8(gu + t * 2 * I + c, g);
-    load8(gu + t * 2 * I + I + c, u);
+    load8(gu + t * 2 * I + gu_col(c, layout), g);
+    load8(gu + t * 2 * I + gu_col(c, layout) + gu_up(I, layout), u);
 #pragma unroll
     for (int j = 0; j < 8; ++j) o[j] = act_eval(g[j], act) * u[j];
     store8(a + t * I + c, o);
@@ -331,7 +336,7 @@ template <typename TA>
 __global__ void __launch_bounds__(256) gated_act_bwd_kernel(const TA* __restrict__ ga,
                                                             const TA* __restrict__ gu,
                                                             TA* __restrict__ ggu, int64_t T, int I, int act,
-                                                            int cp_variant) {
+                                                            int cp_variant, int layout) {
   const int chunks = I >> 3;
   const int64_t total = T * chunks;
   for (int64_t idx = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; idx < total;
@@ -339,8 +344,10 @@ __global__ void __launch_bounds__(256) gated_act_bwd_kernel(const TA* __restrict
     const int64_t t = idx / chunks;
     const int c = int(idx - t * chunks) * 8;
     float g[8], u[8], d[8], og[8], ou[8];
-    load8(gu + t * 2 * I + c, g);
-    load8(gu + t * 2 * I + I + c, u);
+    const int64_t gc = t * 2 * I + gu_col(c, layout);
+    const int uo = gu_up(I, layout);
+    load8(gu + gc, g);
+    load8(gu + gc + uo, u);
     load8(ga + t * I + c, d);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -354,8 +361,8 @@ __global__ void __launch_bounds__(256) gated_act_bwd_kernel(const TA* __restrict
         og[j] = (s / (g[j] + 1e-10f)) * (gh * u[j]);
       }
     }
-    store8(ggu + t * 2 * I + c, og);
-    store8(ggu + t * 2 * I + I + c, ou);
+    store8(ggu + gc, og);
+    store8(ggu + gc + uo, ou);
   }
 }
 
@@ -683,36 +690,39 @@ int lrp_rope_inplace(void* qk, int64_t ld, int n_heads_total, int D, const float
   return lrp_rope_inplace_t(qk, 0, ld, n_heads_total, D, cos_t, sin_t, T, S, inverse, stream);
 }
 
-int lrp_gated_act_fwd_t(const void* gu, void* a, int is_f32, int T, int I, int act, void* stream) {
+int lrp_gated_act_fwd_t(const void* gu, void* a, int is_f32, int layout, int T, int I, int act, void* stream) {
   if (T <= 0 || I <= 0 || (I % 8) != 0) return set_error(LRP_ERR_ARG, "gated_act_fwd: I must be a positive multiple of 8");
   if (act < 0 || act > 2) return set_error(LRP_ERR_ARG, "gated_act_fwd: unknown activation");
+  if (layout != 0 && (layout != 1 || (I % 32) != 0)) return set_error(LRP_ERR_ARG, "gated_act_fwd: the interleaved layout needs I % 32 == 0");
   const int64_t total = int64_t(T) * (I / 8);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (is_f32) gated_act_fwd_kernel<float><<<grid_for(total, 256), 256, 0, st>>>((const float*)gu, (float*)a, T, I, act);
-  else gated_act_fwd_kernel<bf16><<<grid_for(total, 256), 256, 0, st>>>((const bf16*)gu, (bf16*)a, T, I, act);
+  if (is_f32) gated_act_fwd_kernel<float><<<grid_for(total, 256), 256, 0, st>>>((const float*)gu, (float*)a, T, I, act, layout);
+  else gated_act_fwd_kernel<bf16><<<grid_for(total, 256), 256, 0, st>>>((const bf16*)gu, (bf16*)a, T, I, act, layout);
   LRP_CHECK_LAUNCH();
   return LRP_OK;
 }
 
 int lrp_gated_act_fwd(const void* gu, void* a, int T, int I, int act, void* stream) {
-  return lrp_gated_act_fwd_t(gu, a, 0, T, I, act, stream);
+  return lrp_gated_act_fwd_t(gu, a, 0, 0, T, I, act, stream);
 }
 
-int lrp_gated_act_bwd_t(const void* ga, const void* gu, void* ggu, int is_f32, int T, int I, int act, int cp_variant, void* stream) {
+int lrp_gated_act_bwd_t(const void* ga, const void* gu, void* ggu, int is_f32, int layout, int T, int I, int act, int cp_variant,
+                        void* stream) {
   if (T <= 0 || I <= 0 || (I % 8) != 0) return set_error(LRP_ERR_ARG, "gated_act_bwd: I must be a positive multiple of 8");
   if (act < 0 || act > 2) return set_error(LRP_ERR_ARG, "gated_act_bwd: unknown activation");
+  if (layout != 0 && (layout != 1 || (I % 32) != 0)) return set_error(LRP_ERR_ARG, "gated_act_bwd: the interleaved layout needs I % 32 == 0");
   const int64_t total = int64_t(T) * (I / 8);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (is_f32)
-    gated_act_bwd_kernel<float><<<grid_for(total, 256), 256, 0, st>>>((const float*)ga, (const float*)gu, (float*)ggu, T, I, act, cp_variant);
+    gated_act_bwd_kernel<float><<<grid_for(total, 256), 256, 0, st>>>((const float*)ga, (const float*)gu, (float*)ggu, T, I, act, cp_variant, layout);
   else
-    gated_act_bwd_kernel<bf16><<<grid_for(total, 256), 256, 0, st>>>((const bf16*)ga, (const bf16*)gu, (bf16*)ggu, T, I, act, cp_variant);
+    gated_act_bwd_kernel<bf16><<<grid_for(total, 256), 256, 0, st>>>((const bf16*)ga, (const bf16*)gu, (bf16*)ggu, T, I, act, cp_variant, layout);
   LRP_CHECK_LAUNCH();
   return LRP_OK;
 }
 
 int lrp_gated_act_bwd(const void* ga, const void* gu, void* ggu, int T, int I, int act, int cp_variant, void* stream) {
-  return lrp_gated_act_bwd_t(ga, gu, ggu, 0, T, I, act, cp_variant, stream);
+  return lrp_gated_act_bwd_t(ga, gu, ggu, 0, 0, T, I, act, cp_variant, stream);
 }
 
 int lrp_split_bf16x2(const float* x, void* hi, void* lo, int64_t n, void* stream) {

@@ -34,6 +34,7 @@ class Epilogue(C.Structure):
         ("gated_out", C.c_void_p),
         ("gated_act", C.c_int32),
         ("gated_cp", C.c_int32),
+        ("act_out", C.c_void_p),
     ]
 
 
@@ -85,13 +86,19 @@ SIGNATURES = {
     "lrp_rmsnorm_fwd_residual_t": (_i, [_vp, _i, _vp, _f, _f, _vp, _vp, _i, _i, _vp]),
     "lrp_headnorm_inplace_t": (_i, [_vp, _i, _i64, _i, _i, _i, _vp, _vp, _f, _f, _vp, _i, _i, _vp]),
     "lrp_rope_inplace_t": (_i, [_vp, _i, _i64, _i, _i, _vp, _vp, _i, _i, _i, _vp]),
-    "lrp_gated_act_fwd_t": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
-    "lrp_gated_act_bwd_t": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    "lrp_gated_act_fwd_t": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    "lrp_gated_act_bwd_t": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "lrp_split_bf16x2": (_i, [_vp, _vp, _vp, _i64, _vp]),
-    "lrp_attn_fwd_f32": (_i, [_vp, _vp, _vp, _i64, _i64, _i64, _vp, _vp, _i, _i, _i, _i, _i, _f, _i, _i, _vp]),
+    "lrp_attn_fwd_f32": (_i, [_vp, _vp, _vp, _i64, _i64, _i64, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _i, _i, _vp]),
     "lrp_attn_bwd_f32": (
         _i,
-        [_vp, _vp, _vp, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _vp,
+        [_vp, _vp, _vp, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _vp, _vp,
+         _i, _i, _i, _i, _i, _f, _i, _i, _f, _f, _f, _vp],
+    ),
+    "lrp_attn_fwd_varlen": (_i, [_vp, _vp, _vp, _i64, _i64, _i64, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _i, _i, _vp]),
+    "lrp_attn_bwd_varlen": (
+        _i,
+        [_vp, _vp, _vp, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _vp, _vp, _vp,
          _i, _i, _i, _i, _i, _f, _i, _i, _f, _f, _f, _vp],
     ),
     "lrp_attn_bwd_workspace_bytes": (_i, [_i, _i, _i, _i, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),

@@ -64,8 +64,11 @@ def _as_2d(x: torch.Tensor) -> torch.Tensor:
 
 
 def _need_bf16_cuda(x: torch.Tensor, what: str) -> None:
-    if not (x.is_cuda and x.dtype == torch.bfloat16):
-        raise LrpError(f"{what}: the B200 path takes CUDA bfloat16 tensors (got {x.device}, {x.dtype}); no fallback exists")
+    """bf16 = production path; fp32 = validation precision (same kernels instantiated for fp32 activations, GEMMs as two-term
+    bf16 splits on the tcgen05 kernel, fp32 CUDA-core attention).  Anything else raises: there is no fallback."""
+    if not (x.is_cuda and x.dtype in (torch.bfloat16, torch.float32)):
+        raise LrpError(f"{what}: the B200 path takes CUDA bfloat16 (or fp32, validation precision) tensors (got {x.device}, {x.dtype}); "
+                       "no fallback exists")
 
 
 class _RMSNormIdentityFn(Function):
@@ -75,6 +78,15 @@ class _RMSNormIdentityFn(Function):
     def forward(ctx, x, weight, eps, w_offset):
         _need_bf16_cuda(x, "rms_norm_forward")
         x2 = _as_2d(x)
+        if x.dtype == torch.float32:
+            # validation precision: x_hat from the fp32 instantiation of the same kernel (zero weight, offset 1), then the fp32
+            # scale vector (w + w_offset) applied by the element-wise kernel — no rounding of an fp32 model's norm weights
+            wz = torch.zeros(x2.shape[1], dtype=torch.bfloat16, device=x.device)
+            xh, rstd = ops.rmsnorm_fwd(x2, wz, eps, w_offset=1.0, out_dtype=torch.float32)
+            wf = (weight.detach().float() + w_offset).contiguous()
+            ctx.save_for_backward(wz, rstd, wf)
+            ctx.w_offset = None
+            return ops.mul(xh, wf).view(x.shape)
         w = weight.detach().to(torch.bfloat16).contiguous()
         y, rstd = ops.rmsnorm_fwd(x2, w, eps, w_offset=w_offset)
         ctx.save_for_backward(w, rstd)
@@ -83,6 +95,10 @@ class _RMSNormIdentityFn(Function):
 
     @staticmethod
     def backward(ctx, gy):
+        if ctx.w_offset is None:
+            wz, rstd, wf = ctx.saved_tensors
+            g2 = ops.mul(_as_2d(gy), wf)
+            return ops.rmsnorm_bwd(g2, wz, rstd, w_offset=1.0, out_dtype=torch.float32).view(gy.shape), None, None, None
         w, rstd = ctx.saved_tensors
         gx = ops.rmsnorm_bwd(_as_2d(gy), w, rstd, w_offset=ctx.w_offset)
         return gx.view(gy.shape), None, None, None
@@ -115,7 +131,7 @@ class _LinearFn(Function):
         x2 = _as_2d(x)
         w = weight.detach()
         w = w if w.is_contiguous() else w.contiguous()
-        y = torch.empty((x2.shape[0], w.shape[0]), dtype=torch.bfloat16, device=x.device)
+        y = torch.empty((x2.shape[0], w.shape[0]), dtype=x.dtype, device=x.device)
         ops.linear_fwd(x2, w, y, bias=None if bias is None else bias.detach().float().contiguous())
         ctx.save_for_backward(w)
         return y.view(*x.shape[:-1], w.shape[0])
@@ -124,20 +140,24 @@ class _LinearFn(Function):
     def backward(ctx, gy):
         (w,) = ctx.saved_tensors
         g2 = _as_2d(gy)
-        gx = torch.empty((g2.shape[0], w.shape[1]), dtype=torch.bfloat16, device=gy.device)
+        gx = torch.empty((g2.shape[0], w.shape[1]), dtype=gy.dtype, device=gy.device)
         ops.linear_dgrad(g2, w, gx)
         return gx.view(*gy.shape[:-1], w.shape[1]), None, None
 
 
 def _linear_ok(x: torch.Tensor, weight: torch.Tensor) -> bool:
-    return (x.is_cuda and x.dtype == torch.bfloat16 and weight.dtype == torch.bfloat16 and weight.shape[0] % 8 == 0
-            and weight.shape[1] % 8 == 0)
+    """bf16 x bf16 (production) or fp32 x {fp32, bf16} (validation precision: split GEMM); feature counts multiples of 8"""
+    if not (x.is_cuda and weight.is_cuda and weight.shape[0] % 8 == 0 and weight.shape[1] % 8 == 0 and x.numel() > 0):
+        return False
+    if x.dtype == torch.bfloat16:
+        return weight.dtype == torch.bfloat16
+    return x.dtype == torch.float32 and weight.dtype in (torch.float32, torch.bfloat16)
 
 
 def _linear(mod, x):
     """run an nn.Linear through the B200 GEMM"""
     if not _linear_ok(x, mod.weight):
-        raise LrpError(f"linear: needs CUDA bf16 with in/out features multiples of 8 (got {x.dtype}, {tuple(mod.weight.shape)})")
+        raise LrpError(f"linear: needs CUDA bf16 (or fp32) with in/out features multiples of 8 (got {x.dtype}, {tuple(mod.weight.shape)})")
     return _LinearFn.apply(x, mod.weight, mod.bias)
 
 
@@ -151,11 +171,11 @@ class _GatedMLPFn(Function):
         T, I = x2.shape[0], wg.shape[0]
         wg, wu, wd = (w.detach().contiguous() for w in (wg, wu, wd))
         f32 = lambda b: None if b is None else b.detach().float().contiguous()
-        gu = torch.empty((T, 2 * I), dtype=torch.bfloat16, device=x.device)
+        gu = torch.empty((T, 2 * I), dtype=x.dtype, device=x.device)
         ops.linear_fwd(x2, wg, gu[:, :I], bias=f32(bg))
         ops.linear_fwd(x2, wu, gu[:, I:], bias=f32(bu))
         a = ops.gated_act_fwd(gu, act)
-        y = torch.empty((T, wd.shape[0]), dtype=torch.bfloat16, device=x.device)
+        y = torch.empty((T, wd.shape[0]), dtype=x.dtype, device=x.device)
         ops.linear_fwd(a, wd, y, bias=f32(bd))
         ctx.save_for_backward(gu, wg, wu, wd)
         ctx.act, ctx.cp = act, cp
@@ -166,13 +186,17 @@ class _GatedMLPFn(Function):
         gu, wg, wu, wd = ctx.saved_tensors
         T, I = gu.shape[0], wg.shape[0]
         g2 = _as_2d(gy)
-        ga = torch.empty((T, I), dtype=torch.bfloat16, device=gy.device)
+        ga = torch.empty((T, I), dtype=gu.dtype, device=gy.device)
         ops.linear_dgrad(g2, wd, ga)
         ggu = ops.gated_act_bwd(ga, gu, ctx.act, cp=ctx.cp)
         acc = torch.empty((T, wg.shape[1]), dtype=torch.float32, device=gy.device)
         ops.linear_dgrad(ggu[:, :I], wg, acc)
-        gx = torch.empty((T, wg.shape[1]), dtype=torch.bfloat16, device=gy.device)
-        ops.linear_dgrad(ggu[:, I:], wu, acc, resid=acc, shadow=gx)
+        if gu.dtype == torch.float32:   # validation precision: the fp32 accumulator is the result
+            ops.linear_dgrad(ggu[:, I:], wu, acc, resid=acc)
+            gx = acc
+        else:
+            gx = torch.empty((T, wg.shape[1]), dtype=torch.bfloat16, device=gy.device)
+            ops.linear_dgrad(ggu[:, I:], wu, acc, resid=acc, shadow=gx)
         return gx.view(*gy.shape[:-1], wg.shape[1]), None, None, None, None, None, None, None, None
 
 
@@ -180,12 +204,13 @@ class _FlashAttnLRPFn(Function):
     """soft-max attention with the AttnLRP backward (dQ/q_div, dK/k_div, dV/v_div); q,k,v in HF layout [B,H,S,D]."""
 
     @staticmethod
-    def forward(ctx, q, k, v, scale, causal, window, q_div, k_div, v_div):
+    def forward(ctx, q, k, v, scale, causal, window, q_div, k_div, v_div, kv_range=None):
         for t, n in ((q, "query"), (k, "key"), (v, "value")):
             _need_bf16_cuda(t, f"attention {n}")
         qs, ks, vs = (t.transpose(1, 2).contiguous() for t in (q, k, v))  # [B,S,H,D]; no copy if already so in memory
-        o, lse = ops.attn_fwd(qs, ks, vs, scale, causal=causal, window=window)
+        o, lse = ops.attn_fwd(qs, ks, vs, scale, causal=causal, window=window, kv_range=kv_range)
         ctx.save_for_backward(qs, ks, vs, o, lse)
+        ctx.kv_range = kv_range
         ctx.cfg = (scale, causal, window, q_div, k_div, v_div)
         return o  # [B,S,H,D] — what HF attention functions return after their transpose(1,2).contiguous()
 
@@ -194,8 +219,8 @@ class _FlashAttnLRPFn(Function):
         qs, ks, vs, o, lse = ctx.saved_tensors
         scale, causal, window, q_div, k_div, v_div = ctx.cfg
         dq, dk, dv = ops.attn_bwd(qs, ks, vs, o, d_o.contiguous(), lse, scale, causal=causal, window=window, q_div=q_div,
-                                  k_div=k_div, v_div=v_div)
-        return dq.transpose(1, 2), dk.transpose(1, 2), dv.transpose(1, 2), None, None, None, None, None, None
+                                  k_div=k_div, v_div=v_div, kv_range=ctx.kv_range)
+        return dq.transpose(1, 2), dk.transpose(1, 2), dv.transpose(1, 2), None, None, None, None, None, None, None
 
 
 class _PackedSelfAttnFn(Function):
@@ -226,41 +251,79 @@ class _PackedSelfAttnFn(Function):
         return g, None, None, None, None, None, None, None
 
 
-def _check_mask_is_causal(mask, S, window):
-    """Only plain (optionally sliding-window) causal attention exists on the B200 path; padding masks raise."""
-    if mask is None:
-        return
-    if mask.dim() != 4 or mask.shape[-1] != S or mask.shape[-2] != S:
-        raise LrpError(f"attention_mask of shape {tuple(mask.shape)} is not supported (causal self-attention only)")
-    i = torch.arange(S, device=mask.device)
-    allowed = i[None, :] <= i[:, None]
-    if window:
-        allowed &= (i[:, None] - i[None, :]) < window
-    got = mask if mask.dtype == torch.bool else (mask == 0)
-    if not bool((got == allowed).all()):
-        raise LrpError("attention_mask is not a plain causal mask (padding / custom masks are not supported)")
+_KV_RANGE_CACHE = {}
+
+
+def _kv_range_from_mask(mask, B, S, causal, window):
+    """HF hands every attention layer the same 4-D mask `[B or 1, 1, S, S]` (bool: True = attend; float: 0 = attend): causal
+    (+ sliding window) AND the 2-D key-padding mask of the batch (transformers masking_utils.sdpa_mask / eager_mask).  The
+    kernels take the causal / window part from flags and the padding part as one valid-key range per sequence, so the mask
+    is reduced ON THE DEVICE (no host synchronisation) to `kv_range[b] = [first valid key, last valid key + 1)`: key j is
+    valid iff some query attends to it.  The result is cached per mask tensor (the same object serves all layers).
+    LRP_VERIFY_MASKS=1 re-expands the range and compares it with the mask (one host sync; raises on custom masks)."""
+    if mask.dim() != 4 or mask.shape[-1] != S or mask.shape[-2] != S or mask.shape[1] != 1 or mask.shape[0] not in (1, B):
+        raise LrpError(f"attention_mask of shape {tuple(mask.shape)} is not supported (expected [B,1,S,S] with S = {S})")
+    key = (mask.data_ptr(), tuple(mask.shape), mask.dtype, mask._version, bool(causal), int(window))
+    hit = _KV_RANGE_CACHE.get(key)
+    if hit is not None:
+        return hit
+    allowed = mask[:, 0] if mask.dtype == torch.bool else (mask[:, 0] == 0)
+    valid = allowed.any(dim=-2)                                   # [B or 1, S]
+    idx = torch.arange(S, device=mask.device)
+    lo = torch.where(valid, idx, S).amin(-1)
+    hi = torch.where(valid, idx + 1, 0).amax(-1)
+    kv_range = torch.stack([lo, hi], -1).to(torch.int32).expand(B, 2).contiguous()
+    import os
+    if os.environ.get("LRP_VERIFY_MASKS", "0") == "1":
+        i = idx
+        exp = (i[None, None, :] >= kv_range[:, 0, None, None]) & (i[None, None, :] < kv_range[:, 1, None, None])
+        if causal:
+            exp = exp & (i[None, None, :] <= i[None, :, None])
+        if window:
+            exp = exp & ((i[None, :, None] - i[None, None, :]) < window)
+        got = allowed.expand(B, S, S)
+        # rows that attend to nothing (padding queries) are don't-cares
+        live = exp.any(-1, keepdim=True)
+        if not bool(((got == exp) | ~live).all()):
+            raise LrpError("attention_mask is not causal(+window) x contiguous key padding; custom masks are not supported")
+    if len(_KV_RANGE_CACHE) > 8:
+        _KV_RANGE_CACHE.clear()
+    _KV_RANGE_CACHE[key] = kv_range
+    return kv_range
+
+
+def _attention_scale(module, query, kwargs):
+    """soft-max scale exactly as the wrapped HF function would use it: the `scaling` kwarg, else `module.scaling`, else
+    head_dim^-0.5; GPT-2's non-default scaling switches are refused rather than silently dropped."""
+    scaling = kwargs.get("scaling")
+    if scaling is None:
+        scaling = getattr(module, "scaling", None)
+    if scaling is None:
+        if getattr(module, "scale_attn_weights", True) is False or getattr(module, "scale_attn_by_inverse_layer_idx", False):
+            raise LrpError("attention: GPT-2 scale_attn_weights=False / scale_attn_by_inverse_layer_idx are not supported")
+        scaling = 1.0 / math.sqrt(query.shape[-1])
+    return float(scaling)
 
 
 def _lrp_attention(module, query, key, value, args, kwargs, q_div, k_div, v_div):
     mask = args[0] if len(args) > 0 else kwargs.get("attention_mask")
-    scaling = kwargs.get("scaling")
-    if scaling is None:
-        scaling = args[2] if len(args) > 2 else 1.0 / math.sqrt(query.shape[-1])
     if kwargs.get("softcap") is not None:
         raise LrpError("attention softcap is not supported by the B200 AttnLRP kernel")
+    if kwargs.get("head_mask") is not None:
+        raise LrpError("attention head_mask is not supported by the B200 AttnLRP kernel")
     window = kwargs.get("sliding_window") or 0
     is_causal = kwargs.get("is_causal")
     if is_causal is None:
         is_causal = getattr(module, "is_causal", True)
-    S = query.shape[2]
+    B, _, S, _ = query.shape
     if key.shape[2] != S:
         raise LrpError("AttnLRP needs full-sequence self-attention (use_cache=False)")
-    if is_causal or mask is not None:
-        _check_mask_is_causal(mask, S, window)
-        causal = True
-    else:
-        causal = False
-    out = _FlashAttnLRPFn.apply(query, key, value, float(scaling), bool(causal), int(window), q_div, k_div, v_div)
+    causal = bool(is_causal)
+    if window and not causal:
+        raise LrpError("a sliding window without causal attention is not supported by the B200 AttnLRP kernel")
+    kv_range = None if mask is None else _kv_range_from_mask(mask, B, S, causal, int(window))
+    out = _FlashAttnLRPFn.apply(query, key, value, _attention_scale(module, query, kwargs), causal, int(window), q_div, k_div, v_div,
+                                kv_range)
     return out, None
 
 
@@ -394,7 +457,8 @@ def b200_cp_multi_head_attention_forward(self, query, key, value, *args, **kwarg
     E, H = self.embed_dim, self.num_heads
     D = E // H
     plain = (query is key and key is value and query.dim() == 3 and self.batch_first and self._qkv_same_embed_dim
-             and self.in_proj_weight is not None and query.is_cuda and query.dtype == torch.bfloat16 and D in (64, 128)
+             and self.in_proj_weight is not None and query.is_cuda and query.dtype in (torch.bfloat16, torch.float32) and D in (64, 128)
+             and query.dtype == self.in_proj_weight.dtype and kwargs.get("need_weights", True) is False
              and kwargs.get("attn_mask") is None and kwargs.get("key_padding_mask") is None and not kwargs.get("is_causal", False)
              and len(args) == 0 and self.bias_k is None and not self.add_zero_attn and (self.dropout == 0.0 or not self.training))
     if not plain:

@@ -98,7 +98,7 @@ class LlamaAttnLRPEngine:
     """B200-native AttnLRP engine.  Construct with `from_weights`, `from_hf` or `random_init`."""
 
     def __init__(self, dims: LlamaDims, device: torch.device, weights: Dict, micro_batch: int = 8, store: str = "all",
-                 rule: str = "attnlrp", cuda_graph: bool = False, precision: str = "bf16"):
+                 rule: str = "attnlrp", cuda_graph: bool = False, precision: str = "bf16", rope: Optional[Sequence] = None):
         if device.type != "cuda":
             raise RuntimeError("LlamaAttnLRPEngine runs on a CUDA (B200) device only; there is no CPU path")
         ops._capi.require_device()
@@ -117,7 +117,13 @@ class LlamaAttnLRPEngine:
         import os
         # fusing the gated-MLP backward rules into the down-dgrad epilogue was measured SLOWER on B200 (16.2 vs 16.9
         # attributions/s: the exp/div epilogue outlasts the K=4096 mainloop), so it is opt-in
-        self.fuse_gated = os.environ.get("LRP_FUSE_GATED", "0") == "1" and not self.hp
+        # gate|up layout: the weight rows (hence the columns of gu / g_gu) are interleaved in blocks of 32 (32 gate, 32 up) when I
+        # allows it, so that one 64-column slab of the gate|up GEMM accumulator holds matching gate and up values and the
+        # epilogue can emit a = act(gate) * up itself (no separate point-wise pass over [T, 2I]).  LRP_FUSE_ACT=0 keeps the
+        # separate kernel (A/B); the validation mode always uses the separate fp32 kernel on the same layout.
+        self.gu_layout = 1 if dims.I % 32 == 0 else 0
+        self.fuse_act = self.gu_layout == 1 and not self.hp and os.environ.get("LRP_FUSE_ACT", "1") == "1"
+        self.fuse_gated = os.environ.get("LRP_FUSE_GATED", "0") == "1" and not self.hp and self.gu_layout == 0
         bf = lambda t: t.to(device=device, dtype=torch.bfloat16).contiguous()
         f32 = lambda t: t.to(device=device, dtype=torch.float32).contiguous()
         self.emb = bf(weights["emb"])
@@ -126,7 +132,7 @@ class LlamaAttnLRPEngine:
         self.layers: List[Dict[str, torch.Tensor]] = []
         for lw in weights["layers"]:
             wqkv = torch.cat([lw["wq"], lw["wk"], lw["wv"]], dim=0)
-            wgu = torch.cat([lw["wg"], lw["wu"]], dim=0)
+            wgu = self._pack_gu(lw["wg"], lw["wu"])
             ln2 = lw["ln_pre_ff"] if dims.post_norms else lw["ln2"]
             layer = dict(wqkv=bf(wqkv), wo=bf(lw["wo"]), wgu=bf(wgu), wd=bf(lw["wd"]), ln1=bf(lw["ln1"]), ln2=bf(ln2),
                          ln1_f=f32(bf(lw["ln1"])) + dims.norm_offset, ln2_f=f32(bf(ln2)) + dims.norm_offset)
@@ -140,10 +146,61 @@ class LlamaAttnLRPEngine:
         self._ws_key = None
         self._ws = None
         self._rope_cache = {}
+        # RoPE per layer as (inv_freq fp32 [D/2], attention_scaling): the default is theta^(-2i/D) (transformers
+        # modeling_llama.py LlamaRotaryEmbedding.compute_default_rope_parameters); `from_hf` passes the model's own tables so
+        # that scaled RoPE variants (llama3, linear, yarn: static inv_freq + a cos/sin factor) are reproduced exactly.
+        if rope is None:
+            rope = []
+            for l in range(dims.L):
+                th = dims.layer_theta(l)
+                rope.append((1.0 / (th ** (torch.arange(0, dims.D, 2, dtype=torch.int64).float() / dims.D)), 1.0))
+        if len(rope) != dims.L:
+            raise ValueError("rope: one (inv_freq, attention_scaling) pair per layer expected")
+        self._rope_spec, self._rope_id, uniq = [], [], {}
+        for inv_freq, att in rope:
+            inv_freq = torch.as_tensor(inv_freq, dtype=torch.float32).detach().cpu().contiguous()
+            if inv_freq.numel() != dims.D // 2:
+                raise ValueError(f"rope: inv_freq must have head_dim/2 = {dims.D // 2} entries")
+            key = (inv_freq.numpy().tobytes(), float(att))
+            if key not in uniq:
+                uniq[key] = len(self._rope_spec)
+                self._rope_spec.append((inv_freq, float(att)))
+            self._rope_id.append(uniq[key])
         # cuda_graph=True captures the whole attribution (≈20 launches per layer) of a given [B,S] once and replays it:
         # small / latency-bound shapes (e.g. TinyLlama, B=1, S=512) stop being bound by host launch overhead.
         self.cuda_graph = cuda_graph
         self._graphs = {}
+        self._graph_ws = {}   # [B,S] -> workspace owned by the captured graph of that shape
+
+    def _pack_gu(self, wg, wu):
+        if self.gu_layout == 0:
+            return torch.cat([wg, wu], dim=0)
+        I, d = wg.shape
+        return torch.stack([wg.reshape(I // 32, 32, d), wu.reshape(I // 32, 32, d)], dim=1).reshape(2 * I, d)
+
+    def export_weights(self) -> Dict:
+        """the weights in the `from_weights` format (packed projections split / de-interleaved again)"""
+        m = self.dims
+        out = dict(emb=self.emb, norm=self.norm_w, lm_head=self.lm_head, layers=[])
+        for lw in self.layers:
+            wq, wk, wv = lw["wqkv"].split([m.H * m.D, m.Hkv * m.D, m.Hkv * m.D], 0)
+            if self.gu_layout == 0:
+                wg, wu = lw["wgu"].split([m.I, m.I], 0)
+            else:
+                blk = lw["wgu"].view(m.I // 32, 2, 32, m.d)
+                wg, wu = blk[:, 0].reshape(m.I, m.d), blk[:, 1].reshape(m.I, m.d)
+            e = dict(wq=wq, wk=wk, wv=wv, wo=lw["wo"], wg=wg, wu=wu, wd=lw["wd"], ln1=lw["ln1"])
+            if m.post_norms:
+                e.update(ln_pre_ff=lw["ln2"], ln_post_attn=lw["ln_post_attn"], ln_post_ff=lw["ln_post_ff"])
+            else:
+                e["ln2"] = lw["ln2"]
+            if m.qk_norm:
+                e.update(qn=lw["qn"], kn=lw["kn"])
+            if "bqkv" in lw:
+                bq, bk, bv = lw["bqkv"].split([m.H * m.D, m.Hkv * m.D, m.Hkv * m.D], 0)
+                e.update(bq=bq, bk=bk, bv=bv)
+            out["layers"].append(e)
+        return out
 
     # ------------------------------------------------------------------ constructors
     @classmethod
@@ -172,6 +229,7 @@ class LlamaAttnLRPEngine:
             raise ValueError(f"LlamaAttnLRPEngine.from_hf: unsupported model_type {mt!r} (use the drop-in monkey_patch API)")
         dims = LlamaDims(d=c.hidden_size, I=c.intermediate_size, H=c.num_attention_heads, Hkv=c.num_key_value_heads, D=D,
                          L=c.num_hidden_layers, V=c.vocab_size, eps=c.rms_norm_eps, theta=float(theta), **extra)
+        kw.setdefault("rope", cls._rope_from_hf(model, dims))
         sd = model.state_dict()
         has_bias = any(k.endswith("self_attn.q_proj.bias") for k in sd)
         if any(k.endswith(("o_proj.bias", "gate_proj.bias", "up_proj.bias", "down_proj.bias")) for k in sd):
@@ -195,6 +253,29 @@ class LlamaAttnLRPEngine:
                 lw.update(ln2=sd[p + "post_attention_layernorm.weight"])
             w["layers"].append(lw)
         return cls(dims, torch.device(device), w, **kw)
+
+    @staticmethod
+    def _rope_from_hf(model, dims: LlamaDims):
+        """Per-layer (inv_freq, attention_scaling) exactly as the HF model's rotary module holds them (rope_type default, linear,
+        llama3, yarn: `ROPE_INIT_FUNCTIONS`, transformers modeling_rope_utils.py).  Types whose tables depend on the sequence
+        length at run time (dynamic NTK, longrope) are refused: the engine would silently compute something else."""
+        c = model.config
+        rot = getattr(getattr(model, "model", model), "rotary_emb", None)
+        if rot is None:
+            raise ValueError("from_hf: the model has no `model.rotary_emb` module to take the RoPE tables from")
+        kinds = getattr(rot, "rope_type", "default")
+        layer_types = list(getattr(c, "layer_types", None) or [None] * dims.L)
+        out = []
+        for l in range(dims.L):
+            lt = layer_types[l] if isinstance(kinds, dict) else None
+            kind = kinds[lt] if isinstance(kinds, dict) else kinds
+            if kind in ("dynamic", "longrope"):
+                raise ValueError(f"from_hf: rope_type {kind!r} changes its tables with the sequence length; not supported by the fused "
+                                 "engine (use the drop-in monkey_patch API)")
+            inv = getattr(rot, f"{lt}_inv_freq" if lt is not None else "inv_freq")
+            att = getattr(rot, f"{lt}_attention_scaling" if lt is not None else "attention_scaling", 1.0)
+            out.append((inv.detach().float().cpu(), float(att)))
+        return out
 
     @classmethod
     def random_init(cls, dims: LlamaDims, device="cuda", seed: int = 0, std: float = 0.02, **kw):
@@ -226,9 +307,11 @@ class LlamaAttnLRPEngine:
 
     def _workspace(self, B: int, S: int):
         key = (B, S)
+        if key in self._graph_ws:       # a captured CUDA graph replays on these buffers: they are never freed or re-keyed
+            return self._graph_ws[key]
         if self._ws_key == key:
             return self._ws
-        self._ws = None  # release the previous workspace before allocating the new one
+        self._ws = None  # release the previous (un-graphed) workspace before allocating the new one
         m, dev = self.dims, self.device
         T = B * S
         e = lambda *s, dt=self.adt: torch.empty(*s, dtype=dt, device=dev)
@@ -268,13 +351,11 @@ class LlamaAttnLRPEngine:
         return max(1, int(math.ceil(math.sqrt(self.dims.L))))
 
     def _rope(self, S: int, l: int = 0):
-        theta = self.dims.layer_theta(l)
-        key = (S, theta)
+        key = (S, self._rope_id[l])
         if key not in self._rope_cache:
-            m = self.dims
-            inv_freq = 1.0 / (theta ** (torch.arange(0, m.D, 2, dtype=torch.int64).float() / m.D))
+            inv_freq, att = self._rope_spec[self._rope_id[l]]
             fr = torch.outer(torch.arange(S, dtype=torch.float32), inv_freq)
-            self._rope_cache[key] = (fr.cos().to(self.device).contiguous(), fr.sin().to(self.device).contiguous())
+            self._rope_cache[key] = ((fr.cos() * att).to(self.device).contiguous(), (fr.sin() * att).to(self.device).contiguous())
         return self._rope_cache[key]
 
     # ------------------------------------------------------------------ one layer
@@ -296,7 +377,7 @@ class LlamaAttnLRPEngine:
         q, k, v = self._qkv_views(st.qkv, B, S)
         if self.hp:
             C.check(lib.lrp_attn_fwd_f32(q.data_ptr(), k.data_ptr(), v.data_ptr(), m.qkv_width, m.qkv_width, m.qkv_width,
-                                         st.o.data_ptr(), st.lse.data_ptr(), B, S, m.H, m.Hkv, m.D, scale, 1, win, ops._stream()),
+                                         st.o.data_ptr(), st.lse.data_ptr(), None, B, S, m.H, m.Hkv, m.D, scale, 1, win, ops._stream()),
                     "attn_fwd_f32")
         else:
             C.check(lib.lrp_attn_fwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), m.qkv_width, m.qkv_width, m.qkv_width,
@@ -309,8 +390,12 @@ class LlamaAttnLRPEngine:
             ops.linear_fwd(st.o, lw["wo"], h, resid=h)
         C.check(lib.lrp_rmsnorm_fwd_t(h.data_ptr(), 1, lw["ln2"].data_ptr(), off, m.eps, ws["xn"].data_ptr(), f, st.rstd2.data_ptr(),
                                       T, m.d, ops._stream()), "rmsnorm_fwd")
-        ops.linear_fwd(ws["xn"], lw["wgu"], st.gu)
-        C.check(lib.lrp_gated_act_fwd_t(st.gu.data_ptr(), ws["a"].data_ptr(), f, T, m.I, m.act_code, ops._stream()), "gated_act_fwd")
+        if self.fuse_act:   # a = act(gate) * up leaves the gate|up GEMM's epilogue together with gu
+            ops.linear_fwd(ws["xn"], lw["wgu"], st.gu, act_out=ws["a"], act=m.act_code)
+        else:
+            ops.linear_fwd(ws["xn"], lw["wgu"], st.gu)
+            C.check(lib.lrp_gated_act_fwd_t(st.gu.data_ptr(), ws["a"].data_ptr(), f, self.gu_layout, T, m.I, m.act_code, ops._stream()),
+                    "gated_act_fwd")
         if m.post_norms:
             ops.linear_fwd(ws["a"], lw["wd"], ws["y"])
             C.check(lib.lrp_rmsnorm_fwd_residual_t(ws["y"].data_ptr(), f, lw["ln_post_ff"].data_ptr(), off, m.eps, h.data_ptr(),
@@ -337,8 +422,8 @@ class LlamaAttnLRPEngine:
             ops.linear_dgrad_gated_bwd(src, lw["wd"], st.gu, ws["g_gu"], m.act_code, self.cp)
         else:
             ops.linear_dgrad(src, lw["wd"], ws["a"])                               # g_a [T, I]
-            C.check(lib.lrp_gated_act_bwd_t(ws["a"].data_ptr(), st.gu.data_ptr(), ws["g_gu"].data_ptr(), f, T, m.I, m.act_code,
-                                            int(self.cp), ops._stream()), "gated_act_bwd")
+            C.check(lib.lrp_gated_act_bwd_t(ws["a"].data_ptr(), st.gu.data_ptr(), ws["g_gu"].data_ptr(), f, self.gu_layout, T, m.I,
+                                            m.act_code, int(self.cp), ops._stream()), "gated_act_bwd")
         ops.linear_dgrad(ws["g_gu"], lw["wgu"], g_h, resid=g_h, rowscale=st.rstd2, colscale=lw["ln2_f"], shadow=shadow)
         # ---- attention
         src = g_hb
@@ -351,7 +436,7 @@ class LlamaAttnLRPEngine:
         if self.hp:
             C.check(lib.lrp_attn_bwd_f32(q.data_ptr(), k.data_ptr(), v.data_ptr(), m.qkv_width, m.qkv_width, m.qkv_width,
                                          st.o.data_ptr(), ws["g_o"].data_ptr(), st.lse.data_ptr(), dq.data_ptr(), dk.data_ptr(),
-                                         dv.data_ptr(), m.qkv_width, m.qkv_width, m.qkv_width, ws["delta"].data_ptr(), B, S, m.H,
+                                         dv.data_ptr(), m.qkv_width, m.qkv_width, m.qkv_width, ws["delta"].data_ptr(), None, B, S, m.H,
                                          m.Hkv, m.D, scale, 1, win, *divs, ops._stream()), "attn_bwd_f32")
         else:
             C.check(lib.lrp_attn_bwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), m.qkv_width, m.qkv_width, m.qkv_width,
@@ -453,9 +538,13 @@ class LlamaAttnLRPEngine:
         key = tuple(ids.shape)
         ent = self._graphs.get(key)
         if ent is None:
-            if self._graphs:
-                raise RuntimeError("one graphed [B,S] shape per engine (the workspace is shared); build another engine")
             static_ids = ids.clone()
+            # the graph bakes raw pointers into its workspace: give this shape a private one that `_workspace` never frees
+            # (a later call of another shape, e.g. the trailing partial micro-batch of `attribute`, allocates its own)
+            self._ws_key, self._ws = None, None          # drop the shared slot, allocate a fresh workspace ...
+            ws_private = self._workspace(*key)
+            self._ws_key, self._ws = None, None          # ... and move it out of the shared slot into the graph's ownership
+            self._graph_ws[key] = ws_private
             side = torch.cuda.Stream(device=self.device)
             side.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(side):

@@ -47,7 +47,8 @@ def _rowmajor2d(t: torch.Tensor, name: str) -> int:
 
 
 def make_epilogue(out: torch.Tensor, *, resid: Optional[torch.Tensor] = None, rowscale=None, colscale=None, bias=None,
-                  shadow: Optional[torch.Tensor] = None, alpha: float = 1.0) -> Epilogue:
+                  shadow: Optional[torch.Tensor] = None, alpha: float = 1.0, act_out: Optional[torch.Tensor] = None,
+                  act: int = ACT_SILU) -> Epilogue:
     ldc = _rowmajor2d(out, "out")
     e = Epilogue()
     e.out = out.data_ptr()
@@ -70,6 +71,12 @@ def make_epilogue(out: torch.Tensor, *, resid: Optional[torch.Tensor] = None, ro
     e.bias = _p(bias)
     e.alpha = alpha
     e.ldc = ldc
+    if act_out is not None:   # fused gated-MLP forward: out = interleaved (gate | up) blocks, act_out = act(gate) * up
+        _need(act_out, torch.bfloat16, "act_out")
+        if out.dtype != torch.bfloat16 or not act_out.is_contiguous() or tuple(act_out.shape) != (out.shape[0], out.shape[1] // 2):
+            raise _capi.LrpError("act_out must be a contiguous bf16 [M, N/2] tensor next to a bf16 output")
+        e.act_out = act_out.data_ptr()
+        e.gated_act = act
     return e
 
 
@@ -85,6 +92,20 @@ def split_bf16x2(x: torch.Tensor):
     return hi, lo
 
 
+_WSPLIT = {}
+
+
+def _split_weight_cached(w: torch.Tensor):
+    """(hi, lo) bf16 split of an fp32 weight, cached per storage (weights are frozen on this path)"""
+    key = (w.data_ptr(), tuple(w.shape), tuple(w.stride()), w._version)
+    ent = _WSPLIT.get(key)
+    if ent is None:
+        if len(_WSPLIT) > 4096:
+            _WSPLIT.clear()
+        ent = _WSPLIT[key] = split_bf16x2(w.detach())
+    return ent
+
+
 def gemm(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor, *, b_layout: int, tile_n: int = 0, **epi) -> torch.Tensor:
     """out = epilogue(a @ b.T) for b_layout 0 (b is [N,K]) or epilogue(a @ b) for b_layout 1 (b is [K,N]).
     An fp32 `a` selects the validation-precision form: a = hi + lo (two bf16 terms), out = epilogue(hi b) then
@@ -95,8 +116,13 @@ def gemm(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor, *, b_layout: int, 
         if epi.get("shadow") is not None:
             raise _capi.LrpError("gemm: no bf16 shadow in validation precision")
         hi, lo = split_bf16x2(a)
-        gemm(hi, b, out, b_layout=b_layout, tile_n=tile_n, **epi)
         epi2 = {k: v for k, v in epi.items() if k in ("rowscale", "colscale", "alpha")}
+        if b.dtype == torch.float32:   # fp32 weights (an fp32 HF model): W = Wh + Wl as well; the lo*lo term (2^-18) is dropped
+            bh, bl = _split_weight_cached(b)
+            gemm(hi, bh, out, b_layout=b_layout, tile_n=tile_n, **epi)
+            gemm(lo, bh, out, b_layout=b_layout, tile_n=tile_n, resid=out, **epi2)
+            return gemm(hi, bl, out, b_layout=b_layout, tile_n=tile_n, resid=out, **epi2)
+        gemm(hi, b, out, b_layout=b_layout, tile_n=tile_n, **epi)
         return gemm(lo, b, out, b_layout=b_layout, tile_n=tile_n, resid=out, **epi2)
     _need(a, torch.bfloat16, "a")
     _need(b, torch.bfloat16, "b")
@@ -232,7 +258,7 @@ def rope_inplace(qk: torch.Tensor, n_heads: int, D: int, cos: torch.Tensor, sin:
     return qk
 
 
-def gated_act_fwd(gu: torch.Tensor, act: int = ACT_SILU, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+def gated_act_fwd(gu: torch.Tensor, act: int = ACT_SILU, out: Optional[torch.Tensor] = None, layout: int = 0) -> torch.Tensor:
     if gu.dtype not in (torch.float32, torch.bfloat16):
         raise _capi.LrpError("gated_act_fwd: gu must be bf16 or fp32")
     _need(gu, gu.dtype, "gu")
@@ -242,12 +268,13 @@ def gated_act_fwd(gu: torch.Tensor, act: int = ACT_SILU, out: Optional[torch.Ten
     a = out if out is not None else torch.empty((T, I2 // 2), dtype=gu.dtype, device=gu.device)
     if a.dtype != gu.dtype or not a.is_contiguous():
         raise _capi.LrpError("gated_act_fwd: output must be contiguous and share gu's dtype")
-    check(_capi.lib().lrp_gated_act_fwd_t(gu.data_ptr(), a.data_ptr(), int(gu.dtype == torch.float32), T, I2 // 2, act, _stream()),
-          "lrp_gated_act_fwd")
+    check(_capi.lib().lrp_gated_act_fwd_t(gu.data_ptr(), a.data_ptr(), int(gu.dtype == torch.float32), int(layout), T, I2 // 2, act,
+                                          _stream()), "lrp_gated_act_fwd")
     return a
 
 
-def gated_act_bwd(ga: torch.Tensor, gu: torch.Tensor, act: int = ACT_SILU, out: Optional[torch.Tensor] = None, cp: bool = False) -> torch.Tensor:
+def gated_act_bwd(ga: torch.Tensor, gu: torch.Tensor, act: int = ACT_SILU, out: Optional[torch.Tensor] = None, cp: bool = False,
+                  layout: int = 0) -> torch.Tensor:
     if gu.dtype not in (torch.float32, torch.bfloat16):
         raise _capi.LrpError("gated_act_bwd: gu must be bf16 or fp32")
     _need(ga, gu.dtype, "ga")
@@ -259,8 +286,8 @@ def gated_act_bwd(ga: torch.Tensor, gu: torch.Tensor, act: int = ACT_SILU, out: 
         out = torch.empty_like(gu)
     if out.dtype != gu.dtype or not out.is_contiguous():
         raise _capi.LrpError("gated_act_bwd: output must be contiguous and share gu's dtype")
-    check(_capi.lib().lrp_gated_act_bwd_t(ga.data_ptr(), gu.data_ptr(), out.data_ptr(), int(gu.dtype == torch.float32), T, I2 // 2,
-                                          act, int(cp), _stream()), "lrp_gated_act_bwd")
+    check(_capi.lib().lrp_gated_act_bwd_t(ga.data_ptr(), gu.data_ptr(), out.data_ptr(), int(gu.dtype == torch.float32), int(layout), T,
+                                          I2 // 2, act, int(cp), _stream()), "lrp_gated_act_bwd")
     return out
 
 
@@ -291,8 +318,17 @@ def _bshd(t: torch.Tensor, name: str, dtype=torch.bfloat16):
     return t.stride(1)
 
 
-def attn_fwd(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, scale: float, *, causal: bool = True, window: int = 0):
-    """q [B,S,H,D], k/v [B,S,Hkv,D] (views into a packed buffer are fine) -> (o [B,S,H,D] bf16, lse fp32 [B,H,S])"""
+def _kv_range_ptr(kv_range, B: int):
+    if kv_range is None:
+        return None
+    if not (kv_range.is_cuda and kv_range.dtype == torch.int32 and kv_range.is_contiguous() and tuple(kv_range.shape) == (B, 2)):
+        raise _capi.LrpError("kv_range must be a contiguous CUDA int32 tensor of shape [B, 2] (valid key range per sequence)")
+    return kv_range.data_ptr()
+
+
+def attn_fwd(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, scale: float, *, causal: bool = True, window: int = 0, kv_range=None):
+    """q [B,S,H,D], k/v [B,S,Hkv,D] (views into a packed buffer are fine) -> (o [B,S,H,D] bf16, lse fp32 [B,H,S]).
+    kv_range: optional int32 [B,2] device tensor, keys outside [lo, hi) of each sequence are masked (padded batches)."""
     dt = q.dtype
     if dt not in (torch.float32, torch.bfloat16):
         raise _capi.LrpError("attn_fwd: q must be bf16 or fp32")
@@ -303,15 +339,17 @@ def attn_fwd(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, scale: float, *,
     lse = torch.empty((B, H, S), dtype=torch.float32, device=q.device)
     if dt == torch.float32:   # validation precision: fp32 CUDA-core kernel
         check(_capi.lib().lrp_attn_fwd_f32(q.data_ptr(), k.data_ptr(), v.data_ptr(), ldq, ldk, ldv, o.data_ptr(), lse.data_ptr(),
-                                           B, S, H, Hkv, D, scale, int(causal), window, _stream()), "lrp_attn_fwd_f32")
+                                           _kv_range_ptr(kv_range, B), B, S, H, Hkv, D, scale, int(causal), window, _stream()),
+              "lrp_attn_fwd_f32")
         return o, lse
-    check(_capi.lib().lrp_attn_fwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), ldq, ldk, ldv, o.data_ptr(), lse.data_ptr(),
-                                   B, S, H, Hkv, D, scale, int(causal), window, _stream()), "lrp_attn_fwd")
+    check(_capi.lib().lrp_attn_fwd_varlen(q.data_ptr(), k.data_ptr(), v.data_ptr(), ldq, ldk, ldv, o.data_ptr(), lse.data_ptr(),
+                                          _kv_range_ptr(kv_range, B), B, S, H, Hkv, D, scale, int(causal), window, _stream()),
+          "lrp_attn_fwd")
     return o, lse
 
 
 def attn_bwd(q, k, v, o, d_o, lse, scale: float, *, causal: bool = True, window: int = 0, q_div: float = 4.0,
-             k_div: float = 4.0, v_div: float = 2.0, dq=None, dk=None, dv=None, dq_acc=None, delta=None):
+             k_div: float = 4.0, v_div: float = 2.0, dq=None, dk=None, dv=None, dq_acc=None, delta=None, kv_range=None):
     """LRP backward of attention: returns (dq, dk, dv) already divided by (q_div, k_div, v_div)."""
     dt = q.dtype
     if dt not in (torch.float32, torch.bfloat16):
@@ -335,17 +373,17 @@ def attn_bwd(q, k, v, o, d_o, lse, scale: float, *, causal: bool = True, window:
             delta = torch.empty((B, H, S), dtype=torch.float32, device=q.device)
         check(_capi.lib().lrp_attn_bwd_f32(q.data_ptr(), k.data_ptr(), v.data_ptr(), ldq, ldk, ldv, o.data_ptr(), d_o.data_ptr(),
                                            lse.data_ptr(), dq.data_ptr(), dk.data_ptr(), dv.data_ptr(), lddq, lddk, lddv,
-                                           delta.data_ptr(), B, S, H, Hkv, D, scale, int(causal), window, q_div, k_div, v_div,
-                                           _stream()), "lrp_attn_bwd_f32")
+                                           delta.data_ptr(), _kv_range_ptr(kv_range, B), B, S, H, Hkv, D, scale, int(causal), window,
+                                           q_div, k_div, v_div, _stream()), "lrp_attn_bwd_f32")
         return dq, dk, dv
     if dq_acc is None:
         dq_acc = torch.empty((B, S, H, D), dtype=torch.float32, device=q.device)
     if delta is None:
         delta = torch.empty((B, H, S), dtype=torch.float32, device=q.device)
-    check(_capi.lib().lrp_attn_bwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), ldq, ldk, ldv, o.data_ptr(), d_o.data_ptr(),
-                                   lse.data_ptr(), dq.data_ptr(), dk.data_ptr(), dv.data_ptr(), lddq, lddk, lddv,
-                                   dq_acc.data_ptr(), delta.data_ptr(), B, S, H, Hkv, D, scale, int(causal), window,
-                                   q_div, k_div, v_div, _stream()), "lrp_attn_bwd")
+    check(_capi.lib().lrp_attn_bwd_varlen(q.data_ptr(), k.data_ptr(), v.data_ptr(), ldq, ldk, ldv, o.data_ptr(), d_o.data_ptr(),
+                                          lse.data_ptr(), dq.data_ptr(), dk.data_ptr(), dv.data_ptr(), lddq, lddk, lddv,
+                                          dq_acc.data_ptr(), delta.data_ptr(), _kv_range_ptr(kv_range, B), B, S, H, Hkv, D, scale,
+                                          int(causal), window, q_div, k_div, v_div, _stream()), "lrp_attn_bwd")
     return dq, dk, dv
 
 

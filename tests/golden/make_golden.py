@@ -192,6 +192,58 @@ def gen_llama(name, cfg, B, S, seed):
     np.savez_compressed(os.path.join(HERE, f"{name}.npz"), **save)
 
 
+def gen_llama_padded():
+    """A batch of two prompts of DIFFERENT lengths through the real reference (lxt.efficient.monkey_patch(modeling_llama), HF
+    `attention_mask`): left padding with the logit read at the last position, right padding with the logit read at each
+    prompt's own last token.  Weights / ids of llama_tiny_d64.npz; stores the relevance of the fp32 run (sdpa)."""
+    global _patched
+    if not _patched:
+        monkey_patch(modeling_llama, verbose=True)
+        _patched = True
+    sys.path.insert(0, os.path.dirname(HERE))
+    from helpers import load_llama_golden
+    cfg, w, ids, _ = load_llama_golden("llama_tiny_d64.npz")
+    B, S = ids.shape
+    lens = [S, 97]
+    hf_cfg = LlamaConfig(hidden_size=cfg["d"], intermediate_size=cfg["I"], num_hidden_layers=cfg["L"],
+                         num_attention_heads=cfg["H"], num_key_value_heads=cfg["Hkv"], head_dim=cfg["D"],
+                         vocab_size=cfg["V"], rms_norm_eps=cfg["eps"],
+                         rope_parameters={"rope_type": "default", "rope_theta": cfg["theta"]},
+                         max_position_embeddings=512, attention_bias=False, tie_word_embeddings=False)
+    hf_cfg._attn_implementation = "sdpa"
+    model = LlamaForCausalLM(hf_cfg).to(torch.float32).eval()
+    sd = {"model.embed_tokens.weight": w["emb"], "model.norm.weight": w["norm"], "lm_head.weight": w["lm_head"]}
+    for i, lw in enumerate(w["layers"]):
+        p = f"model.layers.{i}."
+        sd.update({p + "self_attn.q_proj.weight": lw["wq"], p + "self_attn.k_proj.weight": lw["wk"],
+                   p + "self_attn.v_proj.weight": lw["wv"], p + "self_attn.o_proj.weight": lw["wo"],
+                   p + "mlp.gate_proj.weight": lw["wg"], p + "mlp.up_proj.weight": lw["wu"],
+                   p + "mlp.down_proj.weight": lw["wd"], p + "input_layernorm.weight": lw["ln1"],
+                   p + "post_attention_layernorm.weight": lw["ln2"]})
+    model.load_state_dict({k: v.float() for k, v in sd.items()}, strict=True)
+    for p_ in model.parameters():
+        p_.requires_grad_(False)
+    save = dict(lens=np.array(lens))
+    for side in ("left", "right"):
+        mask = torch.zeros(B, S, dtype=torch.long)
+        for b, n in enumerate(lens):
+            if side == "left":
+                mask[b, S - n:] = 1
+            else:
+                mask[b, :n] = 1
+        emb = model.get_input_embeddings()(ids).detach().requires_grad_()
+        logits = model(inputs_embeds=emb, attention_mask=mask, use_cache=False).logits
+        last = torch.tensor([S - 1] * B) if side == "left" else torch.tensor([n - 1 for n in lens])
+        mx, mi = torch.max(logits[torch.arange(B), last, :], dim=-1)
+        mx.sum().backward()
+        rel = (emb * emb.grad).float().sum(-1) * mask      # relevance of padding tokens is not defined: zeroed
+        save[f"mask_{side}"] = mask.numpy()
+        save[f"rel_{side}"] = rel.detach().numpy()
+        save[f"idx_{side}"] = mi.numpy()
+        print("padded", side, "relevance norm", float(rel.norm()), "idx", mi.tolist())
+    np.savez_compressed(os.path.join(HERE, "llama_tiny_d64_padded.npz"), **save)
+
+
 def gen_vit():
     """torchvision ViT, lxt.efficient.monkey_patch(vision_transformer) (cp_LRP map), examples/vit_torch.py:84-91."""
     from torchvision.models import vision_transformer
@@ -212,6 +264,48 @@ def gen_vit():
         save["sd_" + k] = v.numpy()
     np.savez_compressed(os.path.join(HERE, "vit_tiny.npz"), **save)
     print("vit_tiny.npz heat norm", float(heat.norm()))
+
+
+def build_vit_l16(seed=5):
+    """torchvision vit_l_16 (BASELINE configs[3]) with seeded random weights and the head re-initialised (torchvision zero-fills it).
+    The 304 M weights are NOT stored: the GPU test rebuilds them from the same seed (same torch build, CPU generator)."""
+    from torchvision.models import vision_transformer
+    torch.manual_seed(seed)
+    model = vision_transformer.vit_l_16(weights=None).eval()
+    torch.nn.init.normal_(model.heads.head.weight, std=0.02)
+    for p_ in model.parameters():
+        p_.requires_grad_(False)
+    return model
+
+
+def vit_weight_fingerprint(model):
+    sd = model.state_dict()
+    keys = ["conv_proj.weight", "encoder.layers.encoder_layer_11.mlp.0.weight", "heads.head.weight"]
+    return np.array([float(sd[k].double().abs().sum()) for k in keys])
+
+
+def gen_vit_l16():
+    """ViT-L/16 at full size, lxt.efficient.monkey_patch(vision_transformer) (cp_LRP map), examples/vit_torch.py:84-91:
+    pixel relevance of the arg-max class from the reference's fp32 run and from its bf16 run."""
+    from torchvision.models import vision_transformer
+    monkey_patch(vision_transformer, verbose=True)
+    model = build_vit_l16()
+    x0 = torch.randn(1, 3, 224, 224, generator=torch.Generator().manual_seed(6))
+    x = x0.clone().requires_grad_()
+    y = model(x)
+    cls = y.argmax(-1)
+    y[torch.arange(1), cls].sum().backward()
+    heat = (x * x.grad).sum(1)
+    fp = vit_weight_fingerprint(model)
+    m16 = model.to(torch.bfloat16)
+    x16 = x0.to(torch.bfloat16).requires_grad_()
+    y16 = m16(x16)
+    y16[torch.arange(1), cls].sum().backward()
+    heat16 = (x16 * x16.grad).float().sum(1)
+    np.savez_compressed(os.path.join(HERE, "vit_l16.npz"), x=x0.numpy(), heat=heat.detach().numpy(), heat_bf16=heat16.detach().numpy(),
+                        cls=cls.numpy(), logits=y.detach().numpy(), fingerprint=fp)
+    e = float((heat16.detach().double() - heat.detach().double()).norm() / heat.detach().double().norm())
+    print("vit_l16.npz heat norm", float(heat.norm()), "reference bf16 vs fp32 rel-L2", e)
 
 
 def gen_llama_cp():
@@ -375,6 +469,12 @@ if __name__ == "__main__":
         sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "--vit":
         gen_vit()
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "--padded":
+        gen_llama_padded()
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "--vit-l16":
+        gen_vit_l16()
         sys.exit(0)
     gen_rules()
     gen_llama("llama_tiny_d64", dict(d=256, I=512, H=4, Hkv=2, D=64, L=2, V=256, eps=1e-5, theta=10000.0), B=2, S=160, seed=0)

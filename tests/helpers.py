@@ -55,3 +55,20 @@ def load_gemma_golden(name):
                                 ln1=sd[p + "input_layernorm.weight"], ln_post_attn=sd[p + "post_attention_layernorm.weight"],
                                 ln_pre_ff=sd[p + "pre_feedforward_layernorm.weight"], ln_post_ff=sd[p + "post_feedforward_layernorm.weight"]))
     return cfg, w, torch.from_numpy(z["ids"]), z
+
+
+def build_vit_l16(seed=5):
+    """same construction as tests/golden/make_golden.py::build_vit_l16 (seeded torchvision vit_l_16, head re-initialised)"""
+    from torchvision.models import vision_transformer
+    torch.manual_seed(seed)
+    model = vision_transformer.vit_l_16(weights=None).eval()
+    torch.nn.init.normal_(model.heads.head.weight, std=0.02)
+    for p_ in model.parameters():
+        p_.requires_grad_(False)
+    return model
+
+
+def vit_weight_fingerprint(model):
+    sd = model.state_dict()
+    keys = ["conv_proj.weight", "encoder.layers.encoder_layer_11.mlp.0.weight", "heads.head.weight"]
+    return np.array([float(sd[k].double().abs().sum()) for k in keys])

@@ -112,6 +112,56 @@ def test_engine_cuda_graph_replay_matches_eager():
     assert rel_l2(eng.attribute(ids2.pin_memory()), torch.roll(eager, 1, 0)) < 1e-5
 
 
+def test_engine_cuda_graph_survives_partial_micro_batches_and_other_shapes():
+    """a trailing partial micro-batch (N % micro_batch != 0) or any other [B,S] between two graphed calls must not
+    invalidate the captured graph's workspace."""
+    cfg, w, ids, z = load_llama_golden("llama_tiny_d64.npz")
+    ids3 = torch.cat([ids, ids[:1]], 0)                       # N = 3, micro_batch = 2 -> one graphed batch + one eager tail
+    eager = _engine(cfg, w, micro_batch=2).attribute(ids3.pin_memory()).clone()
+    eng = _engine(cfg, w, micro_batch=2, cuda_graph=True)
+    for _ in range(3):
+        got = eng.attribute(ids3.pin_memory()).clone()
+        assert rel_l2(got, eager) < 1e-5
+        eng.attribute_device(ids[:1, :96].cuda())             # a different shape through the shared workspace slot
+        torch.cuda.empty_cache()
+    assert rel_l2(eng.attribute(ids3.pin_memory()), eager) < 1e-5
+
+
+def test_engine_from_hf_reproduces_scaled_rope():
+    """rope_scaling (llama3 / linear) must be honoured by from_hf — engine vs the patched HF model itself."""
+    from transformers import LlamaConfig, LlamaForCausalLM
+    from transformers.models.llama import modeling_llama
+    from lxt_b200.efficient import monkey_patch
+    from lxt_b200.engine import LlamaAttnLRPEngine
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        monkey_patch(modeling_llama)
+    for rope in ({"rope_type": "llama3", "rope_theta": 10000.0, "factor": 8.0, "low_freq_factor": 1.0, "high_freq_factor": 4.0,
+                  "original_max_position_embeddings": 64},
+                 {"rope_type": "linear", "rope_theta": 10000.0, "factor": 4.0}):
+        torch.manual_seed(0)
+        hf = LlamaConfig(hidden_size=256, intermediate_size=512, num_hidden_layers=2, num_attention_heads=4, num_key_value_heads=2,
+                         head_dim=64, vocab_size=256, rope_parameters=rope, max_position_embeddings=512, tie_word_embeddings=False)
+        hf._attn_implementation = "sdpa"
+        model = LlamaForCausalLM(hf).to(torch.bfloat16).cuda().eval()
+        for p_ in model.parameters():
+            p_.requires_grad_(False)
+        ids = torch.randint(0, 256, (2, 200), generator=torch.Generator().manual_seed(3)).cuda()
+        emb = model.get_input_embeddings()(ids).detach().requires_grad_()
+        logits = model(inputs_embeds=emb, use_cache=False).logits
+        mx, mi = torch.max(logits[:, -1, :], dim=-1)
+        mx.sum().backward()
+        rel_hf = (emb * emb.grad).float().sum(-1).detach().cpu()
+        eng = LlamaAttnLRPEngine.from_hf(model, micro_batch=2)
+        rel, aux = eng.attribute_device(ids, return_aux=True)
+        plain = LlamaAttnLRPEngine.from_hf(model, micro_batch=2, rope=None).attribute_device(ids).cpu()   # default tables: must differ
+        e, e_plain = rel_l2(rel.cpu(), rel_hf), rel_l2(plain, rel_hf)
+        print(f"rope {rope['rope_type']}: engine vs patched HF {e:.2e}; with default RoPE tables {e_plain:.2e}")
+        assert torch.equal(aux["idx"].cpu().long(), mi.cpu())
+        assert e < 1.5e-2 and e_plain > 5 * e
+
+
 @pytest.mark.parametrize("name", ["gemma3_tiny.npz", "gemma3_tiny_d256.npz"])
 def test_engine_gemma3_matches_reference_golden(name):
     """The fused engine on the Gemma-3 layer layout ((1+w) norms, pre/post norms around both branches, per-head q/k-norm,

@@ -39,12 +39,7 @@ def test_sqrt_checkpoint_schedule_equals_full_store(setup):
     from lxt_b200.engine import LlamaAttnLRPEngine
     dims, eng, ids = setup
     rel = eng.attribute_device(ids[:2]).clone()
-    w = dict(emb=eng.emb, norm=eng.norm_w, lm_head=eng.lm_head, layers=[])
-    H, Hkv, D = dims.H, dims.Hkv, dims.D
-    for lw in eng.layers:
-        wq, wk, wv = lw["wqkv"].split([H * D, Hkv * D, Hkv * D], 0)
-        wg, wu = lw["wgu"].split([dims.I, dims.I], 0)
-        w["layers"].append(dict(wq=wq, wk=wk, wv=wv, wo=lw["wo"], wg=wg, wu=wu, wd=lw["wd"], ln1=lw["ln1"], ln2=lw["ln2"]))
+    w = eng.export_weights()
     eng2 = LlamaAttnLRPEngine.from_weights(dims, w, device="cuda", micro_batch=2, store="sqrt")
     assert rel_l2(eng2.attribute_device(ids[:2]), rel) < 1e-3
 

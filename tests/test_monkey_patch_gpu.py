@@ -9,11 +9,11 @@ from helpers import load_llama_golden, rel_l2
 pytestmark = pytest.mark.gpu
 
 
-def _hf_model(cfg, w, impl):
+def _hf_model(cfg, w, impl, max_pos=512):
     from transformers import LlamaConfig, LlamaForCausalLM
     hf = LlamaConfig(hidden_size=cfg["d"], intermediate_size=cfg["I"], num_hidden_layers=cfg["L"], num_attention_heads=cfg["H"],
                      num_key_value_heads=cfg["Hkv"], head_dim=cfg["D"], vocab_size=cfg["V"], rms_norm_eps=cfg["eps"],
-                     rope_parameters={"rope_type": "default", "rope_theta": cfg["theta"]}, max_position_embeddings=512,
+                     rope_parameters={"rope_type": "default", "rope_theta": cfg["theta"]}, max_position_embeddings=max_pos,
                      attention_bias=False, tie_word_embeddings=False)
     hf._attn_implementation = impl
     m = LlamaForCausalLM(hf).to(torch.bfloat16)

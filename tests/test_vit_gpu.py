@@ -65,3 +65,44 @@ def test_vit_pixel_relevance_matches_reference():
     err = rel_l2(heat, z["heat"])
     print(f"ViT heat-map rel-L2 vs reference = {err:.3e}")
     assert err < 1e-3
+
+
+def test_vit_l16_matches_reference_golden():
+    """BASELINE configs[3] at FULL size: torchvision vit_l_16 (24 layers, d=1024, 16 heads, 197 tokens), pixel relevance of the
+    arg-max class through the drop-in API vs the golden heat-map of the real reference (fp32 run), examples/vit_torch.py:84-91.
+    fp32 model: <= 1e-3 (the stated tolerance); bf16 model: self-calibrated against the reference's own bf16 run."""
+    import json
+    import os
+    import warnings
+    from torchvision.models import vision_transformer
+    from helpers import build_vit_l16, vit_weight_fingerprint
+    from lxt_b200.efficient import monkey_patch
+    z = load_npz("vit_l16.npz")
+    model = build_vit_l16()
+    fp = vit_weight_fingerprint(model)
+    if not np.allclose(fp, z["fingerprint"], rtol=1e-6):
+        pytest.skip("this torch build seeds vit_l_16 differently from the container that generated the golden")
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        monkey_patch(vision_transformer)
+    cls = torch.from_numpy(z["cls"]).cuda()
+    ref_gap = rel_l2(z["heat_bf16"], z["heat"])
+    out = {}
+    for tag, dt in (("fp32", torch.float32), ("bf16", torch.bfloat16)):
+        m = model.to(dt).cuda()
+        x = torch.from_numpy(z["x"]).cuda().to(dt).requires_grad_()
+        y = m(x)
+        if tag == "fp32":
+            assert np.array_equal(y.argmax(-1).cpu().numpy(), z["cls"])
+        y[torch.arange(1), cls].sum().backward()
+        heat = (x * x.grad).float().sum(1).detach().cpu()
+        out[tag] = rel_l2(heat, z["heat"])
+    row = dict(config="vit_l_16 full size, drop-in monkey_patch(vision_transformer)", dropin_fp32_vs_reference_fp32=out["fp32"],
+               dropin_bf16_vs_reference_fp32=out["bf16"], reference_bf16_vs_fp32=ref_gap)
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    os.makedirs(os.path.join(root, "gpurun_out"), exist_ok=True)
+    with open(os.path.join(root, "gpurun_out", "parity_r02.jsonl"), "a") as f:
+        f.write(json.dumps(row) + "\n")
+    print("PARITY " + json.dumps(row))
+    assert out["fp32"] <= 1e-3
+    assert out["bf16"] <= 1.1 * ref_gap
