@@ -46,6 +46,8 @@ def parse():
     ap.add_argument("--model", default="llama3-8b", choices=["llama3-8b", "tinyllama-1.1b", "gemma3-4b", "llama-test"])
     ap.add_argument("--layers", type=int, default=0, help="override the number of layers (debug only; invalidates the metric)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--dropin", type=int, default=1, help="also time the drop-in monkey_patch API on an HF Llama of the same dims (N=1)")
+    ap.add_argument("--dropin-batch", type=int, default=4)
     return ap.parse_args()
 
 
@@ -304,6 +306,27 @@ def cpu_baseline_block(dims, seq, warmup=1, steps=1, budget_s=150.0):
     return v, blk, 2e3 * sum(dts) / len(dts), len(vals), extra
 
 
+def cpu_baseline_subprocess(args):
+    """The CPU leg of our arm runs `bench.py --impl reference` in a SEPARATE process: this process has lxt_b200's patches
+    installed on the transformers modules (class-level, process-global, like the reference's), and the reference must run
+    on stock modules; it also keeps the CPU leg off the GPU (CUDA_VISIBLE_DEVICES is cleared)."""
+    cmd = [sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "1", "--warmup", "1", "--model", args.model,
+           "--seq", str(args.seq)] + (["--layers", str(args.layers)] if args.layers else [])
+    env = dict(os.environ, CUDA_VISIBLE_DEVICES="")
+    for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "MASTER_ADDR", "MASTER_PORT"):
+        env.pop(k, None)
+    try:
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
+        line = [ln for ln in r.stdout.strip().split("\n") if ln.startswith("{")][-1]
+        ref = json.loads(line)
+        blk = ref["cpu_baseline"]
+        blk["extrapolation"] = ref.get("extrapolation")
+        blk["timed_ms_per_step"] = ref.get("ms_per_step")
+        return blk
+    except Exception as ex:  # pragma: no cover
+        return {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "reference", "sample": f"failed: {ex!r}"}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -449,14 +472,81 @@ def run_b200(args):
             out["kernels"] = secondary_kernel_rooflines(dims, S, dev, peaks)
         except Exception as ex:  # pragma: no cover
             out["kernels"] = {"error": str(ex)}
-    if not args.no_cpu_baseline and world == 1:   # reported on rank 0 at N=1 only
+    if args.dropin and world == 1 and args.model in ("llama3-8b", "tinyllama-1.1b", "llama-test"):
         try:
-            v, blk, ms_step, steps_run, extra = cpu_baseline_block(dims, S, warmup=1, steps=1, budget_s=60.0)
-            blk["extrapolation"] = extra
-            out["cpu_baseline"] = blk
+            del eng
+            torch.cuda.empty_cache()
+            out["dropin_api"] = dropin_api_bench(dims, S, dev, batch=args.dropin_batch)
         except Exception as ex:  # pragma: no cover
-            out["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {ex}"}
+            out["dropin_api"] = {"error": repr(ex)}
+    if not args.no_cpu_baseline and world == 1:   # reported on rank 0 at N=1 only
+        out["cpu_baseline"] = cpu_baseline_subprocess(args)
     print(json.dumps(out))
+
+
+def dropin_api_bench(dims, S, dev, batch=4, steps=2):
+    """The API north_star names, at the headline width and depth: `lxt_b200.efficient.monkey_patch(modeling_llama)` on an
+    unmodified HuggingFace `LlamaForCausalLM` (bf16, sdpa entry of the attention registry), user code of
+    examples/quantized_llama.py:35-47 on `batch` prompts per step (HF computes the logits of ALL positions and autograd
+    keeps every intermediate, so the batch is smaller than the engine's).  Returns attributions/s, device-timed."""
+    import warnings
+    from transformers import LlamaConfig, LlamaForCausalLM
+    from transformers.models.llama import modeling_llama
+    from lxt_b200 import ops
+    from lxt_b200.efficient import monkey_patch
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        monkey_patch(modeling_llama)
+    cfg = LlamaConfig(hidden_size=dims.d, intermediate_size=dims.I, num_attention_heads=dims.H, num_key_value_heads=dims.Hkv,
+                      head_dim=dims.D, num_hidden_layers=dims.L, vocab_size=dims.V, rms_norm_eps=dims.eps,
+                      rope_parameters={"rope_type": "default", "rope_theta": dims.theta}, max_position_embeddings=max(S, 2048),
+                      tie_word_embeddings=False)
+    cfg._attn_implementation = "sdpa"
+    torch.set_default_dtype(torch.bfloat16)
+    try:
+        try:
+            from transformers.initialization import no_init_weights
+            with torch.device(dev), no_init_weights():
+                model = LlamaForCausalLM(cfg)
+        except ImportError:
+            with torch.device(dev):
+                model = LlamaForCausalLM(cfg)
+    finally:
+        torch.set_default_dtype(torch.float32)
+    g = torch.Generator(device=dev).manual_seed(0)
+    with torch.no_grad():
+        for prm in model.parameters():
+            if prm.dim() >= 2:
+                prm.copy_((torch.randn(prm.shape, generator=g, device=dev, dtype=torch.float32) * 0.02).to(torch.bfloat16))
+            else:
+                prm.fill_(1.0)
+            prm.requires_grad_(False)
+    model.eval()
+    ids = torch.randint(0, dims.V, (batch, S), generator=torch.Generator().manual_seed(1)).to(dev)
+
+    def one():
+        emb = model.get_input_embeddings()(ids).detach().requires_grad_()
+        logits = model(inputs_embeds=emb, use_cache=False).logits
+        mx, _ = torch.max(logits[:, -1, :], dim=-1)
+        mx.sum().backward()
+        return (emb * emb.grad).float().sum(-1)
+
+    one()
+    l0 = ops.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(steps):
+        rel = one()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    res = {"api": "lxt_b200.efficient.monkey_patch(transformers.models.llama.modeling_llama) on HF LlamaForCausalLM (bf16, all-position logits)",
+           "value": batch / (ms * 1e-3), "unit": UNIT, "batch": batch, "seq_len": S, "layers": dims.L, "ms_per_step": ms,
+           "gpu_launches_per_step": int((ops.launch_count() - l0) / steps), "finite": bool(torch.isfinite(rel).all())}
+    del model
+    torch.cuda.empty_cache()
+    return res
 
 
 def secondary_kernel_rooflines(dims, S, dev, peaks):

@@ -81,6 +81,14 @@ typedef struct lrp_epilogue {
 int lrp_gemm_bf16(const void* A, int64_t lda, const void* B, int64_t ldb, int b_layout, int M, int N, int K,
                   const lrp_epilogue_t* epi, int tile_n, void* stream);
 
+/* Strided-batched form (one launch for `batch` independent problems; 3-D tensor maps): the two contractions of the matmul rule
+ * R_A = (s B^T) * A, R_B = (A^T s) * B of lxt/explicit/functional.py:393-408 over all [B*H] slices, and its forward A B.
+ * a_layout 0: A_i is [M,K] row-major;  a_layout 1: the caller holds A_i^T, i.e. a [K,M] row-major tensor (consumed through an
+ * MN-major descriptor, no transposed copy).  b_layout as in lrp_gemm_bf16.  Problem i reads A + i*stride_a, B + i*stride_b and
+ * writes out (resid / shadow) + i*stride_c (strides in elements); rowscale / colscale / bias are shared by all problems. */
+int lrp_gemm_bf16_batched(const void* A, int64_t lda, int64_t stride_a, int a_layout, const void* B, int64_t ldb, int64_t stride_b,
+                          int b_layout, int batch, int M, int N, int K, const lrp_epilogue_t* epi, int64_t stride_c, void* stream);
+
 /* nn.Linear forward  y[T,N] = x[T,K] W[N,K]^T (+bias) with the fused epilogue above.
  * Replaces: every `nn.Linear` on the path (transformers modeling_llama.py:183,262-264,288), left unpatched
  * by the reference and therefore executed by cuBLAS there. */
@@ -214,6 +222,10 @@ int lrp_gxi_reduce(const float* x, const float* g, float* rel, int T, int d, voi
 /* bf16 variant of the same reduction (x, g bf16) */
 /* same for bf16 x / g (the dtype the reference's example runs in, examples/quantized_llama.py:13-19,47) */
 int lrp_gxi_reduce_bf16(const void* x, const void* g, float* rel, int T, int d, void* stream);
+/* latent relevance of a layer output (docs/source/latent-feature-attribution-efficient.rst:49-90: `output * output.grad` summed over
+ * features): x = the bf16 copy of the layer output that the forward residual GEMM epilogue writes as its shadow, g = the fp32
+ * gradient stream at that layer in the backward sweep (same reduction as examples/quantized_llama.py:47 applied per layer) */
+int lrp_gxi_reduce_mixed(const void* x_bf16, const float* g, float* rel, int T, int d, void* stream);
 /* out_bf16 = bf16(in_f32), n elements */
 /* fp32 -> bf16 rounding of an activation / gradient stream (the reference's `.to(input_dtype)` casts,
  * lxt/efficient/patches.py:118-123) */
@@ -235,6 +247,9 @@ int lrp_identity_rule_bwd(const void* gy, const void* x, const void* y, void* gx
 /* Deep-Taylor softmax rule over the last dim (functional.py:308-322): out = x~*(r - p*sum(r)), -inf -> 0. */
 int lrp_softmax_dt_bwd(const void* x, const void* p, const void* r, void* out, int64_t rows, int cols, int is_f32,
                        void* stream);
+/* soft-max forward over the last dim, out = softmax(x / temperature), fp32 arithmetic (lxt/explicit/functional.py:293-306
+ * `softmax_fn.forward`; its Deep-Taylor backward is lrp_softmax_dt_bwd). */
+int lrp_softmax_fwd(const void* x, void* out, int64_t rows, int cols, float temperature, int is_f32, void* stream);
 /* epsilon rule of a+b (functional.py:439-459): ra = a*r/(a+b+eps), rb = b*r/(a+b+eps). */
 int lrp_add2_bwd(const void* a, const void* b, const void* r, void* ra, void* rb, int64_t n, float eps, int is_f32,
                  void* stream);

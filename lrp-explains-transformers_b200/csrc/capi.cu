@@ -143,6 +143,12 @@ int lrp_gemm_bf16(const void* A, int64_t lda, const void* B, int64_t ldb, int b_
   return gemm_bf16(A, lda, B, ldb, b_layout, M, N, K, epi, tile_n, static_cast<cudaStream_t>(stream));
 }
 
+int lrp_gemm_bf16_batched(const void* A, int64_t lda, int64_t stride_a, int a_layout, const void* B, int64_t ldb, int64_t stride_b,
+                          int b_layout, int batch, int M, int N, int K, const lrp_epilogue_t* epi, int64_t stride_c, void* stream) {
+  return gemm_bf16_batched(A, lda, stride_a, a_layout, B, ldb, stride_b, b_layout, batch, M, N, K, epi, stride_c,
+                           static_cast<cudaStream_t>(stream));
+}
+
 int lrp_linear_fwd(const void* x, int64_t ldx, const void* W, int64_t ldw, int T, int N, int K,
                    const lrp_epilogue_t* epi, void* stream) {
   return gemm_bf16(x, ldx, W, ldw, /*NT*/ 0, T, N, K, epi, 0, static_cast<cudaStream_t>(stream));

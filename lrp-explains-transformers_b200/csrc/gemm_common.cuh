@@ -23,6 +23,8 @@ struct GemmParams {
   int gated_act, gated_cp;
   __nv_bfloat16* act_out;   // fused gated-MLP forward: a[m, n/2] = act(gate) * up from 32-interleaved (gate | up) column blocks
   int group_m;  // rasterisation: `group_m` m-blocks share each streamed B panel through L2
+  int batch;              // strided-batched form (one-CTA kernel only): `batch` independent problems in one launch
+  int64_t batch_stride_c; // element distance between consecutive problems in out / resid / shadow
 };
 
 __device__ __forceinline__ float gemm_act_eval(float x, int act) {

@@ -38,7 +38,10 @@ struct GemmCfg {
   static constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
 };
 
-template <int BN, bool B_MN>
+// A_MN: the A operand is stored contraction-major, i.e. the caller holds A^T as a [K, M] row-major tensor (the `a^T s`
+//       contraction of the matmul rule, lxt/explicit/functional.py:393-408) and it is consumed through an MN-major descriptor.
+// BATCHED: 3-D tensor maps, tile index runs over batch x tiles (strided-batched problems in ONE launch).
+template <int BN, bool B_MN, bool A_MN = false, bool BATCHED = false>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                  const GemmParams p) {
@@ -57,7 +60,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
 
   const int num_m = (p.M + BM - 1) / BM;
   const int num_n = (p.N + BN - 1) / BN;
-  const int num_tiles = num_m * num_n;
+  const int tiles_per_problem = num_m * num_n;
+  const int num_tiles = tiles_per_problem * (BATCHED ? p.batch : 1);
   const int num_k = (p.K + BK - 1) / BK;
 
   if (warp == 0 && lane == 0) {
@@ -91,19 +95,37 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
       uint32_t phase = 0;
       for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
         int m_blk, n_blk;
-        tile_coords(t, num_m, num_n, p.group_m, m_blk, n_blk);
+        const int bz = BATCHED ? t / tiles_per_problem : 0;
+        tile_coords(BATCHED ? t - bz * tiles_per_problem : t, num_m, num_n, p.group_m, m_blk, n_blk);
         for (int kb = 0; kb < num_k; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
           uint8_t* sb = sa + Cfg::A_BYTES;
           mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
-          tma_load_2d(sa, &tma_a, &full_bar[stage], kb * BK, m_blk * BM);
-          if constexpr (!B_MN) {
-            tma_load_2d(sb, &tma_b, &full_bar[stage], kb * BK, n_blk * BN);
-          } else {
+          if constexpr (BATCHED) {
+            if constexpr (!A_MN) {
+              tma_load_3d(sa, &tma_a, &full_bar[stage], kb * BK, m_blk * BM, bz);
+            } else {
 #pragma unroll
-            for (int j = 0; j < BN / 64; ++j)
-              tma_load_2d(sb + j * (64 * BK * 2), &tma_b, &full_bar[stage], n_blk * BN + j * 64, kb * BK);
+              for (int j = 0; j < BM / 64; ++j)
+                tma_load_3d(sa + j * (64 * BK * 2), &tma_a, &full_bar[stage], m_blk * BM + j * 64, kb * BK, bz);
+            }
+            if constexpr (!B_MN) {
+              tma_load_3d(sb, &tma_b, &full_bar[stage], kb * BK, n_blk * BN, bz);
+            } else {
+#pragma unroll
+              for (int j = 0; j < BN / 64; ++j)
+                tma_load_3d(sb + j * (64 * BK * 2), &tma_b, &full_bar[stage], n_blk * BN + j * 64, kb * BK, bz);
+            }
+          } else {
+            tma_load_2d(sa, &tma_a, &full_bar[stage], kb * BK, m_blk * BM);
+            if constexpr (!B_MN) {
+              tma_load_2d(sb, &tma_b, &full_bar[stage], kb * BK, n_blk * BN);
+            } else {
+#pragma unroll
+              for (int j = 0; j < BN / 64; ++j)
+                tma_load_2d(sb + j * (64 * BK * 2), &tma_b, &full_bar[stage], n_blk * BN + j * 64, kb * BK);
+            }
           }
           if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
         }
@@ -111,7 +133,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     }
   } else if (warp == 1) {
     // ================= MMA issuer =================
-    constexpr uint32_t idesc = make_idesc_bf16(BM, BN, 0, B_MN ? 1 : 0);
+    constexpr uint32_t idesc = make_idesc_bf16(BM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
     int stage = 0;
     uint32_t phase = 0;
     int acc = 0;
@@ -126,11 +148,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
         if (lane == 0) {
           const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
           const uint32_t sb = sa + Cfg::A_BYTES;
-          const uint64_t adesc = make_sdesc_sw128(sa, 16, 1024);
+          const uint64_t adesc = A_MN ? make_sdesc_sw128(sa, 64 * BK * 2, 1024) : make_sdesc_sw128(sa, 16, 1024);
           const uint64_t bdesc = B_MN ? make_sdesc_sw128(sb, 64 * BK * 2, 1024) : make_sdesc_sw128(sb, 16, 1024);
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k) {
-            const uint64_t a_adv = uint64_t((k * UMMA_K * 2) >> 4);
+            const uint64_t a_adv = A_MN ? uint64_t((k * UMMA_K * 128) >> 4) : uint64_t((k * UMMA_K * 2) >> 4);
             const uint64_t b_adv = B_MN ? uint64_t((k * UMMA_K * 128) >> 4) : uint64_t((k * UMMA_K * 2) >> 4);
             tc_mma_ss(tmem_d, adesc + a_adv, bdesc + b_adv, idesc, (kb | k) != 0 ? 1u : 0u);
           }
@@ -149,14 +171,15 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     uint32_t acc_phase = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
       int m_blk, n_blk;
-      tile_coords(t, num_m, num_n, p.group_m, m_blk, n_blk);
+      const int bz = BATCHED ? t / tiles_per_problem : 0;
+      tile_coords(BATCHED ? t - bz * tiles_per_problem : t, num_m, num_n, p.group_m, m_blk, n_blk);
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
       const int m = m_blk * BM + q * 32 + lane;
       const bool row_ok = m < p.M;
       const float rs = (p.rowscale != nullptr && row_ok) ? p.rowscale[m] * p.alpha : p.alpha;
       const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + acc * BN;
-      const int64_t row_off = int64_t(m) * p.ldc;
+      const int64_t row_off = int64_t(m) * p.ldc + (BATCHED ? int64_t(bz) * p.batch_stride_c : 0);
       if (p.act_out != nullptr) {
         // gate|up forward with act(gate) * up fused: 64-column (gate block, up block) pairs
 #pragma unroll 1
@@ -227,6 +250,70 @@ static int launch_gemm(const void* A, int64_t lda, const void* B, int64_t ldb, c
 
 int gemm_bf16_pair(const void* A, int64_t lda, const void* B, int64_t ldb, int b_layout, const GemmParams& p, cudaStream_t stream);
 
+// strided-batched launch of the one-CTA 128 x 128 kernel: 3-D tensor maps (dim2 = problem index)
+template <bool B_MN, bool A_MN>
+static int launch_gemm_batched(const void* A, int64_t lda, int64_t sa, const void* B, int64_t ldb, int64_t sb, const GemmParams& p,
+                               cudaStream_t stream) {
+  constexpr int BN = 128;
+  using Cfg = GemmCfg<BN>;
+  CUtensorMap ta, tb;
+  const uint64_t nb = uint64_t(p.batch);
+  if (!A_MN) {   // A: [batch][M][K], box 64 (k) x 128 (m)
+    if (int e = make_tmap_3d_bf16(&ta, A, uint64_t(p.K), uint64_t(p.M), nb, uint64_t(lda), uint64_t(sa), 64, BM)) return e;
+  } else {       // A^T stored: [batch][K][M], box 64 (m) x 64 (k)
+    if (int e = make_tmap_3d_bf16(&ta, A, uint64_t(p.M), uint64_t(p.K), nb, uint64_t(lda), uint64_t(sa), 64, BK)) return e;
+  }
+  if (!B_MN) {
+    if (int e = make_tmap_3d_bf16(&tb, B, uint64_t(p.K), uint64_t(p.N), nb, uint64_t(ldb), uint64_t(sb), 64, BN)) return e;
+  } else {
+    if (int e = make_tmap_3d_bf16(&tb, B, uint64_t(p.N), uint64_t(p.K), nb, uint64_t(ldb), uint64_t(sb), 64, BK)) return e;
+  }
+  auto kern = gemm_bf16_kernel<BN, B_MN, A_MN, true>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t ce = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    if (ce != cudaSuccess) return set_error(LRP_ERR_CUDA, cudaGetErrorString(ce));
+    attr_done = true;
+  }
+  const int64_t num_tiles = int64_t((p.M + BM - 1) / BM) * ((p.N + BN - 1) / BN) * p.batch;
+  const int grid = num_tiles < sm_count() ? int(num_tiles) : sm_count();
+  kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(ta, tb, p);
+  LRP_CHECK_LAUNCH();
+  return LRP_OK;
+}
+
+int gemm_bf16_batched(const void* A, int64_t lda, int64_t stride_a, int a_layout, const void* B, int64_t ldb, int64_t stride_b,
+                      int b_layout, int batch, int M, int N, int K, const lrp_epilogue_t* epi, int64_t stride_c, cudaStream_t stream) {
+  if (batch <= 0 || M <= 0 || N <= 0 || K <= 0) return set_error(LRP_ERR_ARG, "gemm_batched: empty problem");
+  if ((N % 8) != 0 || (K % 8) != 0 || (lda % 8) != 0 || (ldb % 8) != 0 || (stride_a % 8) != 0 || (stride_b % 8) != 0 ||
+      (a_layout != 0 && (M % 8) != 0))
+    return set_error(LRP_ERR_ARG, "gemm_batched: N, K, leading dimensions and batch strides must be multiples of 8");
+  if ((reinterpret_cast<uintptr_t>(A) & 15) || (reinterpret_cast<uintptr_t>(B) & 15))
+    return set_error(LRP_ERR_ARG, "gemm_batched: A/B must be 16-byte aligned");
+  if (epi == nullptr || epi->out == nullptr || epi->gated_gu != nullptr || epi->act_out != nullptr || (epi->ldc % 8) != 0)
+    return set_error(LRP_ERR_ARG, "gemm_batched: needs a plain epilogue with an output");
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  p.M = M; p.N = N; p.K = K;
+  p.out = epi->out;
+  p.shadow = reinterpret_cast<__nv_bfloat16*>(epi->shadow_bf16);
+  p.resid = epi->resid_f32;
+  p.rowscale = epi->rowscale;
+  p.colscale = epi->colscale;
+  p.bias = epi->bias;
+  p.alpha = epi->alpha;
+  p.ldc = epi->ldc;
+  p.out_is_f32 = epi->out_is_f32;
+  p.group_m = 16;
+  p.batch = batch;
+  p.batch_stride_c = stride_c;
+  if (a_layout == 0)
+    return b_layout == 0 ? launch_gemm_batched<false, false>(A, lda, stride_a, B, ldb, stride_b, p, stream)
+                         : launch_gemm_batched<true, false>(A, lda, stride_a, B, ldb, stride_b, p, stream);
+  return b_layout == 0 ? launch_gemm_batched<false, true>(A, lda, stride_a, B, ldb, stride_b, p, stream)
+                       : launch_gemm_batched<true, true>(A, lda, stride_a, B, ldb, stride_b, p, stream);
+}
+
 int gemm_bf16(const void* A, int64_t lda, const void* B, int64_t ldb, int b_layout, int M, int N, int K,
               const lrp_epilogue_t* epi, int force_bn, cudaStream_t stream) {
   if (M <= 0 || N <= 0 || K <= 0) return set_error(LRP_ERR_ARG, "gemm: empty problem");
@@ -239,6 +326,8 @@ int gemm_bf16(const void* A, int64_t lda, const void* B, int64_t ldb, int b_layo
     return set_error(LRP_ERR_ARG, "gemm: fused gated backward needs gated_out and a valid activation");
   if ((epi->ldc % 8) != 0) return set_error(LRP_ERR_ARG, "gemm: ldc must be a multiple of 8");
   GemmParams p;
+  memset(&p, 0, sizeof(p));
+  p.batch = 1;
   p.M = M; p.N = N; p.K = K;
   p.out = epi->out;
   p.shadow = reinterpret_cast<__nv_bfloat16*>(epi->shadow_bf16);

@@ -25,6 +25,9 @@ int make_tmap_3d_f32(CUtensorMap* out, const void* base, uint64_t dim0, uint64_t
 int gemm_bf16(const void* A, int64_t lda, const void* B, int64_t ldb, int b_layout, int M, int N, int K,
               const lrp_epilogue_t* epi, int force_bn, cudaStream_t stream);
 
+int gemm_bf16_batched(const void* A, int64_t lda, int64_t stride_a, int a_layout, const void* B, int64_t ldb, int64_t stride_b,
+                      int b_layout, int batch, int M, int N, int K, const lrp_epilogue_t* epi, int64_t stride_c, cudaStream_t stream);
+
 int attn_bwd_v2(const void* q, const void* k, const void* v, int64_t ldq, int64_t ldk, int64_t ldv, const void* d_o,
                 const float* lse, const float* delta, void* dq, void* dk, void* dv, int64_t lddq, int64_t lddk, int64_t lddv,
                 const int32_t* kv_range, int B, int S, int H, int Hkv, int D, float scale, int causal, int window, float q_div,

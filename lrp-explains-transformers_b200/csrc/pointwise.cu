@@ -443,8 +443,8 @@ __global__ void __launch_bounds__(1024) argmax_rows_kernel(const float* __restri
   }
 }
 
-template <typename T>
-__global__ void __launch_bounds__(256) gxi_reduce_kernel(const T* __restrict__ x, const T* __restrict__ g,
+template <typename T, typename TG = T>
+__global__ void __launch_bounds__(256) gxi_reduce_kernel(const T* __restrict__ x, const TG* __restrict__ g,
                                                          float* __restrict__ rel, int64_t Tn, int d) {
   // one warp per row
   const int64_t row = blockIdx.x * int64_t(blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -541,6 +541,29 @@ __global__ void __launch_bounds__(256) softmax_dt_bwd_kernel(const T* __restrict
     if (xv == -INFINITY) xv = 0.f;
     stf(out, i, xv * (ldf(r, i) - ldf(p, i) * s));
   }
+}
+// soft-max forward over the last dimension, p = softmax(x / temperature) (functional.py:293-306); fp32 arithmetic, one warp per
+// row, -inf inputs give 0, a row of only -inf gives zeros
+template <typename T>
+__global__ void __launch_bounds__(256) softmax_fwd_kernel(const T* __restrict__ x, T* __restrict__ out, int64_t rows, int cols,
+                                                          float inv_temp) {
+  const int64_t row = blockIdx.x * int64_t(blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31;
+  const int64_t base = row * cols;
+  float m = -INFINITY;
+  for (int c = lane; c < cols; c += 32) m = fmaxf(m, ldf(x, base + c) * inv_temp);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if (m == -INFINITY) {
+    for (int c = lane; c < cols; c += 32) stf(out, base + c, 0.f);
+    return;
+  }
+  float s = 0.f;
+  for (int c = lane; c < cols; c += 32) s += expf(ldf(x, base + c) * inv_temp - m);
+  s = warp_sum(s);
+  const float inv = 1.f / s;
+  for (int c = lane; c < cols; c += 32) stf(out, base + c, expf(ldf(x, base + c) * inv_temp - m) * inv);
 }
 // epsilon rule for a + b (functional.py:439-459): s = r / (a + b + eps); ra = s*a; rb = s*b
 template <typename T>
@@ -784,6 +807,13 @@ int lrp_gxi_reduce_bf16(const void* x, const void* g, float* rel, int T, int d, 
   return LRP_OK;
 }
 
+int lrp_gxi_reduce_mixed(const void* x_bf16, const float* g, float* rel, int T, int d, void* stream) {
+  if (T <= 0 || d <= 0 || (d % 8) != 0) return set_error(LRP_ERR_ARG, "gxi_reduce: d must be a positive multiple of 8");
+  gxi_reduce_kernel<bf16, float><<<(T + 7) / 8, 256, 0, static_cast<cudaStream_t>(stream)>>>((const bf16*)x_bf16, g, rel, T, d);
+  LRP_CHECK_LAUNCH();
+  return LRP_OK;
+}
+
 int lrp_cast_f32_to_bf16(const float* in, void* out, int64_t n, void* stream) {
   if (n <= 0 || (n % 8) != 0) return set_error(LRP_ERR_ARG, "cast: n must be a positive multiple of 8");
   cast_f32_bf16_kernel<<<grid_for(n / 8, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(in, (bf16*)out, n / 8);
@@ -831,6 +861,15 @@ int lrp_softmax_dt_bwd(const void* x, const void* p, const void* r, void* out, i
   const unsigned g = unsigned((rows + 7) / 8);
   if (is_f32) softmax_dt_bwd_kernel<float><<<g, 256, 0, st>>>((const float*)x, (const float*)p, (const float*)r, (float*)out, rows, cols);
   else softmax_dt_bwd_kernel<bf16><<<g, 256, 0, st>>>((const bf16*)x, (const bf16*)p, (const bf16*)r, (bf16*)out, rows, cols);
+  LRP_CHECK_LAUNCH();
+  return LRP_OK;
+}
+int lrp_softmax_fwd(const void* x, void* out, int64_t rows, int cols, float temperature, int is_f32, void* stream) {
+  if (rows <= 0 || cols <= 0 || !(temperature != 0.f)) return set_error(LRP_ERR_ARG, "softmax_fwd: empty tensor or zero temperature");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const unsigned g = unsigned((rows + 7) / 8);
+  if (is_f32) softmax_fwd_kernel<float><<<g, 256, 0, st>>>((const float*)x, (float*)out, rows, cols, 1.f / temperature);
+  else softmax_fwd_kernel<bf16><<<g, 256, 0, st>>>((const bf16*)x, (bf16*)out, rows, cols, 1.f / temperature);
   LRP_CHECK_LAUNCH();
   return LRP_OK;
 }

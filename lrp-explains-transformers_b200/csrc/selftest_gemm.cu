@@ -253,6 +253,17 @@ int main(int argc, char** argv) {
   bool perf = argc > 1 && !strcmp(argv[1], "--perf");
   if (lrp_check_device() != 0) { printf("no device: %s\n", lrp_last_error()); return 1; }
   printf("lrp_version=%d\n", lrp_version());
+  if (argc > 1 && !strcmp(argv[1], "--sweep")) {
+    // every GEMM shape of one Llama-3-8B layer (forward NT, LRP dgrad NN) at the token counts of micro-batch 8 / 4 / 2,
+    // CTA-pair kernel (bn=2) vs one-CTA 128x256 kernel (bn=256): the table behind the per-shape dispatch in gemm_sm100.cu
+    const int fwd[][2] = {{6144, 4096}, {4096, 4096}, {28672, 4096}, {4096, 14336}};
+    const int bwd[][2] = {{14336, 4096}, {4096, 28672}, {4096, 4096}, {4096, 6144}};
+    for (int M : {16384, 8192, 4096}) {
+      for (auto& s : fwd) for (int bn : {2, 256}) perf_case(M, s[0], s[1], 0, bn, 0);
+      for (auto& s : bwd) for (int bn : {2, 256}) perf_case(M, s[0], s[1], 1, bn, 1);
+    }
+    return 0;
+  }
   const int shapes[][3] = {{128, 128, 64}, {128, 256, 128}, {256, 256, 256}, {300, 520, 200}, {1000, 1024, 4096},
                            {64, 2048, 512}};
   for (auto& s : shapes)

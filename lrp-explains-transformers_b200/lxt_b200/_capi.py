@@ -48,6 +48,7 @@ SIGNATURES = {
     "lrp_check_device": (_i, []),
     "lrp_launch_count": (_i64, []),
     "lrp_gemm_bf16": (_i, [_vp, _i64, _vp, _i64, _i, _i, _i, _i, _EP, _i, _vp]),
+    "lrp_gemm_bf16_batched": (_i, [_vp, _i64, _i64, _i, _vp, _i64, _i64, _i, _i, _i, _i, _i, _EP, _i64, _vp]),
     "lrp_linear_fwd": (_i, [_vp, _i64, _vp, _i64, _i, _i, _i, _EP, _vp]),
     "lrp_linear_dgrad_fused": (_i, [_vp, _i64, _vp, _i64, _i, _i, _i, _EP, _vp]),
     "lrp_linear_eps_bwd": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _i, _i, _i, _f, _vp]),
@@ -73,6 +74,7 @@ SIGNATURES = {
     "lrp_argmax_rows": (_i, [_vp, _vp, _vp, _i, _i, _vp]),
     "lrp_gxi_reduce": (_i, [_vp, _vp, _vp, _i, _i, _vp]),
     "lrp_gxi_reduce_bf16": (_i, [_vp, _vp, _vp, _i, _i, _vp]),
+    "lrp_gxi_reduce_mixed": (_i, [_vp, _vp, _vp, _i, _i, _vp]),
     "lrp_cast_f32_to_bf16": (_i, [_vp, _vp, _i64, _vp]),
     "lrp_eps_div": (_i, [_vp, _vp, _vp, _i64, _f, _f, _i, _vp]),
     "lrp_mul": (_i, [_vp, _vp, _vp, _i64, _f, _i, _vp]),
@@ -80,6 +82,7 @@ SIGNATURES = {
     "lrp_identity_rule_bwd": (_i, [_vp, _vp, _vp, _vp, _i64, _i, _vp]),
     "lrp_softmax_dt_bwd": (_i, [_vp, _vp, _vp, _vp, _i64, _i, _i, _vp]),
     "lrp_add2_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _i64, _f, _i, _vp]),
+    "lrp_softmax_fwd": (_i, [_vp, _vp, _i64, _i, _f, _i, _vp]),
     # validation-precision mode (fp32 activations)
     "lrp_rmsnorm_fwd_t": (_i, [_vp, _i, _vp, _f, _f, _vp, _i, _vp, _i, _i, _vp]),
     "lrp_rmsnorm_bwd_t": (_i, [_vp, _i, _vp, _f, _vp, _vp, _i, _i, _i, _i, _vp]),

@@ -131,8 +131,9 @@ class _LinearFn(Function):
         x2 = _as_2d(x)
         w = weight.detach()
         w = w if w.is_contiguous() else w.contiguous()
+        ctx.split = _wsplit(weight, x)
         y = torch.empty((x2.shape[0], w.shape[0]), dtype=x.dtype, device=x.device)
-        ops.linear_fwd(x2, w, y, bias=None if bias is None else bias.detach().float().contiguous())
+        ops.linear_fwd(x2, w, y, bias=None if bias is None else bias.detach().float().contiguous(), b_split=ctx.split)
         ctx.save_for_backward(w)
         return y.view(*x.shape[:-1], w.shape[0])
 
@@ -141,8 +142,15 @@ class _LinearFn(Function):
         (w,) = ctx.saved_tensors
         g2 = _as_2d(gy)
         gx = torch.empty((g2.shape[0], w.shape[1]), dtype=gy.dtype, device=gy.device)
-        ops.linear_dgrad(g2, w, gx)
+        ops.linear_dgrad(g2, w, gx, b_split=ctx.split)
         return gx.view(*gy.shape[:-1], w.shape[1]), None, None
+
+
+def _wsplit(weight: torch.Tensor, x: torch.Tensor):
+    """validation precision with fp32 weights: the (hi, lo) bf16 split memoised on the Parameter object; None otherwise"""
+    if x.dtype == torch.float32 and weight.dtype == torch.float32 and weight.is_contiguous():
+        return ops.weight_split(weight)
+    return None
 
 
 def _linear_ok(x: torch.Tensor, weight: torch.Tensor) -> bool:
@@ -169,14 +177,15 @@ class _GatedMLPFn(Function):
         _need_bf16_cuda(x, "gated_mlp_forward")
         x2 = _as_2d(x)
         T, I = x2.shape[0], wg.shape[0]
+        ctx.splits = sg, su, sd = [_wsplit(w, x) for w in (wg, wu, wd)]
         wg, wu, wd = (w.detach().contiguous() for w in (wg, wu, wd))
         f32 = lambda b: None if b is None else b.detach().float().contiguous()
         gu = torch.empty((T, 2 * I), dtype=x.dtype, device=x.device)
-        ops.linear_fwd(x2, wg, gu[:, :I], bias=f32(bg))
-        ops.linear_fwd(x2, wu, gu[:, I:], bias=f32(bu))
+        ops.linear_fwd(x2, wg, gu[:, :I], bias=f32(bg), b_split=sg)
+        ops.linear_fwd(x2, wu, gu[:, I:], bias=f32(bu), b_split=su)
         a = ops.gated_act_fwd(gu, act)
         y = torch.empty((T, wd.shape[0]), dtype=x.dtype, device=x.device)
-        ops.linear_fwd(a, wd, y, bias=f32(bd))
+        ops.linear_fwd(a, wd, y, bias=f32(bd), b_split=sd)
         ctx.save_for_backward(gu, wg, wu, wd)
         ctx.act, ctx.cp = act, cp
         return y.view(*x.shape[:-1], wd.shape[0])
@@ -186,13 +195,14 @@ class _GatedMLPFn(Function):
         gu, wg, wu, wd = ctx.saved_tensors
         T, I = gu.shape[0], wg.shape[0]
         g2 = _as_2d(gy)
+        sg, su, sd = ctx.splits
         ga = torch.empty((T, I), dtype=gu.dtype, device=gy.device)
-        ops.linear_dgrad(g2, wd, ga)
+        ops.linear_dgrad(g2, wd, ga, b_split=sd)
         ggu = ops.gated_act_bwd(ga, gu, ctx.act, cp=ctx.cp)
         acc = torch.empty((T, wg.shape[1]), dtype=torch.float32, device=gy.device)
-        ops.linear_dgrad(ggu[:, :I], wg, acc)
+        ops.linear_dgrad(ggu[:, :I], wg, acc, b_split=sg)
         if gu.dtype == torch.float32:   # validation precision: the fp32 accumulator is the result
-            ops.linear_dgrad(ggu[:, I:], wu, acc, resid=acc)
+            ops.linear_dgrad(ggu[:, I:], wu, acc, resid=acc, b_split=su)
             gx = acc
         else:
             gx = torch.empty((T, wg.shape[1]), dtype=torch.bfloat16, device=gy.device)
@@ -263,10 +273,11 @@ def _kv_range_from_mask(mask, B, S, causal, window):
     LRP_VERIFY_MASKS=1 re-expands the range and compares it with the mask (one host sync; raises on custom masks)."""
     if mask.dim() != 4 or mask.shape[-1] != S or mask.shape[-2] != S or mask.shape[1] != 1 or mask.shape[0] not in (1, B):
         raise LrpError(f"attention_mask of shape {tuple(mask.shape)} is not supported (expected [B,1,S,S] with S = {S})")
-    key = (mask.data_ptr(), tuple(mask.shape), mask.dtype, mask._version, bool(causal), int(window))
+    # memoised per mask OBJECT (weak reference + version; never by address: freed masks' storage is handed out again)
+    key = (id(mask), bool(causal), int(window))
     hit = _KV_RANGE_CACHE.get(key)
-    if hit is not None:
-        return hit
+    if hit is not None and hit[0]() is mask and hit[1] == mask._version:
+        return hit[2]
     allowed = mask[:, 0] if mask.dtype == torch.bool else (mask[:, 0] == 0)
     valid = allowed.any(dim=-2)                                   # [B or 1, S]
     idx = torch.arange(S, device=mask.device)
@@ -288,7 +299,8 @@ def _kv_range_from_mask(mask, B, S, causal, window):
             raise LrpError("attention_mask is not causal(+window) x contiguous key padding; custom masks are not supported")
     if len(_KV_RANGE_CACHE) > 8:
         _KV_RANGE_CACHE.clear()
-    _KV_RANGE_CACHE[key] = kv_range
+    import weakref
+    _KV_RANGE_CACHE[key] = (weakref.ref(mask), mask._version, kv_range)
     return kv_range
 
 

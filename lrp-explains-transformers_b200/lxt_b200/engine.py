@@ -359,7 +359,9 @@ class LlamaAttnLRPEngine:
         return self._rope_cache[key]
 
     # ------------------------------------------------------------------ one layer
-    def _layer_fwd(self, lw, st: _LayerStore, h, ws, B, S, l: int = 0):
+    def _layer_fwd(self, lw, st: _LayerStore, h, ws, B, S, l: int = 0, h_copy=None):
+        """h_copy: optional bf16 [T,d] buffer that receives a copy of this layer's OUTPUT residual stream, written by the last
+        residual epilogue of the layer (the latent-relevance trace needs the layer outputs in the backward sweep)"""
         m = self.dims
         T = B * S
         cos, sin = self._rope(S, l)
@@ -400,8 +402,14 @@ class LlamaAttnLRPEngine:
             ops.linear_fwd(ws["a"], lw["wd"], ws["y"])
             C.check(lib.lrp_rmsnorm_fwd_residual_t(ws["y"].data_ptr(), f, lw["ln_post_ff"].data_ptr(), off, m.eps, h.data_ptr(),
                                                    st.rstd_pf.data_ptr(), T, m.d, ops._stream()), "rmsnorm_fwd_residual")
+            if h_copy is not None:
+                h_copy.copy_(h)
+        elif h_copy is not None and not self.hp:
+            ops.linear_fwd(ws["a"], lw["wd"], h, resid=h, shadow=h_copy)   # bf16 copy of the layer output from the GEMM epilogue
         else:
             ops.linear_fwd(ws["a"], lw["wd"], h, resid=h)
+            if h_copy is not None:
+                h_copy.copy_(h)
 
     def _layer_bwd(self, lw, st: _LayerStore, ws, B, S, l: int = 0):
         m = self.dims
@@ -478,11 +486,12 @@ class LlamaAttnLRPEngine:
 
         seg = self._segment_len()
         if self.store_policy == "all":
-            h_outs = [] if trace else None
+            # latent trace: the layer outputs are kept as the bf16 shadow the down-projection's residual epilogue writes anyway
+            # (no extra pass over the residual stream, half the bytes of an fp32 clone; fp32 in validation mode)
+            h_outs = [torch.empty((T, m.d), dtype=torch.float32 if self.hp else torch.bfloat16, device=self.device)
+                      for _ in range(m.L)] if trace else None
             for l, lw in enumerate(self.layers):
-                self._layer_fwd(lw, ws["stores"][l], h, ws, B, S, l)
-                if trace:
-                    h_outs.append(h.clone())
+                self._layer_fwd(lw, ws["stores"][l], h, ws, B, S, l, h_copy=h_outs[l] if trace else None)
         else:
             for l, lw in enumerate(self.layers):
                 if l % seg == 0:

@@ -3,9 +3,10 @@
 
 All arithmetic of the backward rules runs in liblrp_b200.so kernels:
   linear_epsilon   one fused tcgen05 launch  (z, R/(z+eps), contraction with W, * x)
-  matmul           eps+uniform rule: eps_div kernel + two tcgen05 GEMMs per batch slice + mul kernel
-  softmax          Deep-Taylor rule kernel;  add2 / mul2 / rms_norm_identity element-wise kernels
-CUDA tensors only (bf16 or fp32; GEMM operands are consumed as bf16).
+  matmul           eps+uniform rule: eps_div kernel + two strided-batched tcgen05 launches (all [B*H] slices at once, a^T
+                   consumed in place through an MN-major descriptor) + mul kernels; fp32 operands: two-term bf16 split
+  softmax          forward kernel + Deep-Taylor rule kernel;  add2 / mul2 / rms_norm_identity element-wise kernels
+CUDA tensors only (bf16 or fp32).
 """
 from __future__ import annotations
 
@@ -77,21 +78,27 @@ class linear_epsilon_fn(Function):
         return r_in.to(inputs.dtype).view(inputs.shape), None, None, None
 
 
-def _bmm_kernel(a3, b3, b_layout, mul=None):
-    """per-slice tcgen05 GEMMs over the leading batch dim; a3 [G,M,K]; b3 [G,N,K] (layout 0) or [G,K,N] (layout 1)"""
-    G, M0, _ = a3.shape
+def _bmm_kernel(a3, b3, b_layout, a_layout=0):
+    """ONE strided-batched tcgen05 launch over the leading batch dim (three for fp32 operands: two-term bf16 split).
+    a3 [G,M,K] (a_layout 0) or [G,K,M] (a_layout 1, the stored tensor is a^T); b3 [G,N,K] (b_layout 0) or [G,K,N] (b_layout 1).
+    Returns fp32 [G,M,N].  Extents that are not multiples of 8 are zero-padded (the products are unchanged)."""
+    G = a3.shape[0]
+    M0 = a3.shape[1] if a_layout == 0 else a3.shape[2]
     N0 = b3.shape[1] if b_layout == 0 else b3.shape[2]
-    ab = ops.pad_to8(a3.to(torch.bfloat16), [1, 2]).contiguous()   # zero padding leaves the products unchanged
-    bb = ops.pad_to8(b3.to(torch.bfloat16), [1, 2]).contiguous()
-    M = ab.shape[1]
+    dt = torch.float32 if torch.float32 in (a3.dtype, b3.dtype) else torch.bfloat16
+    ab = ops.pad_to8(a3.to(dt), [1, 2]).contiguous()
+    bb = ops.pad_to8(b3.to(dt), [1, 2]).contiguous()
+    M = ab.shape[1] if a_layout == 0 else ab.shape[2]
     N = bb.shape[1] if b_layout == 0 else bb.shape[2]
     out = torch.empty((G, M, N), dtype=torch.float32, device=a3.device)
-    for g in range(G):
-        ops.gemm(ab[g], bb[g], out[g], b_layout=b_layout)
+    ops.gemm_batched(ab, bb, out, a_layout=a_layout, b_layout=b_layout)
     return out[:, :M0, :N0] if (M, N) != (M0, N0) else out
 
 
 class matmul_fn(Function):
+    """epsilon + uniform rule for torch.matmul (reference lxt/explicit/functional.py:367-408) at any batch shape, e.g. the
+    [B,H,S,S] attention products: forward one batched launch, backward eps_div + two batched launches + two multiplies."""
+
     @staticmethod
     def forward(ctx, input_a, input_b, inplace=False, epsilon=1e-6):
         if not input_a.is_cuda:
@@ -115,8 +122,8 @@ class matmul_fn(Function):
         s3 = s.reshape(-1, M, N)
         a3 = a.reshape(-1, M, K)
         b3 = b.expand(*a.shape[:-2], K, N).reshape(-1, K, N)
-        ra = ops.mul(_bmm_kernel(s3, b3, 0).to(a.dtype).view(a.shape), a)                   # (s b^T) * a
-        rb = _bmm_kernel(a3.transpose(1, 2).contiguous(), s3, 1).to(b.dtype)                # (a^T s)
+        ra = ops.mul(_bmm_kernel(s3, b3, 0).to(a.dtype).view(a.shape), a)                   # (s b^T) * a : b3 is [G, N_out=K, contraction N]
+        rb = _bmm_kernel(a3, s3, 1, a_layout=1).to(b.dtype)                                 # (a^T s): a3 consumed as the stored transpose
         rb = ops.mul(rb.view(*a.shape[:-2], K, N), b.expand(*a.shape[:-2], K, N))
         if rb.shape != b.shape:
             rb = rb.sum_to_size(b.shape)
@@ -126,10 +133,19 @@ class matmul_fn(Function):
 class softmax_fn(Function):
     @staticmethod
     def forward(ctx, inputs, dim, dtype=None, temperature=1.0, inplace=False):
+        if not inputs.is_cuda:
+            raise LrpError("softmax: CUDA tensors only (no CPU fallback)")
         if dtype is not None:
             inputs = inputs.to(dtype)
-        inputs = inputs / temperature
-        outputs = F.softmax(inputs, dim=dim, dtype=dtype)
+        if inputs.dtype not in (torch.float32, torch.bfloat16):
+            inputs = inputs.float()
+        if temperature != 1.0:
+            inputs = ops.scale(inputs, 1.0 / temperature)      # the rule is stated on x / temperature (functional.py:297-299)
+        d = dim if dim >= 0 else inputs.dim() + dim
+        if d != inputs.dim() - 1:
+            outputs = ops.softmax_fwd(inputs.transpose(d, -1).contiguous()).transpose(d, -1)
+        else:
+            outputs = ops.softmax_fwd(inputs)
         ctx.save_for_backward(inputs, outputs)
         ctx.dim = dim
         return outputs

@@ -92,21 +92,22 @@ def split_bf16x2(x: torch.Tensor):
     return hi, lo
 
 
-_WSPLIT = {}
+def weight_split(w: torch.Tensor):
+    """(hi, lo) bf16 split of an fp32 weight, memoised ON the tensor object (a module's Parameter): it lives and dies with that
+    object and is invalidated by in-place updates.  (Never keyed by address: the caching allocator hands the storage of a
+    freed model to the next one.)"""
+    ent = getattr(w, "_lrp_split", None)
+    if ent is not None and ent[0] == w._version and ent[1].shape == w.shape:
+        return ent[1], ent[2]
+    hi, lo = split_bf16x2(w.detach())
+    try:
+        w._lrp_split = (w._version, hi, lo)
+    except Exception:   # pragma: no cover  (tensor subclasses without a __dict__)
+        pass
+    return hi, lo
 
 
-def _split_weight_cached(w: torch.Tensor):
-    """(hi, lo) bf16 split of an fp32 weight, cached per storage (weights are frozen on this path)"""
-    key = (w.data_ptr(), tuple(w.shape), tuple(w.stride()), w._version)
-    ent = _WSPLIT.get(key)
-    if ent is None:
-        if len(_WSPLIT) > 4096:
-            _WSPLIT.clear()
-        ent = _WSPLIT[key] = split_bf16x2(w.detach())
-    return ent
-
-
-def gemm(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor, *, b_layout: int, tile_n: int = 0, **epi) -> torch.Tensor:
+def gemm(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor, *, b_layout: int, tile_n: int = 0, b_split=None, **epi) -> torch.Tensor:
     """out = epilogue(a @ b.T) for b_layout 0 (b is [N,K]) or epilogue(a @ b) for b_layout 1 (b is [K,N]).
     An fp32 `a` selects the validation-precision form: a = hi + lo (two bf16 terms), out = epilogue(hi b) then
     out += alpha * rowscale * colscale * (lo b), both on the same bf16 tcgen05 kernel with fp32 accumulation; `out` must be fp32."""
@@ -118,7 +119,7 @@ def gemm(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor, *, b_layout: int, 
         hi, lo = split_bf16x2(a)
         epi2 = {k: v for k, v in epi.items() if k in ("rowscale", "colscale", "alpha")}
         if b.dtype == torch.float32:   # fp32 weights (an fp32 HF model): W = Wh + Wl as well; the lo*lo term (2^-18) is dropped
-            bh, bl = _split_weight_cached(b)
+            bh, bl = b_split if b_split is not None else split_bf16x2(b)
             gemm(hi, bh, out, b_layout=b_layout, tile_n=tile_n, **epi)
             gemm(lo, bh, out, b_layout=b_layout, tile_n=tile_n, resid=out, **epi2)
             return gemm(hi, bl, out, b_layout=b_layout, tile_n=tile_n, resid=out, **epi2)
@@ -143,6 +144,41 @@ def gemm(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor, *, b_layout: int, 
     if prof is not None:
         ev1.record()
         prof.append((2.0 * M * N * K, ev0, ev1))
+    return out
+
+
+def gemm_batched(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor, *, a_layout: int = 0, b_layout: int = 0) -> torch.Tensor:
+    """One launch for G independent products.  a [G,M,K] (a_layout 0) or [G,K,M] (a_layout 1: the stored tensor is A^T);
+    b [G,N,K] (b_layout 0) or [G,K,N] (b_layout 1); out [G,M,N] bf16 or fp32, all contiguous.
+    fp32 operands select validation precision: both sides are split into two bf16 terms and the three significant products
+    (hi*hi, lo*hi, hi*lo) accumulate in fp32 on the same kernel."""
+    if a.dim() != 3 or b.dim() != 3 or out.dim() != 3 or not (a.is_contiguous() and b.is_contiguous() and out.is_contiguous()):
+        raise _capi.LrpError("gemm_batched: contiguous 3-D tensors expected")
+    G = a.shape[0]
+    M, K = (a.shape[1], a.shape[2]) if a_layout == 0 else (a.shape[2], a.shape[1])
+    N = b.shape[1] if b_layout == 0 else b.shape[2]
+    if b.shape[0] != G or (b.shape[2] if b_layout == 0 else b.shape[1]) != K or tuple(out.shape) != (G, M, N):
+        raise _capi.LrpError(f"gemm_batched: shapes {tuple(a.shape)}, {tuple(b.shape)} -> {tuple(out.shape)} do not match")
+    if a.dtype == torch.float32 or b.dtype == torch.float32:
+        if out.dtype != torch.float32:
+            raise _capi.LrpError("gemm_batched: fp32 operands need an fp32 output")
+        ah, al = split_bf16x2(a.float())
+        bh, bl = split_bf16x2(b.float())
+        _gemm_batched_bf16(ah, bh, out, a_layout, b_layout, False)
+        _gemm_batched_bf16(al, bh, out, a_layout, b_layout, True)
+        return _gemm_batched_bf16(ah, bl, out, a_layout, b_layout, True)
+    return _gemm_batched_bf16(a, b, out, a_layout, b_layout, False)
+
+
+def _gemm_batched_bf16(a, b, out, a_layout, b_layout, accumulate):
+    _need(a, torch.bfloat16, "a")
+    _need(b, torch.bfloat16, "b")
+    G = a.shape[0]
+    M, K = (a.shape[1], a.shape[2]) if a_layout == 0 else (a.shape[2], a.shape[1])
+    N = b.shape[1] if b_layout == 0 else b.shape[2]
+    e = make_epilogue(out[0], resid=out[0] if accumulate else None)
+    check(_capi.lib().lrp_gemm_bf16_batched(a.data_ptr(), a.stride(1), a.stride(0), a_layout, b.data_ptr(), b.stride(1), b.stride(0),
+                                            b_layout, G, M, N, K, C.byref(e), out.stride(0), _stream()), "lrp_gemm_bf16_batched")
     return out
 
 
@@ -176,7 +212,7 @@ def linear_dgrad_gated_bwd(gy: torch.Tensor, w: torch.Tensor, gu: torch.Tensor, 
 
 
 def linear_fwd(x: torch.Tensor, w: torch.Tensor, out: torch.Tensor, **epi) -> torch.Tensor:
-    """y = x W^T (+ fused epilogue).  x [T,K] bf16, w [N,K] bf16."""
+    """y = x W^T (+ fused epilogue).  x [T,K] bf16, w [N,K] bf16  (fp32 x / w: validation precision, see `gemm`)."""
     return gemm(x, w, out, b_layout=0, **epi)
 
 
@@ -408,11 +444,14 @@ def argmax_rows(logits: torch.Tensor):
 
 def gxi_reduce(x: torch.Tensor, g: torch.Tensor) -> torch.Tensor:
     """relevance[t] = sum_d x[t,d]*g[t,d]; x,g both fp32 or both bf16, contiguous [T,d]"""
-    if x.dtype != g.dtype or x.shape != g.shape or not (x.is_contiguous() and g.is_contiguous()):
-        raise _capi.LrpError("gxi_reduce: x and g must be contiguous tensors of identical dtype/shape")
+    mixed = x.dtype == torch.bfloat16 and g.dtype == torch.float32
+    if (x.dtype != g.dtype and not mixed) or x.shape != g.shape or not (x.is_contiguous() and g.is_contiguous()):
+        raise _capi.LrpError("gxi_reduce: x and g must be contiguous tensors of identical shape and dtype (or bf16 x with fp32 g)")
     T, d = x.shape
     rel = torch.empty((T,), dtype=torch.float32, device=x.device)
-    if x.dtype == torch.float32:
+    if x.dtype == torch.bfloat16 and g.dtype == torch.float32:
+        check(_capi.lib().lrp_gxi_reduce_mixed(x.data_ptr(), g.data_ptr(), rel.data_ptr(), T, d, _stream()), "lrp_gxi_reduce_mixed")
+    elif x.dtype == torch.float32:
         check(_capi.lib().lrp_gxi_reduce(x.data_ptr(), g.data_ptr(), rel.data_ptr(), T, d, _stream()), "lrp_gxi_reduce")
     else:
         _need(x, torch.bfloat16, "x")
@@ -482,6 +521,16 @@ def softmax_dt_bwd(x: torch.Tensor, p: torch.Tensor, r: torch.Tensor) -> torch.T
     out = torch.empty_like(x)
     check(_capi.lib().lrp_softmax_dt_bwd(x.data_ptr(), p.data_ptr(), r.data_ptr(), out.data_ptr(), x.numel() // cols, cols, f32,
                                          _stream()), "lrp_softmax_dt_bwd")
+    return out
+
+
+def softmax_fwd(x: torch.Tensor, temperature: float = 1.0) -> torch.Tensor:
+    """softmax(x / temperature) over the LAST dimension (fp32 arithmetic; bf16 or fp32 storage)"""
+    (x,), f32 = _ew_prepare(x)
+    cols = x.shape[-1]
+    out = torch.empty_like(x)
+    check(_capi.lib().lrp_softmax_fwd(x.data_ptr(), out.data_ptr(), x.numel() // cols, cols, float(temperature), f32, _stream()),
+          "lrp_softmax_fwd")
     return out
 
 

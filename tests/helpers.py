@@ -72,3 +72,16 @@ def vit_weight_fingerprint(model):
     sd = model.state_dict()
     keys = ["conv_proj.weight", "encoder.layers.encoder_layer_11.mlp.0.weight", "heads.head.weight"]
     return np.array([float(sd[k].double().abs().sum()) for k in keys])
+
+
+def build_hf(Model, cfg, dtype=torch.bfloat16):
+    """Construct an HF model the way `from_pretrained(torch_dtype=...)` does: parameters in `dtype`, RoPE `inv_freq` buffers in
+    fp32.  (`Model(cfg).to(torch.bfloat16)` also rounds the non-persistent inv_freq buffer to bf16, and HF computes RoPE from that
+    buffer: at position 2048 the angle of the fastest dimension is then off by radians — a property of that model object, which
+    both the reference and this repo reproduce faithfully, but not what the fp32 goldens / oracle compute.)"""
+    old = torch.get_default_dtype()
+    torch.set_default_dtype(dtype)
+    try:
+        return Model(cfg)
+    finally:
+        torch.set_default_dtype(old)

@@ -144,7 +144,8 @@ def test_engine_from_hf_reproduces_scaled_rope():
         hf = LlamaConfig(hidden_size=256, intermediate_size=512, num_hidden_layers=2, num_attention_heads=4, num_key_value_heads=2,
                          head_dim=64, vocab_size=256, rope_parameters=rope, max_position_embeddings=512, tie_word_embeddings=False)
         hf._attn_implementation = "sdpa"
-        model = LlamaForCausalLM(hf).to(torch.bfloat16).cuda().eval()
+        from helpers import build_hf
+        model = build_hf(LlamaForCausalLM, hf).cuda().eval()
         for p_ in model.parameters():
             p_.requires_grad_(False)
         ids = torch.randint(0, 256, (2, 200), generator=torch.Generator().manual_seed(3)).cuda()

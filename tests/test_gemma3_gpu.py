@@ -28,7 +28,8 @@ def test_patched_gemma3_matches_reference(name, head_dim):
                            query_pre_attn_scalar=head_dim, rms_norm_eps=1e-6, tie_word_embeddings=True)
     cfg._attn_implementation = "sdpa"
     assert list(z["layer_types"]) == cfg.layer_types and "full_attention" in cfg.layer_types
-    model = Gemma3ForCausalLM(cfg).to(torch.bfloat16)
+    from helpers import build_hf
+    model = build_hf(Gemma3ForCausalLM, cfg)
     model.load_state_dict({k[3:]: bf16_from_bits(v) for k, v in z.items() if k.startswith("sd_")}, strict=False)
     model = model.cuda().eval()
     for p in model.parameters():

@@ -192,3 +192,39 @@ def test_fused_gated_backward_epilogue_equals_unfused(ops, cp):
     s = torch.nn.functional.silu(gate)
     exp = torch.cat([torch.zeros_like(gate), ga32 * s], 1) if cp else torch.cat([(s / (gate + 1e-10)) * (ga32 / 2 * up), ga32 / 2 * s], 1)
     assert rel_l2(got.float(), exp) < 3e-3
+
+
+@pytest.mark.parametrize("shape", [(300, 512, 256), (4096, 28672 // 4, 1024), (257, 1152, 192)])
+@pytest.mark.parametrize("act", [0, 1])
+def test_gate_up_gemm_with_fused_activation_epilogue(shape, act):
+    """gate|up forward with a = act(gate) * up leaving the GEMM epilogue (interleaved 32-row blocks): gu and a must be
+    bit-identical to the unfused pair (plain GEMM, then lrp_gated_act_fwd on the stored bf16 values)."""
+    from lxt_b200 import ops
+    T, I, K = shape
+    g = torch.Generator(device="cuda").manual_seed(7)
+    x = torch.randn(T, K, generator=g, device="cuda").to(torch.bfloat16)
+    wg = (torch.randn(I, K, generator=g, device="cuda") * 0.05).to(torch.bfloat16)
+    wu = (torch.randn(I, K, generator=g, device="cuda") * 0.05).to(torch.bfloat16)
+    w_il = torch.stack([wg.view(I // 32, 32, K), wu.view(I // 32, 32, K)], 1).reshape(2 * I, K).contiguous()
+    gu_f = torch.empty(T, 2 * I, dtype=torch.bfloat16, device="cuda")
+    a_f = torch.empty(T, I, dtype=torch.bfloat16, device="cuda")
+    ops.linear_fwd(x, w_il, gu_f, act_out=a_f, act=act)
+    gu_u = torch.empty_like(gu_f)
+    ops.linear_fwd(x, w_il, gu_u)
+    a_u = ops.gated_act_fwd(gu_u, act, layout=1)
+    assert torch.equal(gu_f, gu_u)
+    assert torch.equal(a_f, a_u)
+    # and against torch on the de-interleaved halves
+    gate = (x.float() @ wg.float().T).to(torch.bfloat16).float()
+    up = (x.float() @ wu.float().T).to(torch.bfloat16).float()
+    ref = (torch.nn.functional.silu(gate) if act == 0 else torch.nn.functional.gelu(gate, approximate="tanh")) * up
+    err = float((a_f.float() - ref).norm() / ref.norm())
+    assert err < 6e-3
+    # interleaved backward layout == halves layout after de-interleaving
+    ga = torch.randn(T, I, generator=g, device="cuda").to(torch.bfloat16)
+    ggu_il = ops.gated_act_bwd(ga, gu_u, act, layout=1)
+    blk = gu_u.view(T, I // 32, 2, 32)
+    gu_h = torch.cat([blk[:, :, 0].reshape(T, I), blk[:, :, 1].reshape(T, I)], 1).contiguous()
+    ggu_h = ops.gated_act_bwd(ga, gu_h, act, layout=0)
+    b2 = ggu_il.view(T, I // 32, 2, 32)
+    assert torch.equal(torch.cat([b2[:, :, 0].reshape(T, I), b2[:, :, 1].reshape(T, I)], 1), ggu_h)

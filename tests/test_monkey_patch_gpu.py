@@ -16,7 +16,8 @@ def _hf_model(cfg, w, impl, max_pos=512):
                      rope_parameters={"rope_type": "default", "rope_theta": cfg["theta"]}, max_position_embeddings=max_pos,
                      attention_bias=False, tie_word_embeddings=False)
     hf._attn_implementation = impl
-    m = LlamaForCausalLM(hf).to(torch.bfloat16)
+    from helpers import build_hf
+    m = build_hf(LlamaForCausalLM, hf)
     sd = {"model.embed_tokens.weight": w["emb"], "model.norm.weight": w["norm"], "lm_head.weight": w["lm_head"]}
     for i, lw in enumerate(w["layers"]):
         p = f"model.layers.{i}."

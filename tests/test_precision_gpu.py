@@ -134,7 +134,8 @@ def test_engine_high_precision_qwen_goldens(family):
               vocab_size=384, max_position_embeddings=512, rms_norm_eps=1e-6, tie_word_embeddings=False)
     if family == "qwen3":
         kw["head_dim"] = 64
-    model = getattr(transformers, f"{family.capitalize()}ForCausalLM")(getattr(transformers, f"{family.capitalize()}Config")(**kw)).to(torch.bfloat16)
+    from helpers import build_hf
+    model = build_hf(getattr(transformers, f"{family.capitalize()}ForCausalLM"), getattr(transformers, f"{family.capitalize()}Config")(**kw))
     model.load_state_dict({k[3:]: bf16_from_bits(v) for k, v in z.items() if k.startswith("sd_")}, strict=True)
     eng = LlamaAttnLRPEngine.from_hf(model, micro_batch=2, precision="high")
     rel, aux = eng.attribute_device(torch.from_numpy(z["ids"]).cuda(), return_aux=True)

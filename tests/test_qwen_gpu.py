@@ -30,7 +30,8 @@ def test_patched_qwen_matches_reference(family):
         kw["head_dim"] = 64
     cfg = Cfg(**kw)
     cfg._attn_implementation = "sdpa"
-    model = Model(cfg).to(torch.bfloat16)
+    from helpers import build_hf
+    model = build_hf(Model, cfg)
     model.load_state_dict({k[3:]: bf16_from_bits(v) for k, v in z.items() if k.startswith("sd_")}, strict=True)
     model = model.cuda().eval()
     for p in model.parameters():

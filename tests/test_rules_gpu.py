@@ -118,3 +118,56 @@ def test_efficient_rules(G):
         assert rel_l2(gx, G[f"id_{name}_g"]) < 1e-5
     _, (gd,) = _grad(lambda t: R.divide_gradient(t * 1.0, 4), x, seed=g)
     assert torch.allclose(gd, G["div4_g"])
+
+
+def test_matmul_and_softmax_rules_at_attention_shape():
+    """lf.matmul / lf.softmax on the [B,H,S,S] attention products (reference lxt/explicit/models/llama.py:379-391 uses exactly
+    these): one strided-batched launch per contraction instead of a Python loop over B*H slices; fp32 operands are held to the
+    reference test's own tolerance (tests/test_functional.py:29-54, atol 1e-4 on O(1) data), bf16 operands to a bf16 bar."""
+    import lxt_b200.explicit.functional as lf
+    from lxt_b200 import ops
+    g = torch.Generator().manual_seed(11)
+    B, H, S, D = 2, 8, 512, 64
+    # positive operands keep 2 O + eps away from zero: the rule divides by it, and a near-singular element would dominate any
+    # norm (the reference's own test avoids this with 10 x 5 outputs)
+    qh = torch.rand(B, H, S, D, generator=g) * 0.5 + 0.1
+    kh = torch.rand(B, H, D, S, generator=g) * 0.5 + 0.1
+    R = torch.randn(B, H, S, S, generator=g)
+    ea, eb = O.matmul_relevance(qh, kh, R, 1e-8)
+    n0 = ops.launch_count()
+    _, (ga, gb) = _grad(lambda p, r: lf.matmul(p, r, False, 1e-8), qh, kh, seed=R)
+    launches = ops.launch_count() - n0
+    assert launches <= 3 * 3 + 2 * 3 + 3 + 8, f"{launches} launches: the batch must not be looped over in Python"
+    assert rel_l2(ga, ea) < 1e-4 and rel_l2(gb, eb) < 1e-4
+    # bf16 operands: one bf16 product per contraction
+    qb, kb, Rb = (t.to(torch.bfloat16) for t in (qh, kh, R))
+    ea16, eb16 = O.matmul_relevance(qb.float(), kb.float(), Rb.float(), 1e-8)
+    _, (ga16, gb16) = _grad(lambda p, r: lf.matmul(p, r, False, 1e-8), qb, kb, seed=Rb)
+    assert rel_l2(ga16, ea16) < 2e-2 and rel_l2(gb16, eb16) < 2e-2
+    # P V with the soft-max rule in front: softmax forward kernel + Deep-Taylor backward at [B,H,S,S]
+    x = torch.randn(B, H, S, S, generator=g)
+    Rp = torch.randn(B, H, S, S, generator=g)
+    y, (gx,) = _grad(lambda t: lf.softmax(t, -1), x, seed=Rp)
+    assert rel_l2(y, torch.softmax(x, -1)) < 1e-6
+    assert rel_l2(gx, O.softmax_relevance(x, Rp)) < 1e-5
+    y2, (gx2,) = _grad(lambda t: lf.softmax(t, 1, None, 2.0), x[:, :, :64, :96].contiguous(), seed=Rp[:, :, :64, :96].contiguous())
+    xs = x[:, :, :64, :96] / 2.0
+    assert rel_l2(y2, torch.softmax(xs, 1)) < 1e-6
+    exp2 = (xs.transpose(1, -1) * (Rp[:, :, :64, :96].transpose(1, -1) - torch.softmax(xs, 1).transpose(1, -1) *
+                                   Rp[:, :, :64, :96].transpose(1, -1).sum(-1, keepdim=True))).transpose(1, -1)
+    assert rel_l2(gx2, exp2) < 1e-5
+
+
+def test_reference_matmul_test_shapes_fp32_tolerance():
+    """the reference's tests/test_functional.py:29-54 (`test_matmul`): a [2,10,32] x [2,32,5], eps 1e-9, closed form via einsum, atol 1e-4"""
+    import lxt_b200.explicit.functional as lf
+    g = torch.Generator().manual_seed(5)
+    a, b, R = torch.randn(2, 10, 32, generator=g), torch.randn(2, 32, 5, generator=g), torch.randn(2, 10, 5, generator=g)
+    out = torch.einsum("bij,bjk->bik", a, b)
+    s = R / (2 * out + 1e-9)
+    exp_a = torch.einsum("bik,bjk->bij", s, b) * a
+    exp_b = torch.einsum("bij,bik->bjk", a, s) * b
+    y, (ga, gb) = _grad(lambda p, r: lf.matmul(p, r, False, 1e-9), a, b, seed=R)
+    assert torch.allclose(y, out, atol=1e-4)
+    scale = float(exp_a.abs().max())
+    assert float((ga - exp_a).abs().max()) < 1e-4 * max(1.0, scale) and float((gb - exp_b).abs().max()) < 1e-4 * max(1.0, float(exp_b.abs().max()))
