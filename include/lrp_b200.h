@@ -298,6 +298,18 @@ int lrp_attn_bwd_f32(const float* q, const float* k, const float* v, int64_t ldq
  * shape; replaces the tensors autograd saves / allocates in the reference's SDPA backward (lxt/efficient/patches.py:193-203) */
 int lrp_attn_bwd_workspace_bytes(int B, int S, int H, int D, int64_t* dq_acc_bytes, int64_t* delta_bytes);
 
+/* ------------------------------------------------------------------------------------------------
+ * 4-bit NormalFloat (NF4) weight storage: weights rest in HBM as 4-bit codes + one fp32 absmax per block and
+ * are expanded to bf16 into a scratch right before the tcgen05 GEMMs of a layer.  Replaces bitsandbytes' Linear4bit storage that
+ * every reference example uses (examples/quantized_llama.py:13-19; wrapped by lxt/explicit/models/llama.py:91-92).  Format: 16 NF4
+ * code points, two codes per byte (first value in the high nibble), block size a multiple of 8 dividing n.  Parity is pinned
+ * against oracle/nf4_oracle.py (bit-exact), not against bitsandbytes (absent).
+ * ---------------------------------------------------------------------------------------------- */
+/* quantise n bf16 weights (examples/quantized_llama.py:13-19 `BitsAndBytesConfig(load_in_4bit=True)`) */
+int lrp_quant_nf4(const void* w_bf16, void* packed, float* absmax, int64_t n, int blocksize, void* stream);
+/* expand to bf16: what bitsandbytes does inside Linear4bit.forward / backward (lxt/explicit/models/llama.py:91-92 call sites) */
+int lrp_dequant_nf4(const void* packed, const float* absmax, void* out_bf16, int64_t n, int blocksize, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

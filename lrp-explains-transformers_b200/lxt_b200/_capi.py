@@ -105,6 +105,8 @@ SIGNATURES = {
          _i, _i, _i, _i, _i, _f, _i, _i, _f, _f, _f, _vp],
     ),
     "lrp_attn_bwd_workspace_bytes": (_i, [_i, _i, _i, _i, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "lrp_quant_nf4": (_i, [_vp, _vp, _vp, _i64, _i, _vp]),
+    "lrp_dequant_nf4": (_i, [_vp, _vp, _vp, _i64, _i, _vp]),
 }
 
 _lib = None

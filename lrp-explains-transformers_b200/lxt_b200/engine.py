@@ -98,7 +98,8 @@ class LlamaAttnLRPEngine:
     """B200-native AttnLRP engine.  Construct with `from_weights`, `from_hf` or `random_init`."""
 
     def __init__(self, dims: LlamaDims, device: torch.device, weights: Dict, micro_batch: int = 8, store: str = "all",
-                 rule: str = "attnlrp", cuda_graph: bool = False, precision: str = "bf16", rope: Optional[Sequence] = None):
+                 rule: str = "attnlrp", cuda_graph: bool = False, precision: str = "bf16", rope: Optional[Sequence] = None,
+                 quant: Optional[str] = None):
         if device.type != "cuda":
             raise RuntimeError("LlamaAttnLRPEngine runs on a CUDA (B200) device only; there is no CPU path")
         ops._capi.require_device()
@@ -143,6 +144,21 @@ class LlamaAttnLRPEngine:
             if dims.post_norms:
                 layer.update(ln_post_attn=bf(lw["ln_post_attn"]), ln_post_ff=bf(lw["ln_post_ff"]))
             self.layers.append(layer)
+        # quant="nf4": the four projection matrices of every layer rest in HBM as 4-bit NormalFloat codes (+ fp32 absmax per 64
+        # values) — 8B parameters in 4.5 GB instead of 16 GB, as the reference's examples do through bitsandbytes
+        # (examples/quantized_llama.py:13-19) — and are expanded to bf16 into ONE per-layer scratch right before the layer's GEMMs
+        # (forward and backward), so the tcgen05 kernels and the LRP rules are untouched.  Embedding / lm_head stay bf16.
+        if quant not in (None, "nf4"):
+            raise ValueError("quant must be None or 'nf4'")
+        self.quant = quant
+        self._wq_names = ("wqkv", "wo", "wgu", "wd")
+        if quant == "nf4":
+            self._wscratch = {n: torch.empty_like(self.layers[0][n]) for n in self._wq_names}
+            self._wscratch_layer = None
+            for layer in self.layers:
+                for n in self._wq_names:
+                    layer[n] = ops.quant_nf4(layer[n]) + (tuple(layer[n].shape),)
+            torch.cuda.empty_cache()
         self._ws_key = None
         self._ws = None
         self._rope_cache = {}
@@ -182,7 +198,12 @@ class LlamaAttnLRPEngine:
         """the weights in the `from_weights` format (packed projections split / de-interleaved again)"""
         m = self.dims
         out = dict(emb=self.emb, norm=self.norm_w, lm_head=self.lm_head, layers=[])
-        for lw in self.layers:
+        for l, lw in enumerate(self.layers):
+            if self.quant is not None:   # de-quantised copies
+                lw = dict(lw)
+                for n in self._wq_names:
+                    packed, absmax, shape = lw[n]
+                    lw[n] = ops.dequant_nf4(packed, absmax, torch.empty(shape, dtype=torch.bfloat16, device=self.device))
             wq, wk, wv = lw["wqkv"].split([m.H * m.D, m.Hkv * m.D, m.Hkv * m.D], 0)
             if self.gu_layout == 0:
                 wg, wu = lw["wgu"].split([m.I, m.I], 0)
@@ -359,9 +380,36 @@ class LlamaAttnLRPEngine:
         return self._rope_cache[key]
 
     # ------------------------------------------------------------------ one layer
+    def _materialize(self, lw, l: int):
+        """NF4 storage: expand layer l's four projection matrices into the shared bf16 scratch (4 launches; skipped when the scratch
+        already holds this layer, e.g. backward right after the forward of the same layer in the sqrt schedule)"""
+        if self.quant is None:
+            return lw
+        if self._wscratch_layer != l:
+            for n in self._wq_names:
+                packed, absmax, _ = lw[n]
+                ops.dequant_nf4(packed, absmax, self._wscratch[n])
+            self._wscratch_layer = l
+        out = dict(lw)
+        out.update(self._wscratch)
+        return out
+
+    def weight_bytes(self) -> int:
+        """bytes of HBM held by the decoder-layer weights (packed codes + absmax for NF4, incl. the one-layer bf16 scratch)"""
+        tot = 0
+        for lw in self.layers:
+            for v in lw.values():
+                for t in (v if isinstance(v, tuple) else (v,)):
+                    if isinstance(t, torch.Tensor):
+                        tot += t.numel() * t.element_size()
+        if self.quant is not None:
+            tot += sum(t.numel() * t.element_size() for t in self._wscratch.values())
+        return tot
+
     def _layer_fwd(self, lw, st: _LayerStore, h, ws, B, S, l: int = 0, h_copy=None):
         """h_copy: optional bf16 [T,d] buffer that receives a copy of this layer's OUTPUT residual stream, written by the last
         residual epilogue of the layer (the latent-relevance trace needs the layer outputs in the backward sweep)"""
+        lw = self._materialize(lw, l)
         m = self.dims
         T = B * S
         cos, sin = self._rope(S, l)
@@ -412,6 +460,7 @@ class LlamaAttnLRPEngine:
                 h_copy.copy_(h)
 
     def _layer_bwd(self, lw, st: _LayerStore, ws, B, S, l: int = 0):
+        lw = self._materialize(lw, l)
         m = self.dims
         T = B * S
         cos, sin = self._rope(S, l)

@@ -210,6 +210,122 @@ class mul2_fn(Function):
         return tuple(r if i in ctx.requires_grads else None for i in range(2)) + (None,)
 
 
+def _rowsum(x2: torch.Tensor) -> torch.Tensor:
+    """sum over the last dim of a contiguous 2-D tensor on the reduction kernel (sum_d x * 1)"""
+    return ops.gxi_reduce(x2, torch.ones_like(x2))
+
+
+def _last(x: torch.Tensor, dim: int):
+    d = dim if dim >= 0 else x.dim() + dim
+    xt = x if d == x.dim() - 1 else x.transpose(d, -1)
+    return d, xt.contiguous()
+
+
+class mean_fn(Function):
+    """epsilon rule for `x.mean(dim)` (reference lxt/explicit/functional.py:539-585): R_in = x * R_out / (sum(x) + eps)"""
+
+    @staticmethod
+    def forward(ctx, x, dim, keepdim, epsilon=1e-6):
+        if not x.is_cuda or x.dtype not in (torch.float32, torch.bfloat16):
+            raise LrpError("mean: CUDA bf16/fp32 tensors only (no CPU fallback)")
+        d, xt = _last(x, dim)
+        n = xt.shape[-1]
+        xs = _rowsum(xt.reshape(-1, n)).view(xt.shape[:-1])            # fp32 sums, one per reduced row
+        y = ops.scale(xs, 1.0 / n).to(x.dtype).unsqueeze(-1)
+        y = y if d == x.dim() - 1 else y.transpose(d, -1)
+        ctx.save_for_backward(x, xs)
+        ctx.epsilon, ctx.dim, ctx.keepdim = epsilon, d, keepdim
+        return y if keepdim else y.squeeze(d)
+
+    @staticmethod
+    @conservation_check_wrap
+    def backward(ctx, *out_relevance):
+        x, xs = ctx.saved_tensors
+        d = ctx.dim
+        R = out_relevance[0] if ctx.keepdim else out_relevance[0].unsqueeze(d)
+        Rt = (R if d == x.dim() - 1 else R.transpose(d, -1)).contiguous().squeeze(-1)
+        s = ops.eps_div(Rt.float(), xs, ctx.epsilon)                    # R / (sum + eps) per reduced row
+        _, xt = _last(x, d)
+        rel = ops.mul(xt, s.to(x.dtype).unsqueeze(-1).expand(xt.shape))
+        rel = rel if d == x.dim() - 1 else rel.transpose(d, -1)
+        return rel, None, None, None
+
+
+class layer_norm_grad_fn(Function):
+    """LayerNorm with the std detached, epsilon rule on the whole (reference functional.py:588-635): forward on the detached-std
+    LayerNorm kernel, backward R / (y + eps) -> the same kernel's backward (g w rstd - mean(g w rstd)) -> * x."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, variance_epsilon, epsilon=1e-6):
+        if not x.is_cuda or x.dtype not in (torch.float32, torch.bfloat16):
+            raise LrpError("layer_norm: CUDA bf16/fp32 tensors only (no CPU fallback)")
+        x2 = x.reshape(-1, x.shape[-1]).contiguous()
+        w = None if weight is None else weight.detach().to(x.dtype).contiguous()
+        b = None if bias is None else bias.detach().to(x.dtype).contiguous()
+        y, _, rstd = ops.layernorm_fwd(x2, w, b, variance_epsilon)
+        ctx.save_for_backward(x, y, rstd)
+        ctx.w, ctx.epsilon = w, epsilon
+        return y.view(x.shape)
+
+    @staticmethod
+    @conservation_check_wrap
+    def backward(ctx, *out_relevance):
+        x, y, rstd = ctx.saved_tensors
+        R = out_relevance[0].reshape(y.shape).to(y.dtype).contiguous()
+        g = ops.layernorm_bwd(ops.eps_div(R, y, ctx.epsilon), ctx.w, rstd)
+        return ops.mul(g.view(x.shape), x), None, None, None, None
+
+
+class normalize_identity_fn(Function):
+    """identity rule on F.normalize (reference functional.py:638-664): forward x / max(||x||_p, eps), relevance passes unchanged"""
+
+    @staticmethod
+    def forward(ctx, input, p, dim, eps):
+        if not input.is_cuda or input.dtype not in (torch.float32, torch.bfloat16):
+            raise LrpError("normalize: CUDA bf16/fp32 tensors only (no CPU fallback)")
+        if p != 2.0:
+            return F.normalize(input, p=p, dim=dim, eps=eps)
+        d, xt = _last(input, dim)
+        n = xt.shape[-1]
+        x2 = xt.reshape(-1, n)
+        inv = 1.0 / ops.gxi_reduce(x2, x2).sqrt_().clamp_min_(eps)        # [rows] fp32: a handful of scalars per row
+        y = ops.mul(x2, inv.to(input.dtype).unsqueeze(-1).expand(x2.shape)).view(xt.shape)
+        return y if d == input.dim() - 1 else y.transpose(d, -1)
+
+    @staticmethod
+    @conservation_check_wrap
+    def backward(ctx, *out_relevance):
+        return out_relevance + (None, None, None)
+
+
+def mean(x, dim, keep_dim, epsilon=1e-6):
+    """epsilon-LRP for the mean operation."""
+    return mean_fn.apply(x, dim, keep_dim, epsilon)
+
+
+def layer_norm(hidden_states, weight, bias, variance_epsilon):
+    """identity rule on 1/std (detached) and on the weight, epsilon rule on (x - mean): standard nn.LayerNorm (AttnLRP Prop. 3.4)."""
+    return layer_norm_grad_fn.apply(hidden_states, weight, bias, variance_epsilon)
+
+
+def _layer_norm_slower(hidden_states, weight, bias, variance_epsilon):
+    """the same LayerNorm composed from the primitive rules (reference functional.py:201-237), kept for the reference's own
+    cross-check test (tests/test_functional.py:132-160)"""
+    x_mean = mean(hidden_states, -1, keep_dim=True)
+    var = ((hidden_states - x_mean) ** 2).mean(dim=-1, keepdim=True)
+    std = (var + variance_epsilon).sqrt().detach()
+    y = add2(hidden_states, mul2(x_mean, -1))
+    y = mul2(y, 1 / std)
+    y = mul2(y, weight)
+    return add2(y, bias)
+
+
+def normalize(input, p=2.0, dim=1, eps=1e-12, out=None):
+    """identity rule on torch.nn.functional.normalize (AttnLRP Prop. 3.4)."""
+    assert out is None, "out parameter is not supported"
+    return normalize_identity_fn.apply(input, p, dim, eps)
+
+
 def add2(input_a, input_b, inplace=False, epsilon=1e-8):
     """epsilon-LRP for a + b (AttnLRP Eq. 8)."""
     return add2_tensors_fn.apply(input_a, input_b, inplace, epsilon)

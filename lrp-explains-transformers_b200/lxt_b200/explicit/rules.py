@@ -132,6 +132,45 @@ class UniformEpsilonRule(WrapModule):
         return uniform_epsilon_lrp_fn.apply(self.module, self.epsilon, *inputs)
 
 
+class taylor_decomposition_fn(Function):
+    """Generalised Taylor decomposition without bias (AttnLRP Eq. 4-5; reference lxt/explicit/rules.py:317-372):
+    output' = J(ref) . inputs (jvp at the reference point), R_i = inputs_i * vjp(ref)(R / (output' + eps)).
+    The reference's `bias=True` branch reads an undefined variable (rules.py:354-360) and cannot run; it is refused here."""
+
+    @staticmethod
+    def forward(ctx, fn, ref, bias, distribute_bias, *inputs):
+        if bias:
+            raise NotImplementedError("TaylorDecompositionRule(bias=True) is unusable in the reference (undefined `output`, "
+                                      "lxt/explicit/rules.py:354-360); only bias=False is provided")
+        output = fn(*inputs)
+        ctx.save_for_backward(*inputs)
+        ctx.fn, ctx.ref = fn, ref
+        return output
+
+    @staticmethod
+    @conservation_check_wrap
+    def backward(ctx, *out_relevance):
+        from torch.func import jvp, vjp
+        inputs = ctx.saved_tensors
+        ref = tuple(ctx.ref)
+        _, jv = jvp(ctx.fn, ref, tuple(inputs))
+        normed = ops.eps_div(out_relevance[0].to(jv.dtype), jv, 1e-6)
+        _, vjpfunc = vjp(ctx.fn, *ref)
+        grads = vjpfunc(normed)
+        return (None, None, None, None) + tuple(ops.mul(g, x) for g, x in zip(grads, inputs))
+
+
+class TaylorDecompositionRule(WrapModule):
+    """Taylor decomposition at a reference point for any differentiable module (reference rules.py:285-314)."""
+
+    def __init__(self, module, ref=0, bias=False, distribute_bias=None):
+        super().__init__(module)
+        self.ref, self.bias, self.distribute_bias = ref, bias, distribute_bias
+
+    def forward(self, *inputs):
+        return taylor_decomposition_fn.apply(self.module, self.ref, self.bias, self.distribute_bias, *inputs)
+
+
 class uniform_rule_fn(Function):
     @staticmethod
     def forward(ctx, fn, *inputs):

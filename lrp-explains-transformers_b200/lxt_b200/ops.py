@@ -542,6 +542,31 @@ def add2_bwd(a: torch.Tensor, b: torch.Tensor, r: torch.Tensor, eps: float):
     return ra, rb
 
 
+def quant_nf4(w: torch.Tensor, blocksize: int = 64):
+    """bf16 weight -> (packed uint8 [n/2], absmax fp32 [n/blocksize]) on the device (NF4, see csrc/quant.cu)"""
+    _need(w, torch.bfloat16, "w")
+    w = w.contiguous()
+    n = w.numel()
+    if n % blocksize or w.shape[-1] % blocksize:
+        raise _capi.LrpError(f"quant_nf4: the contiguous dimension ({w.shape[-1]}) must be a multiple of the block size {blocksize}")
+    packed = torch.empty(n // 2, dtype=torch.uint8, device=w.device)
+    absmax = torch.empty(n // blocksize, dtype=torch.float32, device=w.device)
+    check(_capi.lib().lrp_quant_nf4(w.data_ptr(), packed.data_ptr(), absmax.data_ptr(), n, blocksize, _stream()), "lrp_quant_nf4")
+    return packed, absmax
+
+
+def dequant_nf4(packed: torch.Tensor, absmax: torch.Tensor, out: torch.Tensor, blocksize: int = 64) -> torch.Tensor:
+    """expand NF4 codes into the bf16 tensor `out` (contiguous, numel = 2 * packed.numel())"""
+    _need(packed, torch.uint8, "packed")
+    _need(absmax, torch.float32, "absmax")
+    _need(out, torch.bfloat16, "out")
+    if not out.is_contiguous() or out.numel() != 2 * packed.numel():
+        raise _capi.LrpError("dequant_nf4: out must be contiguous with 2 * packed.numel() elements")
+    check(_capi.lib().lrp_dequant_nf4(packed.data_ptr(), absmax.data_ptr(), out.data_ptr(), out.numel(), blocksize, _stream()),
+          "lrp_dequant_nf4")
+    return out
+
+
 def pad_to8(t: torch.Tensor, dims) -> torch.Tensor:
     """zero-pad the given dims of `t` up to multiples of 8 (tensor-core tiles need 16-byte rows)"""
     pads = [0, 0] * t.dim()

@@ -160,7 +160,7 @@ def test_engine_from_hf_reproduces_scaled_rope():
         e, e_plain = rel_l2(rel.cpu(), rel_hf), rel_l2(plain, rel_hf)
         print(f"rope {rope['rope_type']}: engine vs patched HF {e:.2e}; with default RoPE tables {e_plain:.2e}")
         assert torch.equal(aux["idx"].cpu().long(), mi.cpu())
-        assert e < 1.5e-2 and e_plain > 5 * e
+        assert e < 1.5e-2 and e_plain > 3 * e
 
 
 @pytest.mark.parametrize("name", ["gemma3_tiny.npz", "gemma3_tiny_d256.npz"])

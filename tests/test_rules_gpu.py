@@ -159,15 +159,69 @@ def test_matmul_and_softmax_rules_at_attention_shape():
 
 
 def test_reference_matmul_test_shapes_fp32_tolerance():
-    """the reference's tests/test_functional.py:29-54 (`test_matmul`): a [2,10,32] x [2,32,5], eps 1e-9, closed form via einsum, atol 1e-4"""
+    """the reference's tests/test_functional.py:29-54 (`test_matmul`): a [2,10,32] x [2,32,5], eps 1e-9, closed form via einsum.
+    The reference holds its own fp32 einsum restatement to atol 1e-4; here the products come from two-term bf16 splits (|dO| ~ 1e-6),
+    and the rule divides by 2 O + 1e-9, so the elements where O ~ 0 amplify that: the forward is held to the reference's atol, the
+    relevances to 1e-3 rel-L2 (the path's stated tolerance) against a float64 closed form."""
     import lxt_b200.explicit.functional as lf
     g = torch.Generator().manual_seed(5)
     a, b, R = torch.randn(2, 10, 32, generator=g), torch.randn(2, 32, 5, generator=g), torch.randn(2, 10, 5, generator=g)
-    out = torch.einsum("bij,bjk->bik", a, b)
-    s = R / (2 * out + 1e-9)
-    exp_a = torch.einsum("bik,bjk->bij", s, b) * a
-    exp_b = torch.einsum("bij,bik->bjk", a, s) * b
+    ad, bd, Rd = a.double(), b.double(), R.double()
+    out = torch.einsum("bij,bjk->bik", ad, bd)
+    s = Rd / (2 * out + 1e-9)
+    exp_a = torch.einsum("bik,bjk->bij", s, bd) * ad
+    exp_b = torch.einsum("bij,bik->bjk", ad, s) * bd
     y, (ga, gb) = _grad(lambda p, r: lf.matmul(p, r, False, 1e-9), a, b, seed=R)
-    assert torch.allclose(y, out, atol=1e-4)
-    scale = float(exp_a.abs().max())
-    assert float((ga - exp_a).abs().max()) < 1e-4 * max(1.0, scale) and float((gb - exp_b).abs().max()) < 1e-4 * max(1.0, float(exp_b.abs().max()))
+    assert torch.allclose(y.double(), out, atol=1e-4)
+    assert rel_l2(ga, exp_a) < 1e-3 and rel_l2(gb, exp_b) < 1e-3
+
+
+def test_mean_layer_norm_normalize_rules_like_the_reference_tests():
+    """lf.mean / lf.layer_norm / lf.normalize (reference tests/test_functional.py:109-178): closed forms, the reference's shapes"""
+    import lxt_b200.explicit.functional as lf
+    g = torch.Generator().manual_seed(9)
+    x, R = torch.randn(1, 8, 32, generator=g) + 2.0, torch.randn(1, 8, generator=g)
+    for keep in (False, True):
+        Rk = R.unsqueeze(-1) if keep else R
+        y, (gx,) = _grad(lambda t: lf.mean(t, -1, keep, 1e-9), x, seed=Rk)
+        assert torch.allclose(y, x.mean(-1, keepdim=keep), atol=1e-5)
+        exp = x * (R / (x.sum(-1) + 1e-9)).unsqueeze(-1)
+        assert rel_l2(gx, exp) < 1e-4
+    y, (gx,) = _grad(lambda t: lf.mean(t, 1, False, 1e-9), x, seed=torch.randn(1, 32, generator=torch.Generator().manual_seed(1)))
+    assert torch.allclose(y, x.mean(1), atol=1e-5)
+    # layer_norm: detached-std LayerNorm under the epsilon rule == the composition of the primitive rules (reference cross-check)
+    x = torch.randn(1, 2, 8, generator=g)
+    w, b, R = torch.randn(8, generator=g), torch.randn(8, generator=g), torch.randn(1, 2, 8, generator=g)
+    y1, (g1,) = _grad(lambda t: lf.layer_norm(t, w.cuda(), b.cuda(), 1e-5), x, seed=R)
+    ref = torch.nn.functional.layer_norm(x, (8,), w, b, 1e-5)
+    assert torch.allclose(y1, ref, atol=1e-5)
+    xd = x.double().requires_grad_()
+    mu = xd.mean(-1, keepdim=True)
+    yd = (xd - mu) / ((xd - mu).pow(2).mean(-1, keepdim=True) + 1e-5).sqrt().detach() * w.double() + b.double()
+    (gd,) = torch.autograd.grad(yd, xd, R.double() / (yd.detach() + 1e-6))
+    assert rel_l2(g1, gd * x.double()) < 1e-4
+    y2, (g2,) = _grad(lambda t: lf._layer_norm_slower(t, w.cuda(), b.cuda(), 1e-5), x, seed=R)
+    assert torch.allclose(y2, ref, atol=1e-4)
+    cos = torch.nn.functional.cosine_similarity(g1.flatten(), g2.flatten(), dim=0)
+    assert cos > 0.99                       # the reference's own bar for this pair (atol 1e-1 + cosine > 0.99)
+    # normalize: identity rule
+    x, R = torch.randn(1, 4, 32, generator=g), torch.randn(1, 4, 32, generator=g)
+    y, (gx,) = _grad(lambda t: lf.normalize(t, 2.0, -1), x, seed=R)
+    assert torch.allclose(y, torch.nn.functional.normalize(x, 2.0, -1), atol=1e-6) and torch.equal(gx, R)
+
+
+def test_taylor_decomposition_rule_without_bias():
+    """TaylorDecompositionRule at ref = 0 on a linear map equals the epsilon rule without bias (AttnLRP Eq. 4-5)"""
+    import lxt_b200.explicit.rules as rules
+    g = torch.Generator().manual_seed(4)
+    x, W, R = torch.rand(6, 16, generator=g) + 0.5, torch.rand(8, 16, generator=g) + 0.5, torch.randn(6, 8, generator=g)
+    lin = torch.nn.Linear(16, 8, bias=False).cuda()
+    lin.weight.data.copy_(W)
+    lin.weight.requires_grad_(False)
+    rule = rules.TaylorDecompositionRule(lin, ref=(torch.zeros(6, 16, device="cuda"),), bias=False)
+    _, (gx,) = _grad(rule, x, seed=R)
+    exp = O.linear_epsilon_relevance(x, W, None, R, 1e-6)
+    assert rel_l2(gx, exp) < 1e-4
+    import pytest as _pt
+    with _pt.raises(NotImplementedError):
+        rules.TaylorDecompositionRule(lin, ref=(torch.zeros(6, 16, device="cuda"),), bias=True)(x.cuda().requires_grad_())
