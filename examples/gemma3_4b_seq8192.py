@@ -23,8 +23,14 @@ def main(S=8192, layers=34):
                            max_position_embeddings=131072, query_pre_attn_scalar=256, rms_norm_eps=1e-6, tie_word_embeddings=True)
     cfg._attn_implementation = "sdpa"
     torch.manual_seed(0)
-    with torch.device("cuda"):
-        model = Gemma3ForCausalLM(cfg).to(torch.bfloat16).eval()
+    # bf16 parameters, fp32 RoPE tables — as `from_pretrained(torch_dtype=torch.bfloat16)` builds it (a later `.to(torch.bfloat16)` would
+    # also round HF's non-persistent inv_freq buffer, which ruins RoPE at long context)
+    torch.set_default_dtype(torch.bfloat16)
+    try:
+        with torch.device("cuda"):
+            model = Gemma3ForCausalLM(cfg).eval()
+    finally:
+        torch.set_default_dtype(torch.float32)
     for p in model.parameters():
         p.requires_grad_(False)
     monkey_patch(modeling_gemma3)

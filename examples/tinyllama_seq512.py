@@ -33,7 +33,11 @@ def main(S=512, B=1):
                       rope_parameters={"rope_type": "default", "rope_theta": 10000.0}, tie_word_embeddings=False)
     cfg._attn_implementation = "sdpa"
     torch.manual_seed(0)
-    model = LlamaForCausalLM(cfg).to(torch.bfloat16).cuda().eval()
+    torch.set_default_dtype(torch.bfloat16)   # bf16 parameters, fp32 RoPE tables (like from_pretrained(torch_dtype=bfloat16))
+    try:
+        model = LlamaForCausalLM(cfg).cuda().eval()
+    finally:
+        torch.set_default_dtype(torch.float32)
     for p in model.parameters():
         p.requires_grad_(False)
     ids = torch.randint(0, cfg.vocab_size, (B, S), generator=torch.Generator().manual_seed(1)).cuda()

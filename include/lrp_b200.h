@@ -73,6 +73,15 @@ typedef struct lrp_epilogue {
    * [M, 2I], same interleaved column order) is written as usual and act_out[m, i] = act(gate[m, i]) * up[m, i] (bf16 [M, I],
    * gated_act selects the activation) — bit-identical to lrp_gated_act_fwd on the stored bf16 values. */
   void* act_out;
+  /* Optional fused prologue of the attention backward: when `delta_o` is set, this GEMM is the O-projection dgrad (bf16 output
+   * [B*S, H*D] = dO) and the epilogue also emits delta[b,h,s] = sum_d o[b,s,h,d] * dO[b,s,h,d] (fp32 [B,H,S]), the row term of the
+   * soft-max backward that lrp_attn_bwd otherwise computes in a separate pass (lxt/efficient/patches.py:193-203 -> SDPA backward).
+   * `delta_o` (bf16) has the output's layout; delta_head_dim = D, delta_seq = S. */
+  const void* delta_o;
+  float* delta_out;
+  int32_t delta_head_dim;
+  int32_t delta_seq;
+  int32_t gated_layout;   /* layout of gated_gu / gated_out: 0 = (gate | up) halves, 1 = blocks of 32 interleaved (see act_out) */
 } lrp_epilogue_t;
 
 /* Generic tcgen05 GEMM, A [M,K] bf16.  b_layout 0: B is [N,K] (NT);  b_layout 1: B is [K,N] (NN).
@@ -202,10 +211,12 @@ int lrp_attn_fwd_varlen(const void* q, const void* k, const void* v, int64_t ldq
                         float* lse, const int32_t* kv_range, int B, int S, int H, int Hkv, int D, float scale, int causal,
                         int window, void* stream);
 /* backward of lrp_attn_fwd_varlen (same rule and workspaces as lrp_attn_bwd; lxt/efficient/patches.py:193-203) */
+#define LRP_ATTN_DELTA_READY 1 /* delta_ws already holds sum_d o*dO (written by the O-dgrad GEMM epilogue, lrp_epilogue_t.delta_o) */
+#define LRP_ATTN_ACC_ZERO 2    /* dq_acc_ws is zero on entry and is left zero on return (skips the per-call zero-fill) */
 int lrp_attn_bwd_varlen(const void* q, const void* k, const void* v, int64_t ldq, int64_t ldk, int64_t ldv,
                         const void* o, const void* d_o, const float* lse, void* dq, void* dk, void* dv, int64_t lddq,
-                        int64_t lddk, int64_t lddv, float* dq_acc_ws, float* delta_ws, const int32_t* kv_range, int B, int S,
-                        int H, int Hkv, int D, float scale, int causal, int window, float q_div, float k_div, float v_div,
+                        int64_t lddk, int64_t lddv, float* dq_acc_ws, float* delta_ws, const int32_t* kv_range, int flags, int B,
+                        int S, int H, int Hkv, int D, float scale, int causal, int window, float q_div, float k_div, float v_div,
                         void* stream);
 
 /* ------------------------------------------------------------------------------------------------
@@ -213,6 +224,14 @@ int lrp_attn_bwd_varlen(const void* q, const void* k, const void* v, int64_t ldq
  * ---------------------------------------------------------------------------------------------- */
 /* h[t,:] = float(emb[ids[t],:]) * scale   (ids int64 on device; emb bf16 [V,d]; h fp32 [T,d]) */
 int lrp_embed_gather(const int64_t* ids, const void* emb, float scale, float* h, int T, int d, void* stream);
+/* out[i,:] = src[rows[i],:] (fp32): the hidden states of the last position of every prompt, `logits[0, -1, :]` reads only those
+ * (examples/quantized_llama.py:40) */
+int lrp_gather_rows_f32(const float* src, const int64_t* rows, float* out, int n_rows, int d, void* stream);
+/* seed of the LRP backward sweep, `max_logits.backward()` (examples/quantized_llama.py:40-44): g_h[t,:] = lm_head[idx[b],:] *
+ * (norm_w + w_offset) * rstd_last[b] at the last token t = b*S + S-1 of each prompt (the final RMSNorm's identity rule,
+ * lxt/efficient/patches.py:111-123), 0 elsewhere; g_hb (bf16 copy, may be NULL) is the first dgrad's A operand. */
+int lrp_seed_gradient(const void* lm_head, const int32_t* idx, const void* norm_w, float w_offset, const float* rstd_last, int S,
+                      float* g_h, void* g_hb, int T, int d, void* stream);
 /* argmax over logits[b,:] (fp32 [B,V]) -> idx[b] (int32), val[b] */
 /* arg-max logit per prompt: `output_logits[0, -1, :].max()` examples/quantized_llama.py:40 */
 int lrp_argmax_rows(const float* logits, int32_t* idx, float* val, int B, int V, void* stream);

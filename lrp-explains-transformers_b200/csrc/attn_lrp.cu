@@ -761,8 +761,9 @@ __global__ void __launch_bounds__(256) attn_delta_kernel(const __nv_bfloat16* __
 }
 
 // dq[b,s,h,:] = bf16(dq_acc * inv_q_div), dq strided by lddq
-__global__ void __launch_bounds__(256) attn_dq_finish_kernel(const float* __restrict__ acc, __nv_bfloat16* __restrict__ dq,
-                                                             int64_t lddq, int64_t rows, int HD, float inv_q_div) {
+// rezero = 1: the accumulator is cleared behind the read, so that the next call may skip its zero-fill (LRP_ATTN_ACC_ZERO)
+__global__ void __launch_bounds__(256) attn_dq_finish_kernel(float* __restrict__ acc, __nv_bfloat16* __restrict__ dq,
+                                                             int64_t lddq, int64_t rows, int HD, float inv_q_div, int rezero) {
   const int chunks = HD >> 3;
   const int64_t total = rows * chunks;
   for (int64_t idx = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; idx < total; idx += int64_t(gridDim.x) * blockDim.x) {
@@ -773,6 +774,10 @@ __global__ void __launch_bounds__(256) attn_dq_finish_kernel(const float* __rest
     *reinterpret_cast<uint4*>(dq + t * lddq + c) =
         make_uint4(pack_bf16x2(a.x * inv_q_div, a.y * inv_q_div), pack_bf16x2(a.z * inv_q_div, a.w * inv_q_div),
                    pack_bf16x2(b4.x * inv_q_div, b4.y * inv_q_div), pack_bf16x2(b4.z * inv_q_div, b4.w * inv_q_div));
+    if (rezero) {
+      *reinterpret_cast<float4*>(acc + t * HD + c) = make_float4(0.f, 0.f, 0.f, 0.f);
+      *reinterpret_cast<float4*>(acc + t * HD + c + 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
   }
 }
 
@@ -892,14 +897,14 @@ int lrp_attn_bwd(const void* q, const void* k, const void* v, int64_t ldq, int64
                  const void* d_o, const float* lse, void* dq, void* dk, void* dv, int64_t lddq, int64_t lddk, int64_t lddv,
                  float* dq_acc_ws, float* delta_ws, int B, int S, int H, int Hkv, int D, float scale, int causal, int window,
                  float q_div, float k_div, float v_div, void* stream) {
-  return lrp_attn_bwd_varlen(q, k, v, ldq, ldk, ldv, o, d_o, lse, dq, dk, dv, lddq, lddk, lddv, dq_acc_ws, delta_ws, nullptr, B, S, H,
-                             Hkv, D, scale, causal, window, q_div, k_div, v_div, stream);
+  return lrp_attn_bwd_varlen(q, k, v, ldq, ldk, ldv, o, d_o, lse, dq, dk, dv, lddq, lddk, lddv, dq_acc_ws, delta_ws, nullptr, 0, B, S,
+                             H, Hkv, D, scale, causal, window, q_div, k_div, v_div, stream);
 }
 
 int lrp_attn_bwd_varlen(const void* q, const void* k, const void* v, int64_t ldq, int64_t ldk, int64_t ldv, const void* o,
                         const void* d_o, const float* lse, void* dq, void* dk, void* dv, int64_t lddq, int64_t lddk, int64_t lddv,
-                        float* dq_acc_ws, float* delta_ws, const int32_t* kv_range, int B, int S, int H, int Hkv, int D, float scale,
-                        int causal, int window, float q_div, float k_div, float v_div, void* stream) {
+                        float* dq_acc_ws, float* delta_ws, const int32_t* kv_range, int flags, int B, int S, int H, int Hkv, int D,
+                        float scale, int causal, int window, float q_div, float k_div, float v_div, void* stream) {
   if (int e = check_common(q, k, v, ldq, ldk, ldv, B, S, H, Hkv, D)) return e;
   if ((lddq % 8) || (lddk % 8) || (lddv % 8)) return set_error(LRP_ERR_ARG, "attn_bwd: gradient strides must be multiples of 8");
   if (dq_acc_ws == nullptr || delta_ws == nullptr) return set_error(LRP_ERR_ARG, "attn_bwd: missing workspace");
@@ -913,9 +918,16 @@ int lrp_attn_bwd_varlen(const void* q, const void* k, const void* v, int64_t ldq
   const int64_t rows = int64_t(B) * S * H;
   const char* sel = getenv("LRP_ATTN_BWD");
   const bool two_pass = D == 256 || (sel != nullptr && !strcmp(sel, "v2"));   // head_dim 256 exists only in the two-pass v2 form
-  attn_delta_kernel<<<unsigned((rows + 7) / 8), 256, 0, st>>>((const __nv_bfloat16*)o, (const __nv_bfloat16*)d_o, delta_ws,
-                                                             two_pass ? nullptr : dq_acc_ws, B, S, H, D);
-  LRP_CHECK_LAUNCH();
+  const bool delta_ready = (flags & LRP_ATTN_DELTA_READY) != 0, acc_zero = (flags & LRP_ATTN_ACC_ZERO) != 0;
+  if (!delta_ready) {
+    attn_delta_kernel<<<unsigned((rows + 7) / 8), 256, 0, st>>>((const __nv_bfloat16*)o, (const __nv_bfloat16*)d_o, delta_ws,
+                                                               (two_pass || acc_zero) ? nullptr : dq_acc_ws, B, S, H, D);
+    LRP_CHECK_LAUNCH();
+  } else if (!two_pass && !acc_zero) {
+    cudaError_t ce = cudaMemsetAsync(dq_acc_ws, 0, size_t(rows) * D * sizeof(float), st);
+    if (ce != cudaSuccess) return set_error(LRP_ERR_CUDA, cudaGetErrorString(ce));
+    note_launch();
+  }
   // LRP_ATTN_BWD=v2 selects the two-kernel pipelined, atomic-free (bit-reproducible) backward of attn_bwd_v2.cu.
   // Measured on B200 it is on par with / slightly slower than this single-kernel version (its 64-wide MMAs are
   // smem-operand bound and S/dP/exp are recomputed for dQ), so the single kernel stays the default.
@@ -988,7 +1000,7 @@ int lrp_attn_bwd_varlen(const void* q, const void* k, const void* v, int64_t ldq
   int64_t g = (total + 255) / 256;
   if (g > int64_t(sm_count()) * 16) g = int64_t(sm_count()) * 16;
   attn_dq_finish_kernel<<<unsigned(g), 256, 0, st>>>(dq_acc_ws, (__nv_bfloat16*)dq, lddq, tok, int(HD),
-                                                    q_div > 0.f ? 1.f / q_div : 0.f);
+                                                    q_div > 0.f ? 1.f / q_div : 0.f, acc_zero ? 1 : 0);
   LRP_CHECK_LAUNCH();
   return LRP_OK;
 }

@@ -165,20 +165,30 @@ gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_co
           tmem_ld32(taddr + c * 64 + 32, vu);
           tmem_ld_wait();
           const int n0 = n_blk * P_BN + c * 64;
-          if (row_ok && n0 < p.N) {
-            gemm_epilogue_chunk(p, vg, m, rs, row_off, n0);
-            gemm_epilogue_chunk(p, vu, m, rs, row_off, n0 + 32);
-            gemm_epilogue_act_pair(p, vg, vu, m, rs, n0);
-          }
+          if (row_ok && n0 < p.N) gemm_epilogue_act_pair(p, vg, vu, m, rs, row_off, n0);
         }
-      } else {
+      } else if (p.gated_gu != nullptr) {
+        // down-projection dgrad with the gated-MLP backward rules fused: g_a never reaches HBM
 #pragma unroll 1
         for (int c = 0; c < P_BN / 32; ++c) {
           uint32_t v[32];
           tmem_ld32(taddr + c * 32, v);
           tmem_ld_wait();
           const int n0 = n_blk * P_BN + c * 32;
-          if (row_ok && n0 < p.N) gemm_epilogue_chunk(p, v, m, rs, row_off, n0);
+          if (row_ok && n0 < p.N) gemm_epilogue_gated_bwd(p, v, m, rs, n0);
+        }
+      } else {
+        float dacc = 0.f;
+#pragma unroll 1
+        for (int c = 0; c < P_BN / 32; ++c) {
+          uint32_t v[32];
+          tmem_ld32(taddr + c * 32, v);
+          tmem_ld_wait();
+          const int n0 = n_blk * P_BN + c * 32;
+          if (row_ok && n0 < p.N) {
+            const float dot = gemm_epilogue_chunk(p, v, m, rs, row_off, n0);
+            if (p.delta_o != nullptr) gemm_epilogue_delta(p, dacc, dot, m, n0);
+          }
         }
       }
       tc_fence_before();

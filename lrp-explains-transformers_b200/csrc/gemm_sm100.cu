@@ -189,20 +189,30 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
           tmem_ld32(taddr + c * 64 + 32, vu);
           tmem_ld_wait();
           const int n0 = n_blk * BN + c * 64;
-          if (row_ok && n0 < p.N) {
-            gemm_epilogue_chunk(p, vg, m, rs, row_off, n0);
-            gemm_epilogue_chunk(p, vu, m, rs, row_off, n0 + 32);
-            gemm_epilogue_act_pair(p, vg, vu, m, rs, n0);
-          }
+          if (row_ok && n0 < p.N) gemm_epilogue_act_pair(p, vg, vu, m, rs, row_off, n0);
         }
-      } else {
+      } else if (p.gated_gu != nullptr) {
+        // down-projection dgrad with the gated-MLP backward rules fused: g_a never reaches HBM
 #pragma unroll 1
         for (int c = 0; c < BN / 32; ++c) {
           uint32_t v[32];
           tmem_ld32(taddr + c * 32, v);
           tmem_ld_wait();
           const int n0 = n_blk * BN + c * 32;
-          if (row_ok && n0 < p.N) gemm_epilogue_chunk(p, v, m, rs, row_off, n0);
+          if (row_ok && n0 < p.N) gemm_epilogue_gated_bwd(p, v, m, rs, n0);
+        }
+      } else {
+        float dacc = 0.f;
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+          uint32_t v[32];
+          tmem_ld32(taddr + c * 32, v);
+          tmem_ld_wait();
+          const int n0 = n_blk * BN + c * 32;
+          if (row_ok && n0 < p.N) {
+            const float dot = gemm_epilogue_chunk(p, v, m, rs, row_off, n0);
+            if (p.delta_o != nullptr) gemm_epilogue_delta(p, dacc, dot, m, n0);
+          }
         }
       }
       tc_fence_before();
@@ -342,7 +352,20 @@ int gemm_bf16(const void* A, int64_t lda, const void* B, int64_t ldb, int b_layo
   p.gated_out = reinterpret_cast<__nv_bfloat16*>(epi->gated_out);
   p.gated_act = epi->gated_act;
   p.gated_cp = epi->gated_cp;
+  p.gated_layout = epi->gated_layout;
+  if (epi->gated_gu != nullptr && ((N % 32) != 0 || epi->colscale != nullptr || epi->bias != nullptr || epi->resid_f32 != nullptr ||
+                                   epi->act_out != nullptr || (epi->gated_layout != 0 && epi->gated_layout != 1)))
+    return set_error(LRP_ERR_ARG, "gemm: the fused gated backward needs N % 32 == 0 and no colscale / bias / resid term");
   p.act_out = reinterpret_cast<__nv_bfloat16*>(epi->act_out);
+  p.delta_o = reinterpret_cast<const __nv_bfloat16*>(epi->delta_o);
+  p.delta_out = epi->delta_out;
+  p.delta_D = epi->delta_head_dim;
+  p.delta_S = epi->delta_seq;
+  if (p.delta_o != nullptr) {
+    if (p.delta_out == nullptr || p.delta_D <= 0 || (p.delta_D % 32) != 0 || p.delta_D > 256 || (256 % p.delta_D) != 0 || (N % p.delta_D) != 0 ||
+        p.delta_S <= 0 || (M % p.delta_S) != 0 || epi->out == nullptr || epi->out_is_f32 || epi->act_out != nullptr || epi->gated_gu != nullptr)
+      return set_error(LRP_ERR_ARG, "gemm: the fused attention delta needs a bf16 [B*S, H*D] output with D in {32,64,128,256}");
+  }
   if (p.act_out != nullptr) {
     if ((N % 64) != 0 || epi->out == nullptr || epi->out_is_f32 || epi->gated_gu != nullptr || epi->gated_act < 0 || epi->gated_act > 2 ||
         epi->colscale != nullptr || epi->resid_f32 != nullptr)
@@ -358,10 +381,12 @@ int gemm_bf16(const void* A, int64_t lda, const void* B, int64_t ldb, int b_layo
     group_forced = forced > 0;
   }
   int bn = force_bn;
+  if (p.delta_o != nullptr && bn != 2 && N >= 256) bn = force_bn = 0;
   if (bn == 0) {
     // 256-wide tiles when they still fill the machine; otherwise 128-wide for more parallelism
     const int64_t tiles256 = int64_t((M + BM - 1) / BM) * ((N + 255) / 256);
     bn = (N >= 256 && tiles256 >= sm_count()) ? 256 : 128;
+    if (p.delta_o != nullptr && bn < p.delta_D) bn = 256;   // a tile must hold whole heads
   }
   if (force_bn == 2) return gemm_bf16_pair(A, lda, B, ldb, b_layout, p, stream);   // forced CTA-pair kernel (tests)
   if (bn == 256 && force_bn == 0) {
@@ -370,7 +395,11 @@ int gemm_bf16(const void* A, int64_t lda, const void* B, int64_t ldb, int b_layo
     const int64_t tiles_pair = int64_t((M + 255) / 256) * ((N + 255) / 256);
     if (pair_mode != 0 && tiles_pair >= sm_count() / 2) {
       // the pair kernel measured best with 4096-row groups (sweep 8/16/32/64 in units of 128 rows: 15.7 / 16.2 / 16.4 / 15.6 attr/s)
-      if (!group_forced) p.group_m = 32;
+      // (LRP_GROUP_M_DEEPK=<n> sets another group for deep contractions, K >= 8192: the down projection re-reads its A operand
+      //  5-6x from DRAM — 2.8-3.8 GB per launch against 0.59 GB algorithmic — but 8 / 16 / 32 measured the same step rate,
+      //  16.8 / 16.9 / 17.0 attributions/s, so the default stays 32)
+      static const int deepk = getenv("LRP_GROUP_M_DEEPK") ? atoi(getenv("LRP_GROUP_M_DEEPK")) : 0;
+      if (!group_forced) p.group_m = (K >= 8192 && deepk > 0) ? deepk : 32;
       return gemm_bf16_pair(A, lda, B, ldb, b_layout, p, stream);
     }
   }

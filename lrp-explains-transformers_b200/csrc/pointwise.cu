@@ -411,6 +411,43 @@ __global__ void __launch_bounds__(256) embed_gather_kernel(const int64_t* __rest
   }
 }
 
+// out[i, :] = src[rows[i], :]  (fp32 rows; the last-position hidden states that feed the final norm / lm_head)
+__global__ void __launch_bounds__(256) gather_rows_f32_kernel(const float* __restrict__ src, const int64_t* __restrict__ rows,
+                                                              float* __restrict__ out, int d) {
+  const int64_t r = rows[blockIdx.x];
+  for (int i = threadIdx.x * 4; i < d; i += blockDim.x * 4)
+    *reinterpret_cast<float4*>(out + int64_t(blockIdx.x) * d + i) = *reinterpret_cast<const float4*>(src + r * d + i);
+}
+
+// Seed of the backward sweep (examples/quantized_llama.py:40-44: `max_logits.backward()` of the arg-max logit at the last position):
+// d logit[idx_b] / d h is lm_head[idx_b] pulled through the final RMSNorm with the identity rule (g * (w + off) * rstd) at the last
+// token of prompt b and zero everywhere else.  One pass writes the fp32 gradient stream and its bf16 shadow.
+__global__ void __launch_bounds__(256) seed_gradient_kernel(const __nv_bfloat16* __restrict__ lm_head, const int32_t* __restrict__ idx,
+                                                            const __nv_bfloat16* __restrict__ norm_w, float w_offset,
+                                                            const float* __restrict__ rstd_last, int S, float* __restrict__ g_h,
+                                                            __nv_bfloat16* __restrict__ g_hb, int d) {
+  const int64_t t = blockIdx.x;
+  const bool last = (t % S) == S - 1;
+  const int64_t b = t / S;
+  const __nv_bfloat16* wrow = last ? lm_head + int64_t(idx[b]) * d : nullptr;
+  const float r = last ? rstd_last[b] : 0.f;
+  for (int i = threadIdx.x * 8; i < d; i += blockDim.x * 8) {
+    float o[8];
+    if (last) {
+      float lw[8], nw[8];
+      load8(wrow + i, lw);
+      load8(norm_w + i, nw);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = lw[j] * (nw[j] + w_offset) * r;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = 0.f;
+    }
+    store8(g_h + t * d + i, o);
+    if (g_hb != nullptr) store8(g_hb + t * d + i, o);
+  }
+}
+
 __global__ void __launch_bounds__(1024) argmax_rows_kernel(const float* __restrict__ logits, int32_t* __restrict__ idx,
                                                            float* __restrict__ val, int V) {
   __shared__ float sv[32];
@@ -782,6 +819,23 @@ int lrp_act_identity_bwd(const void* gy, const void* x, void* gx, int64_t n, int
 int lrp_embed_gather(const int64_t* ids, const void* emb, float scale, float* h, int T, int d, void* stream) {
   if (T <= 0 || d <= 0 || (d % 8) != 0) return set_error(LRP_ERR_ARG, "embed_gather: d must be a positive multiple of 8");
   embed_gather_kernel<<<T, 256, 0, static_cast<cudaStream_t>(stream)>>>(ids, (const bf16*)emb, scale, h, d);
+  LRP_CHECK_LAUNCH();
+  return LRP_OK;
+}
+
+int lrp_gather_rows_f32(const float* src, const int64_t* rows, float* out, int n_rows, int d, void* stream) {
+  if (n_rows <= 0 || d <= 0 || (d % 4) != 0) return set_error(LRP_ERR_ARG, "gather_rows: d must be a positive multiple of 4");
+  gather_rows_f32_kernel<<<n_rows, 256, 0, static_cast<cudaStream_t>(stream)>>>(src, rows, out, d);
+  LRP_CHECK_LAUNCH();
+  return LRP_OK;
+}
+
+int lrp_seed_gradient(const void* lm_head, const int32_t* idx, const void* norm_w, float w_offset, const float* rstd_last, int S,
+                      float* g_h, void* g_hb, int T, int d, void* stream) {
+  if (T <= 0 || S <= 0 || (T % S) != 0 || d <= 0 || (d % 8) != 0)
+    return set_error(LRP_ERR_ARG, "seed_gradient: T must be a multiple of S and d a multiple of 8");
+  seed_gradient_kernel<<<T, 256, 0, static_cast<cudaStream_t>(stream)>>>((const bf16*)lm_head, idx, (const bf16*)norm_w, w_offset,
+                                                                        rstd_last, S, g_h, (bf16*)g_hb, d);
   LRP_CHECK_LAUNCH();
   return LRP_OK;
 }

@@ -35,6 +35,11 @@ class Epilogue(C.Structure):
         ("gated_act", C.c_int32),
         ("gated_cp", C.c_int32),
         ("act_out", C.c_void_p),
+        ("delta_o", C.c_void_p),
+        ("delta_out", C.c_void_p),
+        ("delta_head_dim", C.c_int32),
+        ("delta_seq", C.c_int32),
+        ("gated_layout", C.c_int32),
     ]
 
 
@@ -72,6 +77,8 @@ SIGNATURES = {
     ),
     "lrp_embed_gather": (_i, [_vp, _vp, _f, _vp, _i, _i, _vp]),
     "lrp_argmax_rows": (_i, [_vp, _vp, _vp, _i, _i, _vp]),
+    "lrp_gather_rows_f32": (_i, [_vp, _vp, _vp, _i, _i, _vp]),
+    "lrp_seed_gradient": (_i, [_vp, _vp, _vp, _f, _vp, _i, _vp, _vp, _i, _i, _vp]),
     "lrp_gxi_reduce": (_i, [_vp, _vp, _vp, _i, _i, _vp]),
     "lrp_gxi_reduce_bf16": (_i, [_vp, _vp, _vp, _i, _i, _vp]),
     "lrp_gxi_reduce_mixed": (_i, [_vp, _vp, _vp, _i, _i, _vp]),
@@ -101,7 +108,7 @@ SIGNATURES = {
     "lrp_attn_fwd_varlen": (_i, [_vp, _vp, _vp, _i64, _i64, _i64, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _i, _i, _vp]),
     "lrp_attn_bwd_varlen": (
         _i,
-        [_vp, _vp, _vp, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _vp, _vp, _vp,
+        [_vp, _vp, _vp, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _vp, _vp, _vp, _i,
          _i, _i, _i, _i, _i, _f, _i, _i, _f, _f, _f, _vp],
     ),
     "lrp_attn_bwd_workspace_bytes": (_i, [_i, _i, _i, _i, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),

@@ -124,7 +124,11 @@ class LlamaAttnLRPEngine:
         # separate kernel (A/B); the validation mode always uses the separate fp32 kernel on the same layout.
         self.gu_layout = 1 if dims.I % 32 == 0 else 0
         self.fuse_act = self.gu_layout == 1 and not self.hp and os.environ.get("LRP_FUSE_ACT", "1") == "1"
-        self.fuse_gated = os.environ.get("LRP_FUSE_GATED", "0") == "1" and not self.hp and self.gu_layout == 0
+        self.fuse_delta = os.environ.get("LRP_FUSE_DELTA", "1") == "1" and dims.D in (32, 64, 128, 256) and (dims.H * dims.D) % 256 == 0
+        # the backward counterpart: (g_a/2, identity rule on the activation, product rule) in the down-dgrad epilogue.  Round 1's
+        # version (IEEE division, activation chosen per element) was slower than the separate kernel; the lean epilogue
+        # (approximate ex2 / rcp, activation as a template parameter) is not: LRP_FUSE_GATED=0 restores the separate kernel.
+        self.fuse_gated = os.environ.get("LRP_FUSE_GATED", "1") == "1" and not self.hp and dims.I % 32 == 0
         bf = lambda t: t.to(device=device, dtype=torch.bfloat16).contiguous()
         f32 = lambda t: t.to(device=device, dtype=torch.float32).contiguous()
         self.emb = bf(weights["emb"])
@@ -361,9 +365,14 @@ class LlamaAttnLRPEngine:
         ws["g_gu"] = e(T, 2 * m.I)
         ws["g_o"] = e(T, m.H * m.D)
         ws["g_qkv"] = e(T, m.qkv_width)
-        ws["dq_acc"] = None if self.hp else e(B, S, m.H, m.D, dt=torch.float32)
+        # zero once: every attention backward leaves it zero again (LRP_ATTN_ACC_ZERO)
+        ws["dq_acc"] = None if self.hp else torch.zeros(B, S, m.H, m.D, dtype=torch.float32, device=dev)
         ws["delta"] = e(B, m.H, S, dt=torch.float32)
         ws["logits"] = e(B, m.V, dt=torch.float32)
+        ws["h_last"] = e(B, m.d, dt=torch.float32)
+        ws["xn_last"] = e(B, m.d)
+        ws["rstd_last"] = e(B, dt=torch.float32)
+        ws["idx"] = e(B, dt=torch.int32)
         ws["last_rows"] = (torch.arange(B, device=dev, dtype=torch.int64) + 1) * S - 1
         self._ws_key, self._ws = key, ws
         return ws
@@ -476,7 +485,7 @@ class LlamaAttnLRPEngine:
             src = ops.rmsnorm_bwd(g_hb, lw["ln_post_ff"], st.rstd_pf, w_offset=off, out=ws["y"])
         if self.fuse_gated:
             # down dgrad with (÷2, identity rule on SiLU, product rule) fused into its epilogue: g_a never touches HBM
-            ops.linear_dgrad_gated_bwd(src, lw["wd"], st.gu, ws["g_gu"], m.act_code, self.cp)
+            ops.linear_dgrad_gated_bwd(src, lw["wd"], st.gu, ws["g_gu"], m.act_code, self.cp, layout=self.gu_layout)
         else:
             ops.linear_dgrad(src, lw["wd"], ws["a"])                               # g_a [T, I]
             C.check(lib.lrp_gated_act_bwd_t(ws["a"].data_ptr(), st.gu.data_ptr(), ws["g_gu"].data_ptr(), f, self.gu_layout, T, m.I,
@@ -486,7 +495,12 @@ class LlamaAttnLRPEngine:
         src = g_hb
         if m.post_norms:
             src = ops.rmsnorm_bwd(g_hb, lw["ln_post_attn"], st.rstd_pa, w_offset=off, out=ws["y"])
-        ops.linear_dgrad(src, lw["wo"], ws["g_o"])                                 # g_o [T, H D]
+        # g_o [T, H D]; its epilogue also emits delta = sum_d o * g_o per (b, h, s) for the attention backward (no separate pass)
+        fuse_delta = not self.hp and self.fuse_delta
+        if fuse_delta:
+            ops.linear_dgrad(src, lw["wo"], ws["g_o"], delta=(st.o, ws["delta"], m.D, S))
+        else:
+            ops.linear_dgrad(src, lw["wo"], ws["g_o"])
         q, k, v = self._qkv_views(st.qkv, B, S)
         dq, dk, dv = self._qkv_views(ws["g_qkv"], B, S)
         divs = (0.0, 0.0, 1.0) if self.cp else (4.0, 4.0, 2.0)
@@ -496,11 +510,12 @@ class LlamaAttnLRPEngine:
                                          dv.data_ptr(), m.qkv_width, m.qkv_width, m.qkv_width, ws["delta"].data_ptr(), None, B, S, m.H,
                                          m.Hkv, m.D, scale, 1, win, *divs, ops._stream()), "attn_bwd_f32")
         else:
-            C.check(lib.lrp_attn_bwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), m.qkv_width, m.qkv_width, m.qkv_width,
-                                     st.o.data_ptr(), ws["g_o"].data_ptr(), st.lse.data_ptr(), dq.data_ptr(), dk.data_ptr(),
-                                     dv.data_ptr(), m.qkv_width, m.qkv_width, m.qkv_width, ws["dq_acc"].data_ptr(),
-                                     ws["delta"].data_ptr(), B, S, m.H, m.Hkv, m.D, scale, 1, win, *divs, ops._stream()),
-                    "attn_bwd")
+            flags = (1 if fuse_delta else 0) | 2      # LRP_ATTN_DELTA_READY | LRP_ATTN_ACC_ZERO
+            C.check(lib.lrp_attn_bwd_varlen(q.data_ptr(), k.data_ptr(), v.data_ptr(), m.qkv_width, m.qkv_width, m.qkv_width,
+                                            st.o.data_ptr(), ws["g_o"].data_ptr(), st.lse.data_ptr(), dq.data_ptr(), dk.data_ptr(),
+                                            dv.data_ptr(), m.qkv_width, m.qkv_width, m.qkv_width, ws["dq_acc"].data_ptr(),
+                                            ws["delta"].data_ptr(), None, flags, B, S, m.H, m.Hkv, m.D, scale, 1, win, *divs,
+                                            ops._stream()), "attn_bwd")
         ops.rope_inplace(ws["g_qkv"], m.H + m.Hkv, m.D, cos, sin, S, inverse=True)
         if m.qk_norm:
             C.check(lib.lrp_headnorm_inplace_t(ws["g_qkv"].data_ptr(), f, m.qkv_width, m.H, m.Hkv, m.D, lw["qn"].data_ptr(),
@@ -548,17 +563,18 @@ class LlamaAttnLRPEngine:
                 self._layer_fwd(lw, ws["stores"][l % seg], h, ws, B, S, l)
 
         # ---- head: only the last position is read (examples/quantized_llama.py:40)
-        h_last = h.index_select(0, ws["last_rows"])
-        xn_last, rstd_last = ops.rmsnorm_fwd(h_last, self.norm_w, m.eps, w_offset=m.norm_offset, out_dtype=self.adt)
+        C.check(lib.lrp_gather_rows_f32(h.data_ptr(), ws["last_rows"].data_ptr(), ws["h_last"].data_ptr(), B, m.d, ops._stream()),
+                "gather_rows")
+        xn_last, rstd_last = ops.rmsnorm_fwd(ws["h_last"], self.norm_w, m.eps, w_offset=m.norm_offset, out_dtype=self.adt,
+                                             out=ws["xn_last"], rstd=ws["rstd_last"])
         ops.linear_fwd(xn_last, self.lm_head, ws["logits"])
-        idx, _ = ops.argmax_rows(ws["logits"])
-        # seed: d(max logit)/d(xn_last) = lm_head[idx]; through the final norm with the identity rule
-        g_xn_last = self.lm_head.index_select(0, idx.long())
-        g_last = ops.rmsnorm_bwd(g_xn_last, self.norm_w, rstd_last, w_offset=m.norm_offset, out_dtype=torch.float32)
-        g_h.zero_()
-        g_h.index_copy_(0, ws["last_rows"], g_last)
-        if not self.hp:
-            ops.cast_bf16(g_h, g_hb)
+        C.check(lib.lrp_argmax_rows(ws["logits"].data_ptr(), ws["idx"].data_ptr(), None, B, m.V, ops._stream()), "argmax_rows")
+        idx = ws["idx"]
+        # seed: d(max logit)/d(xn_last) = lm_head[idx], through the final norm with the identity rule, scattered to the last position
+        # of every prompt (zero elsewhere) together with the bf16 shadow: one launch
+        C.check(lib.lrp_seed_gradient(self.lm_head.data_ptr(), idx.data_ptr(), self.norm_w.data_ptr(), m.norm_offset,
+                                      rstd_last.data_ptr(), S, g_h.data_ptr(), None if self.hp else g_hb.data_ptr(), T, m.d,
+                                      ops._stream()), "seed_gradient")
 
         if self.store_policy == "all":
             layer_rel = [None] * m.L

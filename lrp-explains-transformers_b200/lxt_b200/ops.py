@@ -48,7 +48,7 @@ def _rowmajor2d(t: torch.Tensor, name: str) -> int:
 
 def make_epilogue(out: torch.Tensor, *, resid: Optional[torch.Tensor] = None, rowscale=None, colscale=None, bias=None,
                   shadow: Optional[torch.Tensor] = None, alpha: float = 1.0, act_out: Optional[torch.Tensor] = None,
-                  act: int = ACT_SILU) -> Epilogue:
+                  act: int = ACT_SILU, delta=None) -> Epilogue:
     ldc = _rowmajor2d(out, "out")
     e = Epilogue()
     e.out = out.data_ptr()
@@ -77,6 +77,14 @@ def make_epilogue(out: torch.Tensor, *, resid: Optional[torch.Tensor] = None, ro
             raise _capi.LrpError("act_out must be a contiguous bf16 [M, N/2] tensor next to a bf16 output")
         e.act_out = act_out.data_ptr()
         e.gated_act = act
+    if delta is not None:   # (o bf16 [M, N], delta_out fp32 [B,H,S], head_dim, seq): fused attention-backward prologue
+        o_t, d_out, D, S = delta
+        _need(o_t, torch.bfloat16, "delta o")
+        _need(d_out, torch.float32, "delta out")
+        if out.dtype != torch.bfloat16 or o_t.shape != out.shape or _rowmajor2d(o_t, "delta o") != ldc or not d_out.is_contiguous() \
+                or d_out.numel() != out.shape[0] * (out.shape[1] // D):
+            raise _capi.LrpError("fused delta: o must share the bf16 output's shape / layout, delta_out holds B*H*S floats")
+        e.delta_o, e.delta_out, e.delta_head_dim, e.delta_seq = o_t.data_ptr(), d_out.data_ptr(), int(D), int(S)
     return e
 
 
@@ -183,7 +191,7 @@ def _gemm_batched_bf16(a, b, out, a_layout, b_layout, accumulate):
 
 
 def linear_dgrad_gated_bwd(gy: torch.Tensor, w: torch.Tensor, gu: torch.Tensor, ggu: torch.Tensor, act: int = ACT_SILU,
-                           cp: bool = False) -> torch.Tensor:
+                           cp: bool = False, layout: int = 0) -> torch.Tensor:
     """Down-projection LRP dgrad with the gated-MLP point-wise rules fused into the epilogue:
     g_a = gy @ w  (never written);  ggu = [g_gate | g_up] as `gated_act_bwd(g_a, gu)` would produce.
     gy [T,d] bf16, w [d,I] bf16 (nn.Linear layout of down_proj), gu/ggu [T,2I] bf16 contiguous."""
@@ -198,7 +206,7 @@ def linear_dgrad_gated_bwd(gy: torch.Tensor, w: torch.Tensor, gu: torch.Tensor, 
     e = Epilogue()
     e.alpha = 1.0
     e.ldc = I
-    e.gated_gu, e.gated_out, e.gated_act, e.gated_cp = gu.data_ptr(), ggu.data_ptr(), act, int(cp)
+    e.gated_gu, e.gated_out, e.gated_act, e.gated_cp, e.gated_layout = gu.data_ptr(), ggu.data_ptr(), act, int(cp), int(layout)
     prof = GEMM_PROFILE
     if prof is not None:
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -385,7 +393,7 @@ def attn_fwd(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, scale: float, *,
 
 
 def attn_bwd(q, k, v, o, d_o, lse, scale: float, *, causal: bool = True, window: int = 0, q_div: float = 4.0,
-             k_div: float = 4.0, v_div: float = 2.0, dq=None, dk=None, dv=None, dq_acc=None, delta=None, kv_range=None):
+             k_div: float = 4.0, v_div: float = 2.0, dq=None, dk=None, dv=None, dq_acc=None, delta=None, kv_range=None, flags: int = 0):
     """LRP backward of attention: returns (dq, dk, dv) already divided by (q_div, k_div, v_div)."""
     dt = q.dtype
     if dt not in (torch.float32, torch.bfloat16):
@@ -418,8 +426,8 @@ def attn_bwd(q, k, v, o, d_o, lse, scale: float, *, causal: bool = True, window:
         delta = torch.empty((B, H, S), dtype=torch.float32, device=q.device)
     check(_capi.lib().lrp_attn_bwd_varlen(q.data_ptr(), k.data_ptr(), v.data_ptr(), ldq, ldk, ldv, o.data_ptr(), d_o.data_ptr(),
                                           lse.data_ptr(), dq.data_ptr(), dk.data_ptr(), dv.data_ptr(), lddq, lddk, lddv,
-                                          dq_acc.data_ptr(), delta.data_ptr(), _kv_range_ptr(kv_range, B), B, S, H, Hkv, D, scale,
-                                          int(causal), window, q_div, k_div, v_div, _stream()), "lrp_attn_bwd")
+                                          dq_acc.data_ptr(), delta.data_ptr(), _kv_range_ptr(kv_range, B), int(flags), B, S, H, Hkv, D,
+                                          scale, int(causal), window, q_div, k_div, v_div, _stream()), "lrp_attn_bwd")
     return dq, dk, dv
 
 

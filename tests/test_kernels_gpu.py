@@ -192,6 +192,15 @@ def test_fused_gated_backward_epilogue_equals_unfused(ops, cp):
     s = torch.nn.functional.silu(gate)
     exp = torch.cat([torch.zeros_like(gate), ga32 * s], 1) if cp else torch.cat([(s / (gate + 1e-10)) * (ga32 / 2 * up), ga32 / 2 * s], 1)
     assert rel_l2(got.float(), exp) < 3e-3
+    # interleaved (gate | up) layout + GELU-tanh: the form the engine uses
+    for act in (0, 1):
+        blk = lambda t: torch.stack([t[:, :I].reshape(T, I // 32, 32), t[:, I:].reshape(T, I // 32, 32)], 2).reshape(T, 2 * I).contiguous()
+        gu_il = blk(gu)
+        got_il = ops.linear_dgrad_gated_bwd(gy, w, gu_il, torch.empty_like(gu), act=act, cp=cp, layout=1)
+        ref_il = ops.gated_act_bwd(ga, gu_il, act, cp=cp, layout=1)
+        assert rel_l2(got_il.float(), ref_il.float()) < 4e-3
+        if act == 0:
+            assert rel_l2(got_il.float(), blk(exp)) < 3e-3
 
 
 @pytest.mark.parametrize("shape", [(300, 512, 256), (4096, 28672 // 4, 1024), (257, 1152, 192)])
@@ -213,7 +222,13 @@ def test_gate_up_gemm_with_fused_activation_epilogue(shape, act):
     ops.linear_fwd(x, w_il, gu_u)
     a_u = ops.gated_act_fwd(gu_u, act, layout=1)
     assert torch.equal(gu_f, gu_u)
-    assert torch.equal(a_f, a_u)
+    # the fused epilogue evaluates the activation with ex2 / rcp / tanh approximations (fp32 relative error ~1e-6), the point-wise
+    # kernel with IEEE division: the bf16 results agree except where that difference crosses a rounding boundary (1 bf16 ulp)
+    da = (a_f.float() - a_u.float()).abs()
+    # (absolute floor: in GELU-tanh's far negative tail 1 + tanh(u) cancels in the fp32 of the point-wise kernel and of torch,
+    #  the x * sigmoid(2u) form of the epilogue does not; the values there are ~1e-6 of the typical magnitude)
+    assert bool((da <= 0.0079 * a_u.float().abs() + 2e-6 * float(a_u.float().abs().max())).all())
+    assert float((da > 0).float().mean()) < 0.02
     # and against torch on the de-interleaved halves
     gate = (x.float() @ wg.float().T).to(torch.bfloat16).float()
     up = (x.float() @ wu.float().T).to(torch.bfloat16).float()
