@@ -356,8 +356,11 @@ def run_b200(args):
 
     if int(os.environ.get("WORLD_SIZE", "1")) > 1:
         # keep the communicator set-up lines (nranks, NVLS / P2P transport) in stderr as evidence of the one collective
-        os.environ.setdefault("NCCL_DEBUG", "INFO")
-        os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
+        # (to stderr: stdout carries exactly one JSON line; an image-level NCCL_DEBUG=VERSION/WARN is raised to INFO)
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION", "WARN"):
+            os.environ["NCCL_DEBUG"] = "INFO"
+            os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
+            os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     rank, world, local = ldist.init_from_env("nccl")
     if world != args.gpus and world > 1:
         args.gpus = world

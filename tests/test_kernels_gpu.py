@@ -243,3 +243,45 @@ def test_gate_up_gemm_with_fused_activation_epilogue(shape, act):
     ggu_h = ops.gated_act_bwd(ga, gu_h, act, layout=0)
     b2 = ggu_il.view(T, I // 32, 2, 32)
     assert torch.equal(torch.cat([b2[:, :, 0].reshape(T, I), b2[:, :, 1].reshape(T, I)], 1), ggu_h)
+
+
+@pytest.mark.parametrize("B,S,H,Hkv,D,causal,window", [(3, 300, 4, 2, 128, True, 0), (3, 520, 4, 2, 64, True, 0), (2, 300, 2, 1, 256, True, 0),
+                                                       (3, 333, 4, 4, 128, False, 0), (2, 520, 4, 1, 64, True, 200), (2, 2100, 8, 2, 128, True, 0)])
+def test_flash_attnlrp_key_padding_ranges(ops, B, S, H, Hkv, D, causal, window):
+    """batches of prompts of different lengths: one valid-key range [lo, hi) per sequence (left / right padding / both) in every
+    attention kernel (persistent forward D=128, first-generation forward D=64/256, pipelined backward, two-pass backward D=256) vs an
+    fp32 torch reference with the corresponding boolean mask.  Query rows that see no key give o = 0, lse = -inf, zero gradients."""
+    qkv = rnd(B, S, (H + 2 * Hkv) * D, scale=1.0, seed=31)
+    q = qkv[:, :, : H * D].view(B, S, H, D)
+    k = qkv[:, :, H * D: (H + Hkv) * D].view(B, S, Hkv, D)
+    v = qkv[:, :, (H + Hkv) * D:].view(B, S, Hkv, D)
+    d_o = rnd(B, S, H, D, seed=32)
+    scale = 1 / math.sqrt(D)
+    rng = torch.tensor([[0, S], [S // 3 + 5, S], [7, S - S // 4]][:B], dtype=torch.int32, device="cuda")   # none, left, both
+    o, lse = ops.attn_fwd(q, k, v, scale, causal=causal, window=window, kv_range=rng)
+    dq, dk, dv = ops.attn_bwd(q, k, v, o, d_o, lse, scale, causal=causal, window=window, kv_range=rng)
+    # reference with the same mask
+    G = H // Hkv
+    qf, kf, vf = (t.float().transpose(1, 2).requires_grad_() for t in (q, k, v))
+    kr, vr = kf.repeat_interleave(G, 1), vf.repeat_interleave(G, 1)
+    sc = qf @ kr.transpose(-1, -2) * scale
+    i = torch.arange(S, device="cuda")
+    m = torch.zeros(B, 1, S, S, dtype=torch.bool, device="cuda")
+    if causal:
+        m |= (i[None, :] > i[:, None])[None, None]
+    if window:
+        m |= ((i[:, None] - i[None, :]) >= window)[None, None]
+    m |= ((i[None, :] < rng[:, 0, None]) | (i[None, :] >= rng[:, 1, None]))[:, None, None, :]
+    dead = m.all(-1, keepdim=True)                                           # query rows that see nothing
+    p = sc.masked_fill(m, float("-inf")).masked_fill(dead, 0.0).softmax(-1).masked_fill(dead, 0.0)
+    oref = (p @ vr).transpose(1, 2)
+    oref.backward(d_o.float())
+    live = (~dead.squeeze(-1)).transpose(1, 2).unsqueeze(-1).expand(B, S, H, 1)   # [B,S,H,1]
+    assert rel_l2(o.float(), oref.detach()) < 5e-3
+    assert bool((o.float().abs().amax(-1, keepdim=True)[~live] == 0).all())
+    lse_ref = torch.logsumexp(sc.masked_fill(m, float("-inf")), -1)
+    ok = torch.isfinite(lse_ref)
+    assert rel_l2(lse[ok], lse_ref[ok]) < 1e-5 and bool((lse[~ok] == float("-inf")).all())
+    assert rel_l2(dq.float(), qf.grad.transpose(1, 2) / 4) < 8e-3
+    assert rel_l2(dk.float(), kf.grad.transpose(1, 2) / 4) < 8e-3
+    assert rel_l2(dv.float(), vf.grad.transpose(1, 2) / 2) < 8e-3
