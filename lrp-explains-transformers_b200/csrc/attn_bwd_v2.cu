@@ -82,7 +82,8 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_const
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int jt = blockIdx.x, hk = blockIdx.y, b = blockIdx.z;
+  int jt, hk, b;
+  sched_decode((p.S + ATT_TILE - 1) / ATT_TILE, p.Hkv, p.B, p.sched_group, jt, hk, b);
   const int G = p.H / p.Hkv;
   const int k0 = jt * ATT_TILE;
   const int nq = (p.S + QT - 1) / QT;
@@ -195,7 +196,7 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_const
       if (key >= kvhi || key < kvlo) { lo = 1; hi = 0; }   // padded (or out-of-range) key: attended by nobody
       const bool need_mask = (p.causal && q0 < k0 + ATT_TILE - 1) || (q0 + QT > p.S) || (k0 + ATT_TILE > kvhi) || (k0 < kvlo) ||
                              (p.window > 0 && q0 + QT - 1 - k0 >= p.window);
-      const bool dbgt = p.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && it < 64 && sid == 0;
+      const bool dbgt = p.dbg != nullptr && blockIdx.x == 0 && it < 64 && sid == 0;
       if (dbgt) p.dbg[it * 16 + 8] = clock64();
       mbar_wait(&st_full[tb], (it >> 1) & 1);
       if (dbgt) p.dbg[it * 16 + 9] = clock64();
@@ -301,8 +302,10 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constan
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int qt = gridDim.x - 1 - blockIdx.x;
-  const int h = blockIdx.y, b = blockIdx.z;
+  const int nqt = (p.S + ATT_TILE - 1) / ATT_TILE;
+  int trank, h, b;
+  sched_decode(nqt, p.H, p.B, p.sched_group, trank, h, b);
+  const int qt = nqt - 1 - trank;
   const int hk = h / (p.H / p.Hkv);
   const int q0 = qt * ATT_TILE;
   const int nkv = (p.S + QT - 1) / QT;
@@ -462,7 +465,7 @@ static int launch_dkdv(const CUtensorMap& tq64, const CUtensorMap& tk128, const 
     done = true;
   }
   const int tiles = (p.S + ATT_TILE - 1) / ATT_TILE;
-  ka<<<dim3(tiles, p.Hkv, p.B), V2_THREADS, dkdv_smem<D, MODE>(), st>>>(tq64, tk128, tv128, tdo64, p);
+  ka<<<dim3(tiles * p.Hkv * p.B), V2_THREADS, dkdv_smem<D, MODE>(), st>>>(tq64, tk128, tv128, tdo64, p);
   LRP_CHECK_LAUNCH();
   return LRP_OK;
 }
@@ -487,7 +490,7 @@ static int launch_v2(const CUtensorMap& tq128, const CUtensorMap& tk128, const C
   }
   const int tiles = (p.S + ATT_TILE - 1) / ATT_TILE;
   if (dqp.inv_q_div != 0.f) {
-    kb<<<dim3(tiles, p.H, p.B), V2_THREADS, dq_smem<D>(), st>>>(tq128, tk64, tv64, tdo128, p, dqp);
+    kb<<<dim3(tiles * p.H * p.B), V2_THREADS, dq_smem<D>(), st>>>(tq128, tk64, tv64, tdo128, p, dqp);
     LRP_CHECK_LAUNCH();
   } else {
     // CP-LRP: q is detached, dQ = 0 (strided rows of the caller's buffer)
@@ -517,6 +520,7 @@ int attn_bwd_v2(const void* q, const void* k, const void* v, int64_t ldq, int64_
   p.B = B; p.S = S; p.H = H; p.Hkv = Hkv; p.D = D;
   p.scale = scale; p.scale_log2 = scale * LOG2E;
   p.causal = causal; p.window = window;
+  p.sched_group = sched_group_default();
   p.lse = const_cast<float*>(lse);
   p.delta = delta;
   p.dk = reinterpret_cast<__nv_bfloat16*>(dk);

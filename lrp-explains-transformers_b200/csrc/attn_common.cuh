@@ -3,6 +3,7 @@
 #pragma once
 #include <math.h>
 #include <string.h>
+#include <stdlib.h>
 #include "ptx_sm100.cuh"
 #include "lrp_internal.h"
 
@@ -32,7 +33,41 @@ struct AttnParams {
   // optional per-sequence range of VALID keys [kv_range[2b], kv_range[2b+1]) (left / right padding of a batch of prompts of
   // different lengths): keys outside it are masked for every query.  NULL = all S keys valid.
   const int* kv_range;
+  // CTA order of the tile-loop kernels: the grid is 1-D and walks groups of `sched_group` sequences tile-major, so the
+  // heaviest causal tiles of a group are dispatched first (longest-processing-time order; 0 = one group = whole batch)
+  int sched_group;
 };
+
+// linear block id -> (tile rank t, y, z) under the order above.  `t` counts tiles in dispatch order; the caller maps it to the
+// heaviest-first tile index (key tile t for the backward, query tile tiles-1-t for the forward).
+__device__ __forceinline__ void sched_decode(int tiles, int Y, int Z, int group, int& t, int& y, int& z) {
+  if (group < 0) {   // first-generation order (tile index fastest): kept for A/B runs, LRP_ATTN_SCHED_GROUP=-1
+    t = int(blockIdx.x) % tiles;
+    y = (int(blockIdx.x) / tiles) % Y;
+    z = int(blockIdx.x) / (tiles * Y);
+    return;
+  }
+  if (group == 0 || group > Z) group = Z;
+  const int per_group = tiles * Y * group;
+  const int ngroups = (Z + group - 1) / group;
+  const int g0 = min(int(blockIdx.x) / per_group, ngroups - 1);
+  const int r = int(blockIdx.x) - g0 * per_group;
+  const int zc = min(group, Z - g0 * group);
+  const int per_tile = Y * zc;
+  t = r / per_tile;
+  const int rr = r - t * per_tile;
+  z = g0 * group + rr / Y;
+  y = rr - (rr / Y) * Y;
+}
+
+inline int sched_group_default() {
+  static int g = -2;
+  if (g == -2) {
+    const char* e = getenv("LRP_ATTN_SCHED_GROUP");
+    g = e != nullptr ? atoi(e) : 2;
+  }
+  return g;
+}
 
 __device__ __forceinline__ void kv_bounds(const AttnParams& p, int b, int& kvlo, int& kvhi) {
   kvlo = 0;
@@ -79,13 +114,28 @@ __device__ __forceinline__ float chunk_max(const uint32_t (&v)[32], int c0, int 
 }
 
 // f[i] = 2^(s*scale_log2 - msub) (0 where masked); returns the chunk's sum
-template <bool MASK>
+// 2^x on the FMA pipe (no MUFU): x = n + f with n = rint(x) taken from the low mantissa bits of x + 1.5*2^23, 2^f by a degree-3
+// polynomial on [-0.5, 0.5] (max relative error 1.0e-4 = 1/40 of the bf16 rounding the result goes through; coefficient
+// study in profiles/microbench/exp2_poly_accuracy.txt), exponent added by integer arithmetic.  Valid for x <= ~120.
+__device__ __forceinline__ float ex2_poly3(float x) {
+  x = fmaxf(x, -125.f);
+  const float magic = 12582912.f;
+  const float t = x + magic;
+  const float f = x - (t - magic);
+  const float pl = fmaf(fmaf(fmaf(0.05592204f, f, 0.24264008f), f, 0.69312102f), f, 0.99992448f);
+  return __int_as_float(__float_as_int(pl) + (__float_as_int(t) << 23));
+}
+
+// POLY > 0: every POLY-th exponential of the chunk is evaluated by ex2_poly3 instead of MUFU.EX2 (16 lanes/clk/SM), which is
+// what bounds soft-max pass A of the backward (16384 exponentials per 128x128 tile = 1024 MUFU cycles)
+template <bool MASK, int POLY = 0>
 __device__ __forceinline__ float chunk_exp(const uint32_t (&v)[32], float (&f)[32], float scale_log2, float msub, int c0,
                                            int lo, int hi) {
   float sum = 0.f;
 #pragma unroll
   for (int i = 0; i < 32; ++i) {
-    float pe = ex2_approx(fmaf(__uint_as_float(v[i]), scale_log2, -msub));
+    const float arg = fmaf(__uint_as_float(v[i]), scale_log2, -msub);
+    float pe = (POLY > 0 && (i % (POLY > 0 ? POLY : 1)) == POLY - 1) ? ex2_poly3(arg) : ex2_approx(arg);
     if (MASK) pe = (c0 + i > hi || c0 + i < lo) ? 0.f : pe;
     f[i] = pe;
     sum += pe;

@@ -47,8 +47,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int qt = gridDim.x - 1 - blockIdx.x;  // heaviest causal tiles first
-  const int h = blockIdx.y, b = blockIdx.z;
+  const int nqt = (p.S + ATT_TILE - 1) / ATT_TILE;
+  int trank, h, b;
+  sched_decode(nqt, p.H, p.B, p.sched_group, trank, h, b);
+  const int qt = nqt - 1 - trank;  // heaviest causal tiles first
   const int hk = h / (p.H / p.Hkv);
   const int q0 = qt * ATT_TILE;
   const int nkv = (p.S + BN - 1) / BN;
@@ -251,7 +253,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int jt = blockIdx.x, hk = blockIdx.y, b = blockIdx.z;
+  int jt, hk, b;
+  sched_decode((p.S + ATT_TILE - 1) / ATT_TILE, p.Hkv, p.B, p.sched_group, jt, hk, b);
   const int G = p.H / p.Hkv;
   const int k0 = jt * ATT_TILE;
   const int nq = (p.S + ATT_TILE - 1) / ATT_TILE;
@@ -287,7 +290,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__
       for (int it = 0; it < n_it; ++it) {
         const int g = it / ni, i = i_lo + (it - g * ni);
         const int h = hk * G + g;
-        const bool dbg = p.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && it < 64;
+        const bool dbg = p.dbg != nullptr && blockIdx.x == 0 && it < 64;
         if (dbg) p.dbg[it * 16 + 0] = clock64();
         mbar_expect_tx(qdo_full, 2 * TILE_BYTES);
         load_tile<D>(sQ, &tmq, qdo_full, h * D, i * ATT_TILE, b);
@@ -335,7 +338,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__
       if (!row_ok) lse2 = 0.f;
       const bool need_mask = (p.causal && k0 + ATT_TILE - 1 > i * ATT_TILE) || (k0 + ATT_TILE > kvhi) || (k0 < kvlo) ||
                              (p.window > 0 && i * ATT_TILE + ATT_TILE - 1 - k0 >= p.window);
-      const bool dbgt = p.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && it < 64 && threadIdx.x == 0;
+      const bool dbgt = p.dbg != nullptr && blockIdx.x == 0 && it < 64 && threadIdx.x == 0;
       if (dbgt) p.dbg[it * 16 + 8] = clock64();
       mbar_wait(s_full, it & 1);
       if (dbgt) p.dbg[it * 16 + 9] = clock64();
@@ -433,7 +436,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__
 //   * the soft-max work is split in two passes: pass A (P = 2^(S*scale_log2 - lse2), the MUFU-heavy half) needs only S
 //     and overlaps the dO_{i+1} load and the dP_{i+1} MMA; pass B (dS = P * (dP*scale - delta*scale)) follows dp_full;
 //   * dQ_i leaves as asynchronous bulk tensor reductions from the P/dS smem (free between MMA2_i and pass A's P store).
-template <int D>
+template <int D, int POLY>
 __global__ void __launch_bounds__(BWD_THREADS, 1)
 attn_bwd_pipe_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__ CUtensorMap tmk,
                      const __grid_constant__ CUtensorMap tmv, const __grid_constant__ CUtensorMap tmdo,
@@ -462,7 +465,8 @@ attn_bwd_pipe_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_const
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int jt = blockIdx.x, hk = blockIdx.y, b = blockIdx.z;
+  int jt, hk, b;
+  sched_decode((p.S + ATT_TILE - 1) / ATT_TILE, p.Hkv, p.B, p.sched_group, jt, hk, b);
   const int G = p.H / p.Hkv;
   const int k0 = jt * ATT_TILE;
   const int nq = (p.S + ATT_TILE - 1) / ATT_TILE;
@@ -470,7 +474,7 @@ attn_bwd_pipe_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_const
   const int i_hi = p.window > 0 ? min(nq - 1, (k0 + ATT_TILE - 1 + p.window - 1) / ATT_TILE) : nq - 1;
   const int ni = i_hi - i_lo + 1;
   const int n_it = ni > 0 ? ni * G : 0;
-  const bool dbg_cta = p.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
+  const bool dbg_cta = p.dbg != nullptr && blockIdx.x == 0;
   int kvlo, kvhi;
   kv_bounds(p, b, kvlo, kvhi);
 
@@ -615,8 +619,8 @@ attn_bwd_pipe_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_const
         uint32_t vs[32];
         tmem_ld32(tmem_S + lane_base + (ch * 2 + cc) * 32, vs);
         tmem_ld_wait();
-        if (mask_tile) chunk_exp<true>(vs, pf[cc], p.scale_log2, lse2, (ch * 2 + cc) * 32, lo, hi);
-        else chunk_exp<false>(vs, pf[cc], p.scale_log2, lse2, (ch * 2 + cc) * 32, lo, hi);
+        if (mask_tile) chunk_exp<true, POLY>(vs, pf[cc], p.scale_log2, lse2, (ch * 2 + cc) * 32, lo, hi);
+        else chunk_exp<false, POLY>(vs, pf[cc], p.scale_log2, lse2, (ch * 2 + cc) * 32, lo, hi);
       }
       if (dbgt) p.dbg[it * 24 + 10] = clock64();
       if (it > 0) {  // the previous tile's first dQ reduction group must have read the P half of the staging smem out
@@ -809,7 +813,7 @@ static int launch_fwd(const CUtensorMap& tq, const CUtensorMap& tk, const CUtens
     if (ce != cudaSuccess) return set_error(LRP_ERR_CUDA, cudaGetErrorString(ce));
     done = true;
   }
-  dim3 grid((p.S + ATT_TILE - 1) / ATT_TILE, p.H, p.B);
+  dim3 grid(((p.S + ATT_TILE - 1) / ATT_TILE) * p.H * p.B);
   kern<<<grid, ATT_THREADS, fwd_smem_bytes<D, BN>(), st>>>(tq, tk, tv, p);
   LRP_CHECK_LAUNCH();
   return LRP_OK;
@@ -825,23 +829,23 @@ static int launch_bwd(const CUtensorMap& tq, const CUtensorMap& tk, const CUtens
     if (ce != cudaSuccess) return set_error(LRP_ERR_CUDA, cudaGetErrorString(ce));
     done = true;
   }
-  dim3 grid((p.S + ATT_TILE - 1) / ATT_TILE, p.Hkv, p.B);
+  dim3 grid(((p.S + ATT_TILE - 1) / ATT_TILE) * p.Hkv * p.B);
   kern<<<grid, BWD_THREADS, bwd_smem_bytes<D>(), st>>>(tq, tk, tv, tdo, p);
   LRP_CHECK_LAUNCH();
   return LRP_OK;
 }
 
-template <int D>
+template <int D, int POLY>
 static int launch_bwd_pipe(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const CUtensorMap& tdo,
                            const CUtensorMap& tdq, const AttnParams& p, cudaStream_t st) {
-  auto kern = attn_bwd_pipe_kernel<D>;
+  auto kern = attn_bwd_pipe_kernel<D, POLY>;
   static bool done = false;
   if (!done) {
     cudaError_t ce = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bwd_pipe_smem_bytes<D>());
     if (ce != cudaSuccess) return set_error(LRP_ERR_CUDA, cudaGetErrorString(ce));
     done = true;
   }
-  dim3 grid((p.S + ATT_TILE - 1) / ATT_TILE, p.Hkv, p.B);
+  dim3 grid(((p.S + ATT_TILE - 1) / ATT_TILE) * p.Hkv * p.B);
   kern<<<grid, BWD_THREADS, bwd_pipe_smem_bytes<D>(), st>>>(tq, tk, tv, tdo, tdq, p);
   LRP_CHECK_LAUNCH();
   return LRP_OK;
@@ -887,6 +891,7 @@ int lrp_attn_fwd_varlen(const void* q, const void* k, const void* v, int64_t ldq
   p.B = B; p.S = S; p.H = H; p.Hkv = Hkv; p.D = D;
   p.scale = scale; p.scale_log2 = scale * LOG2E;
   p.causal = causal; p.window = window;
+  p.sched_group = sched_group_default();
   p.o = reinterpret_cast<__nv_bfloat16*>(o);
   p.lse = lse;
   p.kv_range = kv_range;
@@ -939,6 +944,7 @@ int lrp_attn_bwd_varlen(const void* q, const void* k, const void* v, int64_t ldq
   p.B = B; p.S = S; p.H = H; p.Hkv = Hkv; p.D = D;
   p.scale = scale; p.scale_log2 = scale * LOG2E;
   p.causal = causal; p.window = window;
+  p.sched_group = sched_group_default();
   p.lse = const_cast<float*>(lse);
   p.delta = delta_ws;
   p.dq_acc = dq_acc_ws;
@@ -961,7 +967,10 @@ int lrp_attn_bwd_varlen(const void* q, const void* k, const void* v, int64_t ldq
   if (pipe) {
     CUtensorMap tdq;
     if (int e = make_tmap_3d_f32(&tdq, dq_acc_ws, uint64_t(HD), S, B, HD, uint64_t(S) * HD, 32, ATT_TILE)) return e;
-    le = D == 128 ? launch_bwd_pipe<128>(tq, tk, tv, tdo, tdq, p, st) : launch_bwd_pipe<64>(tq, tk, tv, tdo, tdq, p, st);
+    // LRP_ATTN_POLY=3: every 3rd exponential of soft-max pass A on the FMA pipe instead of MUFU (+2 %, off by default)
+    static const bool poly = getenv("LRP_ATTN_POLY") != nullptr && atoi(getenv("LRP_ATTN_POLY")) == 3;
+    if (D == 128) le = poly ? launch_bwd_pipe<128, 3>(tq, tk, tv, tdo, tdq, p, st) : launch_bwd_pipe<128, 0>(tq, tk, tv, tdo, tdq, p, st);
+    else le = poly ? launch_bwd_pipe<64, 3>(tq, tk, tv, tdo, tdq, p, st) : launch_bwd_pipe<64, 0>(tq, tk, tv, tdo, tdq, p, st);
   } else {
     le = D == 128 ? launch_bwd<128>(tq, tk, tv, tdo, p, st) : launch_bwd<64>(tq, tk, tv, tdo, p, st);
   }

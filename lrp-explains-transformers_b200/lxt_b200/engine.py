@@ -366,7 +366,7 @@ class LlamaAttnLRPEngine:
         ws["g_o"] = e(T, m.H * m.D)
         ws["g_qkv"] = e(T, m.qkv_width)
         # zero once: every attention backward leaves it zero again (LRP_ATTN_ACC_ZERO)
-        ws["dq_acc"] = None if self.hp else torch.zeros(B, S, m.H, m.D, dtype=torch.float32, device=dev)
+        ws["dq_acc"] = None if self.hp else torch.zeros(ops.attn_bwd_workspace_floats(B, S, m.H, m.D), dtype=torch.float32, device=dev)
         ws["delta"] = e(B, m.H, S, dt=torch.float32)
         ws["logits"] = e(B, m.V, dt=torch.float32)
         ws["h_last"] = e(B, m.d, dt=torch.float32)

@@ -162,6 +162,41 @@ class softmax_fn(Function):
         return ops.softmax_dt_bwd(inputs, outputs, R), None, None, None, None
 
 
+class flash_attention_fn(Function):
+    """Relevance-space attention without the [B,H,S,S] tensors: the chain the reference's explicit models spell out as
+        lf.matmul(q, k^T) -> lf.mul2(., scale) -> lf.add2(., mask) -> lf.softmax -> lf.matmul(p, v)
+    (reference lxt/explicit/models/llama.py:378-391) as ONE flash forward and ONE flash backward.  For eps -> 0 the four rules
+    telescope (every division by the scores / probabilities cancels against the factor the next rule multiplies with):
+        g_O = R_O / (O + eps/2);   (dQ, dK, dV) = soft-max attention backward of g_O;
+        R_Q = Q * dQ / 4,  R_K = K * dK / 4,  R_V = V * dV / 2
+    i.e. the Gradient x Input form of the same uniform rules (lxt/efficient/patches.py:193-203), so the kernels of the efficient
+    path serve the explicit API and nothing quadratic in S is stored.  q [B,H,S,D], k/v [B,Hkv,S,D] (grouped heads are consumed
+    natively; the relevance of a shared K/V head is the sum over its query heads, as `repeat_kv` + autograd gives)."""
+
+    @staticmethod
+    def forward(ctx, query, key, value, scale=None, causal=True, window=0, epsilon=1e-6):
+        if not query.is_cuda:
+            raise LrpError("flash_attention: CUDA tensors only (no CPU fallback)")
+        dt = query.dtype if query.dtype in (torch.bfloat16, torch.float32) else torch.float32
+        q, k, v = (t.to(dt).transpose(1, 2).contiguous() for t in (query, key, value))      # [B,S,H,D]
+        scale = float(q.shape[-1]) ** -0.5 if scale is None else float(scale)
+        o, lse = ops.attn_fwd(q, k, v, scale, causal=bool(causal), window=int(window))
+        ctx.save_for_backward(q, k, v, o, lse)
+        ctx.cfg = (scale, bool(causal), int(window), float(epsilon), query.dtype)
+        return o.transpose(1, 2).to(query.dtype)
+
+    @staticmethod
+    @conservation_check_wrap
+    def backward(ctx, *out_relevance):
+        q, k, v, o, lse = ctx.saved_tensors
+        scale, causal, window, epsilon, dt_in = ctx.cfg
+        r = out_relevance[0].to(o.dtype).transpose(1, 2).contiguous()
+        g = ops.eps_div(r, o, 0.5 * epsilon)                                                 # R_O / (O + eps/2)
+        dq, dk, dv = ops.attn_bwd(q, k, v, o, g, lse, scale, causal=causal, window=window, q_div=4.0, k_div=4.0, v_div=2.0)
+        rq, rk, rv = ops.mul(dq, q), ops.mul(dk, k), ops.mul(dv, v)
+        return (rq.transpose(1, 2).to(dt_in), rk.transpose(1, 2).to(dt_in), rv.transpose(1, 2).to(dt_in), None, None, None, None)
+
+
 class add2_tensors_fn(Function):
     @staticmethod
     def forward(ctx, input_a, input_b, inplace=False, epsilon=1e-6):
@@ -344,6 +379,12 @@ def linear_epsilon(input, weight, bias=None, epsilon=1e-6):
 def matmul(input_a, input_b, inplace=False, epsilon=1e-8):
     """epsilon + uniform rule for torch.matmul (AttnLRP Prop. 3.3)."""
     return matmul_fn.apply(input_a, input_b, inplace, epsilon)
+
+
+def flash_attention(query, key, value, scale=None, causal=True, window=0, epsilon=1e-6):
+    """soft-max attention under the explicit rules (eps + uniform matmuls, Deep-Taylor soft-max) with flash kernels: no [B,H,S,S]
+    tensor in HBM.  Extension over the reference API (its explicit models materialise the scores)."""
+    return flash_attention_fn.apply(query, key, value, scale, causal, window, epsilon)
 
 
 def rms_norm_identity(hidden_states, weight, variance_epsilon):

@@ -392,6 +392,17 @@ def attn_fwd(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, scale: float, *,
     return o, lse
 
 
+_ATTN_WS: dict = {}
+
+
+def attn_bwd_workspace_floats(B: int, S: int, H: int, D: int) -> int:
+    """fp32 elements of the `dq_acc` workspace of attn_bwd (lrp_attn_bwd_workspace_bytes: [B,S,H,D] accumulator + counters)"""
+    import ctypes
+    nb = ctypes.c_int64(0)
+    check(_capi.lib().lrp_attn_bwd_workspace_bytes(B, S, H, D, ctypes.byref(nb), None), "lrp_attn_bwd_workspace_bytes")
+    return nb.value // 4
+
+
 def attn_bwd(q, k, v, o, d_o, lse, scale: float, *, causal: bool = True, window: int = 0, q_div: float = 4.0,
              k_div: float = 4.0, v_div: float = 2.0, dq=None, dk=None, dv=None, dq_acc=None, delta=None, kv_range=None, flags: int = 0):
     """LRP backward of attention: returns (dq, dk, dv) already divided by (q_div, k_div, v_div)."""
@@ -420,14 +431,30 @@ def attn_bwd(q, k, v, o, d_o, lse, scale: float, *, causal: bool = True, window:
                                            delta.data_ptr(), _kv_range_ptr(kv_range, B), B, S, H, Hkv, D, scale, int(causal), window,
                                            q_div, k_div, v_div, _stream()), "lrp_attn_bwd_f32")
         return dq, dk, dv
+    need = attn_bwd_workspace_floats(B, S, H, D)
     if dq_acc is None:
-        dq_acc = torch.empty((B, S, H, D), dtype=torch.float32, device=q.device)
+        # kept per (device, stream, shape): the kernel hands the workspace back zero, so only its first use pays the zero-fill
+        key = (q.device.index, _stream(), B, S, H, D)
+        dq_acc = _ATTN_WS.pop(key, None)
+        if dq_acc is None:    # (head_dim 256 runs the atomic-free two-pass kernels: no accumulator, a token buffer satisfies the ABI)
+            dq_acc = torch.zeros(need if D != 256 else 64, dtype=torch.float32, device=q.device)
+        _ATTN_WS[key] = dq_acc                      # re-inserted last: dict order is the LRU order
+        while len(_ATTN_WS) > 4:
+            _ATTN_WS.pop(next(iter(_ATTN_WS)))
+        flags = int(flags) | 2                      # LRP_ATTN_ACC_ZERO
+    elif dq_acc.dtype != torch.float32 or (dq_acc.numel() < need and D != 256) or not dq_acc.is_contiguous():
+        raise _capi.LrpError(f"attn_bwd: dq_acc must be a contiguous fp32 workspace of >= {need} elements "
+                             "(attn_bwd_workspace_floats: accumulator + query-tile counters)")
     if delta is None:
         delta = torch.empty((B, H, S), dtype=torch.float32, device=q.device)
-    check(_capi.lib().lrp_attn_bwd_varlen(q.data_ptr(), k.data_ptr(), v.data_ptr(), ldq, ldk, ldv, o.data_ptr(), d_o.data_ptr(),
-                                          lse.data_ptr(), dq.data_ptr(), dk.data_ptr(), dv.data_ptr(), lddq, lddk, lddv,
-                                          dq_acc.data_ptr(), delta.data_ptr(), _kv_range_ptr(kv_range, B), int(flags), B, S, H, Hkv, D,
-                                          scale, int(causal), window, q_div, k_div, v_div, _stream()), "lrp_attn_bwd")
+    try:
+        check(_capi.lib().lrp_attn_bwd_varlen(q.data_ptr(), k.data_ptr(), v.data_ptr(), ldq, ldk, ldv, o.data_ptr(), d_o.data_ptr(),
+                                              lse.data_ptr(), dq.data_ptr(), dk.data_ptr(), dv.data_ptr(), lddq, lddk, lddv,
+                                              dq_acc.data_ptr(), delta.data_ptr(), _kv_range_ptr(kv_range, B), int(flags), B, S, H, Hkv, D,
+                                              scale, int(causal), window, q_div, k_div, v_div, _stream()), "lrp_attn_bwd")
+    except Exception:
+        _ATTN_WS.clear()      # a failed launch may leave a kept workspace dirty
+        raise
     return dq, dk, dv
 
 

@@ -225,3 +225,53 @@ def test_taylor_decomposition_rule_without_bias():
     import pytest as _pt
     with _pt.raises(NotImplementedError):
         rules.TaylorDecompositionRule(lin, ref=(torch.zeros(6, 16, device="cuda"),), bias=True)(x.cuda().requires_grad_())
+
+
+def test_flash_attention_relevance_space_equals_the_rule_chain():
+    """lf.flash_attention (extension: the explicit rule chain matmul -> mul2 -> add2(mask) -> softmax -> matmul of reference
+    lxt/explicit/models/llama.py:378-391 without any [B,H,S,S] tensor) against (a) that chain evaluated rule by rule with the CPU
+    oracle in float64 and (b) the Gradient x Input closed form under a causal mask with grouped heads."""
+    import lxt_b200.explicit.functional as lf
+    g = torch.Generator().manual_seed(23)
+    B, H, S, D = 2, 4, 256, 64
+    qh = torch.rand(B, H, S, D, generator=g) * 0.5 + 0.1       # positive: keeps O and the scores away from the poles of the rules
+    kh = torch.rand(B, H, S, D, generator=g) * 0.5 + 0.1
+    vh = torch.rand(B, H, S, D, generator=g) * 0.5 + 0.1
+    R = torch.randn(B, H, S, D, generator=g)
+    scale, eps = D ** -0.5, 1e-9
+    q64, k64, v64, R64 = (t.double() for t in (qh, kh, vh, R))
+    A = q64 @ k64.transpose(-1, -2)
+    x = A * scale
+    P = torch.softmax(x, -1)
+    Rp, Rv = O.matmul_relevance(P, v64, R64, eps)
+    Rx = O.softmax_relevance(x, Rp)
+    Rq, Rkt = O.matmul_relevance(q64, k64.transpose(-1, -2), Rx, eps)      # mul2 by a constant hands the relevance through
+    y, (gq, gk, gv) = _grad(lambda a, b, c: lf.flash_attention(a, b, c, None, False, 0, eps), qh, kh, vh, seed=R)
+    assert rel_l2(y, (P @ v64).float()) < 1e-5
+    for got, want in ((gq, Rq), (gk, Rkt.transpose(-1, -2)), (gv, Rv)):
+        assert rel_l2(got, want.float()) < 1e-3
+    # conservation of the uniform rule: R_Q + R_K + R_V = R_O summed (the soft-max rule itself is not conservative: it sheds the
+    # bias term), checked on the part that is: R_V carries half
+    assert abs(float(gv.double().sum()) - 0.5 * float(R64.sum())) < 1e-3 * float(R64.abs().sum())
+
+    # (b) causal, grouped heads, bf16 operands: closed form Q*dQ/4, K*dK/4, V*dV/2 with dO = R/(O + eps/2) by float64 autograd
+    B, H, Hkv, S, D = 1, 4, 2, 4096, 128
+    qb = (torch.randn(B, H, S, D, generator=g) * 0.5).bfloat16()
+    kb = (torch.randn(B, Hkv, S, D, generator=g) * 0.5).bfloat16()
+    vb = (torch.rand(B, Hkv, S, D, generator=g) + 0.2).bfloat16()
+    Rb = torch.randn(B, H, S, D, generator=g).bfloat16()
+    qd, kd, vd = (t.double().requires_grad_() for t in (qb, kb, vb))
+    rep = H // Hkv
+    sc = (qd @ kd.repeat_interleave(rep, 1).transpose(-1, -2)) * D ** -0.5
+    sc = sc.masked_fill(torch.triu(torch.ones(S, S, dtype=torch.bool), 1), float("-inf"))
+    od = torch.softmax(sc, -1) @ vd.repeat_interleave(rep, 1)
+    od.backward((Rb.double() / (od.detach() + 0.5e-6)))
+    want = (qd.detach() * qd.grad / 4, kd.detach() * kd.grad / 4, vd.detach() * vd.grad / 2)
+    torch.cuda.reset_peak_memory_stats()
+    base = torch.cuda.memory_allocated()
+    y, got = _grad(lambda a, b, c: lf.flash_attention(a, b, c), qb, kb, vb, seed=Rb)
+    peak = torch.cuda.max_memory_allocated() - base
+    assert peak < B * H * S * S * 2, f"peak {peak} B: a [B,H,S,S] tensor was materialised"
+    assert rel_l2(y, od.detach().float()) < 1e-2
+    for gg, ww in zip(got, want):
+        assert rel_l2(gg, ww.float()) < 2e-2
