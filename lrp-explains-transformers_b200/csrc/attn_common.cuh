@@ -60,6 +60,10 @@ __device__ __forceinline__ void sched_decode(int tiles, int Y, int Z, int group,
   y = rr - (rr / Y) * Y;
 }
 
+// attn_bwd_ws.cu: warp-specialised backward (head_dim 128, no sliding window)
+int attn_bwd_ws_launch(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const CUtensorMap& tdo,
+                       const CUtensorMap& tdq, const AttnParams& p, cudaStream_t st);
+
 inline int sched_group_default() {
   static int g = -2;
   if (g == -2) {

@@ -964,7 +964,15 @@ int lrp_attn_bwd_varlen(const void* q, const void* k, const void* v, int64_t ldq
   // kernel (per-thread red.global) for A/B measurements
   const bool pipe = !(sel != nullptr && !strcmp(sel, "v1"));
   int le;
-  if (pipe) {
+  // LRP_ATTN_BWD=ws: the warp-specialised experiment of attn_bwd_ws.cu (transposed scores, P^T in TMEM, own dQ drain warpgroup).
+  // It reaches the same ~6k cycles per tile as the pipelined kernel because both are held by the rate at which the L2 takes
+  // the fp32 dQ reductions (profiles/r02_attn_bwd_experiments.md), so it is not the default.
+  const bool ws = D == 128 && window <= 0 && sel != nullptr && !strcmp(sel, "ws");
+  if (ws) {
+    CUtensorMap tdq;
+    if (int e = make_tmap_3d_f32(&tdq, dq_acc_ws, uint64_t(HD), S, B, HD, uint64_t(S) * HD, 32, ATT_TILE)) return e;
+    le = attn_bwd_ws_launch(tq, tk, tv, tdo, tdq, p, st);
+  } else if (pipe) {
     CUtensorMap tdq;
     if (int e = make_tmap_3d_f32(&tdq, dq_acc_ws, uint64_t(HD), S, B, HD, uint64_t(S) * HD, 32, ATT_TILE)) return e;
     // LRP_ATTN_POLY=3: every 3rd exponential of soft-max pass A on the FMA pipe instead of MUFU (+2 %, off by default)
@@ -981,6 +989,18 @@ int lrp_attn_bwd_varlen(const void* q, const void* k, const void* v, int64_t ldq
     cudaDeviceSynchronize();
     cudaMemcpy(h, dbg_dev, sizeof(h), cudaMemcpyDeviceToHost);
     cudaFree(dbg_dev);
+    if (!printed && ws) {
+      printed = true;
+      printf("ws: clock64 stamps of CTA 0 relative to the MMA warp's iteration start\n"
+             "it | mma: p_ready ds_wait ds_ready do_full dq_empty | drain: start dq_full box01 slot0_free slot1_free box3 | smx: start s_full passA dp_full ds_store dk_done end | iter\n");
+      for (int it = 2; it < 14; ++it) {
+        const long long* r = h + it * 24;
+        const long long t0 = r[0];
+        printf("%2d | %5lld %5lld %5lld %5lld %5lld | %5lld %5lld %5lld %5lld %5lld %5lld | %5lld %5lld %5lld %5lld %5lld %5lld %5lld | %6lld\n", it,
+               r[1] - t0, r[2] - t0, r[3] - t0, r[4] - t0, r[5] - t0, r[6] - t0, r[7] - t0, r[8] - t0, r[9] - t0, r[10] - t0, r[11] - t0,
+               r[12] - t0, r[13] - t0, r[14] - t0, r[15] - t0, r[16] - t0, r[17] - t0, r[18] - t0, r[0] - (h + (it - 1) * 24)[0]);
+      }
+    }
     if (!printed && pipe) {
       printed = true;
       printf("pipe: clock64 stamps of one CTA relative to the control thread's iteration start\n"

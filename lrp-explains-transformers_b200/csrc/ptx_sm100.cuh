@@ -128,6 +128,12 @@ __device__ __forceinline__ void tma_store_wait() {
 // ----------------------------------------------------------------------------------------------
 // tcgen05
 // ----------------------------------------------------------------------------------------------
+// register re-allocation between the warpgroups of a warp-specialised kernel (all 4 warps of the warpgroup execute it)
+template <int N>
+__device__ __forceinline__ void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N>
+__device__ __forceinline__ void setmaxnreg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
+
 __device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)),
                "r"(ncols)
