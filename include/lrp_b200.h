@@ -259,6 +259,19 @@ int lrp_cast_f32_to_bf16(const float* in, void* out, int64_t n, void* stream);
 int lrp_eps_div(const void* r, const void* z, void* out, int64_t n, float alpha, float eps, int is_f32, void* stream);
 /* out = a*b*scale: the `.mul_(inputs)` step of the epsilon rules (functional.py:361, rules.py:220). */
 int lrp_mul(const void* a, const void* b, void* out, int64_t n, float scale, int is_f32, void* stream);
+/* zennit's Gamma rule (third-party `zennit`, unpinned in the reference's setup.py:18, absent here: restated from its published
+ * algorithm, PARITY UNPINNED) as the reference runs it in Gradient x Input space (lxt/efficient/zennit_patches.py:33-62,
+ * examples/vit_torch.py:59-62).  xcat [rows, 2K] = [max(x,0) | min(x,0)]: the clamped inputs of the four modified passes
+ * (zennit_patches.py:42-44) side by side, so the passes become GEMMs with a doubled contraction. */
+int lrp_gamma_split(const void* x, void* xcat, int64_t rows, int K, int is_f32, void* stream);
+/* scat [rows, 2N] = [ [y>0] g*y/stab(zp) | [y<0] g*y/stab(zn) ]: `grad_output * output` (zennit_patches.py:38) normalised by the
+ * positive / negative modified pre-activations with zennit's signed stabiliser; the branch follows the sign of the unmodified output
+ * (the rule's gradient_mapper, applied at zennit_patches.py:50). */
+int lrp_gamma_s(const void* g, const void* y, const void* zp, const void* zn, void* scat, int64_t rows, int N, float eps, int is_f32,
+                void* stream);
+/* out = x * (x>0 ? g1 : g2) / stabilize(x, 1e-10): the rule's reducer sum(input_i * gradient_i) (zennit_patches.py:57) followed by
+ * the division that returns to the gradient domain (zennit_patches.py:59-60). */
+int lrp_gamma_combine(const void* x, const void* g1, const void* g2, void* out, int64_t n, int is_f32, void* stream);
 /* out = x*factor: divide_gradient backward (lxt/efficient/rules.py:125-127), mul2 uniform rule (functional.py:524-536). */
 int lrp_scale(const void* x, void* out, int64_t n, float factor, int is_f32, void* stream);
 /* gx = gy * y/(x+1e-10): identity rule in GxI space for an arbitrary y = f(x) (lxt/efficient/rules.py:88-100). */

@@ -555,6 +555,50 @@ __global__ void __launch_bounds__(256) scale_kernel(const T* __restrict__ x, T* 
   for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < n; i += int64_t(gridDim.x) * blockDim.x)
     stf(out, i, ldf(x, i) * factor);
 }
+// ---- Gamma rule in Gradient x Input space (zennit Gamma through lxt/efficient/zennit_patches.py:26-62) ----
+// xcat[t, 0:K] = max(x, 0), xcat[t, K:2K] = min(x, 0): the two clamped inputs of the rule side by side, so that the four modified
+// forward passes become two GEMMs with a doubled contraction
+template <typename T>
+__global__ void __launch_bounds__(256) gamma_split_kernel(const T* __restrict__ x, T* __restrict__ xcat, int64_t rows, int K) {
+  const int64_t n = rows * K;
+  for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < n; i += int64_t(gridDim.x) * blockDim.x) {
+    const int64_t t = i / K;
+    const int k = int(i - t * K);
+    const float v = ldf(x, i);
+    stf(xcat, t * 2 * K + k, fmaxf(v, 0.f));
+    stf(xcat, t * 2 * K + K + k, fminf(v, 0.f));
+  }
+}
+// scat[t, 0:N] = [y > 0] g y / stab(zp), scat[t, N:2N] = [y < 0] g y / stab(zn): relevance g*y of the layer output normalised by the
+// positive / negative modified pre-activation; the branch follows the sign of the UNMODIFIED output y (the rule's fifth, unmodified
+// pass), stab(z) = z + ((z == 0) + sign(z)) eps is zennit's signed stabiliser
+template <typename T>
+__global__ void __launch_bounds__(256) gamma_s_kernel(const T* __restrict__ g, const T* __restrict__ y, const T* __restrict__ zp,
+                                                      const T* __restrict__ zn, T* __restrict__ scat, int64_t rows, int N, float eps) {
+  const int64_t n = rows * N;
+  for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < n; i += int64_t(gridDim.x) * blockDim.x) {
+    const int64_t t = i / N;
+    const int c = int(i - t * N);
+    const float yv = ldf(y, i);
+    const float r = ldf(g, i) * yv;
+    const float p = ldf(zp, i), q = ldf(zn, i);
+    stf(scat, t * 2 * N + c, yv > 0.f ? r / (p + (p < 0.f ? -eps : eps)) : 0.f);
+    stf(scat, t * 2 * N + N + c, yv < 0.f ? r / (q + (q < 0.f ? -eps : eps)) : 0.f);
+  }
+}
+// g_x = x (x > 0 ? g1 : g2) / (x + sign(x) 1e-10), 0 at x = 0: Sigma_i input_i * gradient_i of the rule, then the division that takes
+// the relevance back to a gradient (zennit_patches.py:59-60)
+template <typename T>
+__global__ void __launch_bounds__(256) gamma_combine_kernel(const T* __restrict__ x, const T* __restrict__ g1, const T* __restrict__ g2,
+                                                            T* __restrict__ out, int64_t n) {
+  for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < n; i += int64_t(gridDim.x) * blockDim.x) {
+    const float v = ldf(x, i);
+    float o = 0.f;
+    if (v > 0.f) o = v * ldf(g1, i) / (v + 1e-10f);
+    else if (v < 0.f) o = v * ldf(g2, i) / (v - 1e-10f);
+    stf(out, i, o);
+  }
+}
 // gx = gy * (y / (x + 1e-10))     identity rule in GxI space for an arbitrary f with y = f(x)  (rules.py:88-100)
 template <typename T>
 __global__ void __launch_bounds__(256) identity_rule_bwd_kernel(const T* __restrict__ gy, const T* __restrict__ x,
@@ -903,6 +947,24 @@ int lrp_scale(const void* x, void* out, int64_t n, float factor, int is_f32, voi
   return ew_launch(n, is_f32, stream, "scale: empty tensor",
                    [&](int g, cudaStream_t st) { scale_kernel<float><<<g, 256, 0, st>>>((const float*)x, (float*)out, n, factor); },
                    [&](int g, cudaStream_t st) { scale_kernel<bf16><<<g, 256, 0, st>>>((const bf16*)x, (bf16*)out, n, factor); });
+}
+int lrp_gamma_split(const void* x, void* xcat, int64_t rows, int K, int is_f32, void* stream) {
+  if (K <= 0) return set_error(LRP_ERR_ARG, "gamma_split: bad width");
+  return ew_launch(rows * K, is_f32, stream, "gamma_split: empty tensor",
+                   [&](int g, cudaStream_t st) { gamma_split_kernel<float><<<g, 256, 0, st>>>((const float*)x, (float*)xcat, rows, K); },
+                   [&](int g, cudaStream_t st) { gamma_split_kernel<bf16><<<g, 256, 0, st>>>((const bf16*)x, (bf16*)xcat, rows, K); });
+}
+int lrp_gamma_s(const void* g, const void* y, const void* zp, const void* zn, void* scat, int64_t rows, int N, float eps, int is_f32,
+                void* stream) {
+  if (N <= 0) return set_error(LRP_ERR_ARG, "gamma_s: bad width");
+  return ew_launch(rows * N, is_f32, stream, "gamma_s: empty tensor",
+                   [&](int gr, cudaStream_t st) { gamma_s_kernel<float><<<gr, 256, 0, st>>>((const float*)g, (const float*)y, (const float*)zp, (const float*)zn, (float*)scat, rows, N, eps); },
+                   [&](int gr, cudaStream_t st) { gamma_s_kernel<bf16><<<gr, 256, 0, st>>>((const bf16*)g, (const bf16*)y, (const bf16*)zp, (const bf16*)zn, (bf16*)scat, rows, N, eps); });
+}
+int lrp_gamma_combine(const void* x, const void* g1, const void* g2, void* out, int64_t n, int is_f32, void* stream) {
+  return ew_launch(n, is_f32, stream, "gamma_combine: empty tensor",
+                   [&](int g, cudaStream_t st) { gamma_combine_kernel<float><<<g, 256, 0, st>>>((const float*)x, (const float*)g1, (const float*)g2, (float*)out, n); },
+                   [&](int g, cudaStream_t st) { gamma_combine_kernel<bf16><<<g, 256, 0, st>>>((const bf16*)x, (const bf16*)g1, (const bf16*)g2, (bf16*)out, n); });
 }
 int lrp_identity_rule_bwd(const void* gy, const void* x, const void* y, void* gx, int64_t n, int is_f32, void* stream) {
   return ew_launch(n, is_f32, stream, "identity_rule_bwd: empty tensor",

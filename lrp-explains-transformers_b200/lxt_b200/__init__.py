@@ -22,3 +22,17 @@ def install_as_lxt() -> None:
     sys.modules.setdefault("lxt", sys.modules[__name__])
     sys.modules.setdefault("lxt.efficient", efficient)
     sys.modules.setdefault("lxt.explicit", explicit)
+    try:
+        import zennit  # noqa: F401
+    except ImportError:
+        # the reference's ViT recipe imports `zennit.rules.Gamma` and `zennit.composites.LayerMapComposite` (examples/vit_torch.py:
+        # 7-8): stand-ins backed by efficient/zennit_rules.py when the real package is absent
+        import types
+        from .efficient import zennit_rules
+        z, zr, zc = types.ModuleType("zennit"), types.ModuleType("zennit.rules"), types.ModuleType("zennit.composites")
+        zr.Gamma = zennit_rules.Gamma
+        zc.LayerMapComposite = zennit_rules.LayerMapComposite
+        z.rules, z.composites = zr, zc
+        sys.modules.setdefault("zennit", z)
+        sys.modules.setdefault("zennit.rules", zr)
+        sys.modules.setdefault("zennit.composites", zc)

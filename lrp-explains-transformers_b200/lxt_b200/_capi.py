@@ -85,6 +85,9 @@ SIGNATURES = {
     "lrp_cast_f32_to_bf16": (_i, [_vp, _vp, _i64, _vp]),
     "lrp_eps_div": (_i, [_vp, _vp, _vp, _i64, _f, _f, _i, _vp]),
     "lrp_mul": (_i, [_vp, _vp, _vp, _i64, _f, _i, _vp]),
+    "lrp_gamma_split": (_i, [_vp, _vp, _i64, _i, _i, _vp]),
+    "lrp_gamma_s": (_i, [_vp, _vp, _vp, _vp, _vp, _i64, _i, _f, _i, _vp]),
+    "lrp_gamma_combine": (_i, [_vp, _vp, _vp, _vp, _i64, _i, _vp]),
     "lrp_scale": (_i, [_vp, _vp, _i64, _f, _i, _vp]),
     "lrp_identity_rule_bwd": (_i, [_vp, _vp, _vp, _vp, _i64, _i, _vp]),
     "lrp_softmax_dt_bwd": (_i, [_vp, _vp, _vp, _vp, _i64, _i, _i, _vp]),

@@ -162,6 +162,12 @@ def _linear_ok(x: torch.Tensor, weight: torch.Tensor) -> bool:
     return x.dtype == torch.float32 and weight.dtype in (torch.float32, torch.bfloat16)
 
 
+def _functorch_wrapped(x: torch.Tensor) -> bool:
+    """the autograd bridges are plain autograd.Functions (no functorch rules): transformed tensors take the stock path"""
+    f = getattr(torch._C, "_functorch", None)
+    return f is not None and hasattr(f, "is_functorch_wrapped_tensor") and f.is_functorch_wrapped_tensor(x)
+
+
 def _linear(mod, x):
     """run an nn.Linear through the B200 GEMM"""
     if not _linear_ok(x, mod.weight):
@@ -390,8 +396,9 @@ def mlp_forward(self, x):
 def linear_forward(self, x):
     """nn.Linear on the tcgen05 GEMM (forward + LRP dgrad).  Not part of the reference's patch map — it leaves
     nn.Linear to cuBLAS — added so that a patched model runs every FLOP of the path on the B200 kernels.
-    Inputs the kernel does not take (fp32, CPU, odd widths) go through the original forward unchanged."""
-    if _linear_ok(x, self.weight):
+    Inputs the kernel does not take (CPU, odd widths, tensors wrapped by a torch.func transform such as the jvp / vjp of
+    `TaylorDecompositionRule`) go through the original forward unchanged."""
+    if _linear_ok(x, self.weight) and not _functorch_wrapped(x):
         return _LinearFn.apply(x, self.weight, self.bias)
     return self.original_forward(x)
 

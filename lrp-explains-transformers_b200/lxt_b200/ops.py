@@ -527,6 +527,34 @@ def eps_div(r: torch.Tensor, z: torch.Tensor, eps: float, alpha: float = 1.0) ->
     return out
 
 
+def gamma_split(x2: torch.Tensor) -> torch.Tensor:
+    """[max(x,0) | min(x,0)] side by side: x [T,K] -> [T,2K] (Gamma rule, see efficient/zennit_rules.py)"""
+    (x2,), f32 = _ew_prepare(x2)
+    T, K = x2.shape
+    out = torch.empty((T, 2 * K), dtype=x2.dtype, device=x2.device)
+    check(_capi.lib().lrp_gamma_split(x2.data_ptr(), out.data_ptr(), T, K, f32, _stream()), "lrp_gamma_split")
+    return out
+
+
+def gamma_s(g: torch.Tensor, y: torch.Tensor, zp: torch.Tensor, zn: torch.Tensor, eps: float) -> torch.Tensor:
+    """[ [y>0] g*y/stab(zp) | [y<0] g*y/stab(zn) ]: [T,N] x4 -> [T,2N]"""
+    (g, y, zp, zn), f32 = _ew_prepare(g, y, zp, zn)
+    T, N = g.shape
+    out = torch.empty((T, 2 * N), dtype=g.dtype, device=g.device)
+    check(_capi.lib().lrp_gamma_s(g.data_ptr(), y.data_ptr(), zp.data_ptr(), zn.data_ptr(), out.data_ptr(), T, N, eps, f32, _stream()),
+          "lrp_gamma_s")
+    return out
+
+
+def gamma_combine(x: torch.Tensor, g1: torch.Tensor, g2: torch.Tensor) -> torch.Tensor:
+    """x * (x>0 ? g1 : g2) / stabilize(x, 1e-10)"""
+    (x, g1, g2), f32 = _ew_prepare(x, g1, g2)
+    out = torch.empty_like(x)
+    check(_capi.lib().lrp_gamma_combine(x.data_ptr(), g1.data_ptr(), g2.data_ptr(), out.data_ptr(), x.numel(), f32, _stream()),
+          "lrp_gamma_combine")
+    return out
+
+
 def mul(a: torch.Tensor, b: torch.Tensor, scale: float = 1.0) -> torch.Tensor:
     (a, b), f32 = _ew_prepare(a, b)
     out = torch.empty_like(a)

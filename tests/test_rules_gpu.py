@@ -227,6 +227,33 @@ def test_taylor_decomposition_rule_without_bias():
         rules.TaylorDecompositionRule(lin, ref=(torch.zeros(6, 16, device="cuda"),), bias=True)(x.cuda().requires_grad_())
 
 
+def test_taylor_rule_on_a_linear_whose_class_forward_is_patched():
+    """monkey_patch routes nn.Linear through the B200 GEMM process-wide; the torch.func jvp / vjp of TaylorDecompositionRule must
+    still work on such a module (the patched forward steps aside for transformed tensors)"""
+    import warnings
+    import lxt_b200.explicit.rules as rules
+    from lxt_b200.efficient import patches as P
+    saved = torch.nn.Linear.forward, torch.nn.Linear.__dict__.get("original_forward")
+    try:
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            P.patch_method(P.linear_forward, torch.nn.Linear, keep_original=True)
+        g = torch.Generator().manual_seed(4)
+        x, W, R = torch.rand(6, 16, generator=g) + 0.5, torch.rand(8, 16, generator=g) + 0.5, torch.randn(6, 8, generator=g)
+        lin = torch.nn.Linear(16, 8, bias=False).cuda()
+        lin.weight.data.copy_(W)
+        lin.weight.requires_grad_(False)
+        y, (gx0,) = _grad(lin, x, seed=R)                              # plain call: the kernel path
+        assert rel_l2(y, x @ W.t()) < 1e-5 and rel_l2(gx0, R @ W) < 1e-5
+        rule = rules.TaylorDecompositionRule(lin, ref=(torch.zeros(6, 16, device="cuda"),), bias=False)
+        _, (gx,) = _grad(rule, x, seed=R)
+        assert rel_l2(gx, O.linear_epsilon_relevance(x, W, None, R, 1e-6)) < 1e-4
+    finally:
+        torch.nn.Linear.forward = saved[0]
+        if saved[1] is None and "original_forward" in torch.nn.Linear.__dict__:
+            del torch.nn.Linear.original_forward
+
+
 def test_flash_attention_relevance_space_equals_the_rule_chain():
     """lf.flash_attention (extension: the explicit rule chain matmul -> mul2 -> add2(mask) -> softmax -> matmul of reference
     lxt/explicit/models/llama.py:378-391 without any [B,H,S,S] tensor) against (a) that chain evaluated rule by rule with the CPU
