@@ -45,6 +45,9 @@ def parse():
     ap.add_argument("--seq", type=int, default=2048)
     ap.add_argument("--model", default="llama3-8b", choices=["llama3-8b", "tinyllama-1.1b", "gemma3-4b", "llama-test"])
     ap.add_argument("--layers", type=int, default=0, help="override the number of layers (debug only; invalidates the metric)")
+    ap.add_argument("--store", default="all", choices=["all", "sqrt"],
+                    help="activation schedule of the engine: keep every layer's activations (default) or sqrt(L) segment recompute")
+    ap.add_argument("--quant", default="none", choices=["none", "nf4"], help="weight storage of the engine (nf4: 4-bit, expanded per layer)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-kernels", action="store_true", help="skip the stand-alone secondary kernel timings (profiling runs)")
     ap.add_argument("--dropin", type=int, default=1, help="also time the drop-in monkey_patch API on an HF Llama of the same dims (N=1)")
@@ -376,7 +379,8 @@ def run_b200(args):
     lo, hi = ldist.shard_range(N_total, rank, world)
     Bg = hi - lo
     micro = max(1, min(args.micro_batch, Bg))
-    eng = LlamaAttnLRPEngine.random_init(dims, device=dev, seed=0, micro_batch=micro)
+    eng = LlamaAttnLRPEngine.random_init(dims, device=dev, seed=0, micro_batch=micro, store=args.store,
+                                         quant=None if args.quant == "none" else args.quant)
     ids_all = torch.randint(0, dims.V, (N_total, S), generator=torch.Generator().manual_seed(1))
     ids_host = ids_all[lo:hi].contiguous().pin_memory()
     ids_dev = ids_host.to(dev)
@@ -459,10 +463,12 @@ def run_b200(args):
         "config": {"workload": f"{args.model} random-init bf16, seq {S}, global batch {N_total} per step = {Bg} prompts per GPU "
                                f"(micro-batch {micro}), batch-sharded over {world} GPU(s), 1 NCCL gather",
                    "global_batch": N_total, "seq_len": S, "layers": dims.L, "parallelism": f"dp{world}",
-                   "l2": "inputs larger than L2 (16 GB weights + activation store streamed every step)"},
+                   "l2": "inputs larger than L2 (16 GB weights + activation store streamed every step)",
+                   "store": args.store, "quant": args.quant},
         "e2e": {"value": e2e_v, "unit": UNIT, "h2d_bytes_per_step": int(ids_host.numel() * 8),
                 "d2h_bytes_per_step": int(rel_host.numel() * 4)},
         "gpu_launches": int(launches),
+        "hbm_peak_gb": torch.cuda.max_memory_allocated(dev) / 2 ** 30,
         "clocks": clocks,
         "roofline": {"bound": "tensor", "kernel": "gemm_bf16_pair_kernel (tcgen05 cta_group::2, all Linear fwd + LRP dgrad; gate|up fwd with act*up in its epilogue)",
                      "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / peak_tf,
@@ -471,7 +477,10 @@ def run_b200(args):
                      # dram__bytes_read.sum + dram__bytes_write.sum of the largest-share launch shape
                      # (M=16384 N=28672 K=4096, gate|up forward) from profiles/r01_ncu_summary.md: 1.45 GB + 0.92 GB
                      # per launch vs 1.31 GB algorithmic (A 134 MB + W 235 MB + C 940 MB): W panels re-streamed 4x via L2
-                     "traffic": 2.37e9, "traffic_note": "bytes/launch, ncu --set full, gate|up fwd shape; algorithmic 1.31e9"},
+                     "traffic": 3.63e9,
+                     "traffic_note": "dram read 2.24e9 + write 1.39e9 bytes/launch, ncu --set full of the gate|up forward with act*up in its epilogue "
+                                     "(profiles/r02_ncu_summary.md); algorithmic 0.37e9 read (x, W) + 1.41e9 write (gate|up, a): the operand "
+                                     "re-reads cost 16 % of DRAM bandwidth on a kernel that is 82 % tensor-pipe active"},
     }
     if args.model == "llama3-8b" and not args.no_kernels:
         try:
