@@ -19,9 +19,18 @@ def install_as_lxt() -> None:
     import sys
     from . import efficient, explicit
 
+    import importlib
+
     sys.modules.setdefault("lxt", sys.modules[__name__])
     sys.modules.setdefault("lxt.efficient", efficient)
     sys.modules.setdefault("lxt.explicit", explicit)
+    # every sub-module under its reference name too: `import lxt.explicit.functional as lf` must hand out THIS module object, not
+    # a second copy loaded from the package path (module state such as the conservation-check flag would fork)
+    for pkg, names in (("explicit", ("functional", "rules", "check", "special", "modules")),
+                       ("efficient", ("core", "rules", "patches", "models", "zennit_rules"))):
+        for n in names:
+            sys.modules.setdefault(f"lxt.{pkg}.{n}", importlib.import_module(f"{__name__}.{pkg}.{n}"))
+    sys.modules.setdefault("lxt.efficient.zennit_patches", sys.modules[f"{__name__}.efficient.zennit_rules"])
     try:
         import zennit  # noqa: F401
     except ImportError:

@@ -1,2 +1,3 @@
-"""Drop-in for `lxt.explicit` (functional + rules + conservation check; the fx Composite tooling of the reference is out of scope)."""
-from . import functional, rules, check  # noqa: F401
+"""Drop-in for `lxt.explicit` (functional + rules + modules + special + conservation check; the fx Composite tooling of the
+reference, lxt/explicit/core.py, needs `transformers.utils.fx` and is out of scope)."""
+from . import functional, rules, check, special, modules  # noqa: F401

@@ -1,5 +1,6 @@
 """CPU: host-side logic of the drop-in API (patch plumbing, registries, sharding) and the loud-failure contract
 (no CPU fallback: rules / ops raise on CPU tensors instead of silently computing elsewhere)."""
+import os
 import types
 import warnings
 
@@ -124,3 +125,23 @@ def test_conservation_check_flag_and_wrapper():
         assert abs(float(u[0].sum() + u[2].sum()) - float(R.sum())) < 1e-4     # conserved
         assert float(u[0].max() - u[0].min()) == 0.0                               # uniform
     assert lf.CONSERVATION_CHECK_FLAG[0] is False
+
+
+def test_install_as_lxt_registers_the_reference_module_names():
+    """user scripts written against the reference import `lxt.efficient`, `lxt.explicit.functional`, ... and, for the ViT recipe,
+    `zennit.rules.Gamma` / `zennit.composites.LayerMapComposite` (examples/vit_torch.py:6-10)"""
+    import subprocess
+    import sys
+    code = (
+        "import sys; sys.path.insert(0, 'lrp-explains-transformers_b200')\n"
+        "import lxt_b200; lxt_b200.install_as_lxt()\n"
+        "import lxt.explicit.functional as lf, lxt.explicit.modules as lm, lxt.explicit.special as ls, lxt.explicit.rules as lr\n"
+        "from lxt.efficient import monkey_patch, monkey_patch_zennit\n"
+        "import lxt_b200.explicit.functional as own\n"
+        "assert lf is own and lm.LinearEpsilon.__module__ == 'lxt_b200.explicit.modules'\n"
+        "import zennit.rules as zr; from zennit.composites import LayerMapComposite\n"
+        "assert zr.Gamma(0.25).gamma == 0.25 and callable(LayerMapComposite([]).register)\n"
+        "print('ok')\n")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-c", code], cwd=root, capture_output=True, text=True)
+    assert r.returncode == 0 and "ok" in r.stdout, r.stderr[-2000:]
