@@ -12,6 +12,8 @@
 //                        accumulator in both CTAs
 //   warps 2..5 (both)  : epilogue of the CTA's own 128 rows; arrive on the leader's tmem_empty barrier
 #include <stdlib.h>
+#include <stdio.h>
+#include <stdlib.h>
 #include "gemm_common.cuh"
 
 namespace lrp {
@@ -114,12 +116,20 @@ gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_co
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
+      const bool dbg = p.dbg != nullptr;
+      long long t_start = 0, w_empty = 0, w_full = 0, n_tiles = 0;
+      if (dbg) t_start = clock64();
       for (int t = pair; t < num_tiles; t += num_pairs) {
+        long long c0 = 0;
+        if (dbg) c0 = clock64();
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        if (dbg) { w_empty += clock64() - c0; ++n_tiles; }
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + acc * P_BN;
         for (int kb = 0; kb < num_k; ++kb) {
+          if (dbg) c0 = clock64();
           mbar_wait(&full_bar[stage], phase);
+          if (dbg) w_full += clock64() - c0;
           tc_fence_after();
           if (lane == 0) {
             const uint32_t sa = smem_u32(smem + stage * P_STAGE_BYTES);
@@ -139,6 +149,12 @@ gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_co
           if (++stage == P_STAGES) { stage = 0; phase ^= 1; }
         }
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+      if (dbg && lane == 0) {
+        p.dbg[pair * 4 + 0] = clock64() - t_start;
+        p.dbg[pair * 4 + 1] = w_empty;
+        p.dbg[pair * 4 + 2] = w_full;
+        p.dbg[pair * 4 + 3] = n_tiles;
       }
     }
   } else {
@@ -235,9 +251,30 @@ static int launch_pair(const void* A, int64_t lda, const void* B, int64_t ldb, c
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  cudaError_t ce = cudaLaunchKernelEx(&cfg, kern, ta, tb, p);
+  static const bool want_dbg = getenv("LRP_GEMM_DEBUG") != nullptr;
+  GemmParams pd = p;
+  long long* dbg_dev = nullptr;
+  if (want_dbg) {
+    cudaMalloc(&dbg_dev, pairs * 4 * sizeof(long long));
+    cudaMemset(dbg_dev, 0, pairs * 4 * sizeof(long long));
+    pd.dbg = dbg_dev;
+  }
+  cudaError_t ce = cudaLaunchKernelEx(&cfg, kern, ta, tb, pd);
   if (ce != cudaSuccess) return set_error(LRP_ERR_CUDA, cudaGetErrorString(ce));
   note_launch();
+  if (dbg_dev != nullptr) {   // debug only: synchronous read-back, averages over the CTA pairs
+    cudaDeviceSynchronize();
+    long long* h = new long long[pairs * 4];
+    cudaMemcpy(h, dbg_dev, pairs * 4 * sizeof(long long), cudaMemcpyDeviceToHost);
+    cudaFree(dbg_dev);
+    double tot = 0, we = 0, wf = 0, nt = 0;
+    for (int i = 0; i < pairs; ++i) { tot += h[i * 4]; we += h[i * 4 + 1]; wf += h[i * 4 + 2]; nt += h[i * 4 + 3]; }
+    delete[] h;
+    const double ideal = nt * (double(p.K) / 16.0) * 128.0;       // 128 cycles per 256x256x16 pair MMA
+    printf("gemm pair dbg M=%d N=%d K=%d %s: MMA warp cycles/pair %.0f, waiting for a free accumulator %.1f %%, waiting for operands %.1f %%, "
+           "ideal MMA time %.1f %% (tiles/pair %.2f)\n", p.M, p.N, p.K, B_MN ? "NN" : "NT", tot / pairs, 100 * we / tot, 100 * wf / tot,
+           100 * ideal / tot, nt / pairs);
+  }
   return LRP_OK;
 }
 

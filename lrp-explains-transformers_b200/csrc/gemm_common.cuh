@@ -6,6 +6,19 @@
 
 namespace lrp {
 
+// Epilogue stores: every output of the step's GEMMs (T = 16384 rows) is larger than the 126 MB L2 and is read again only by a later
+// kernel, while the x / W operand panels are what the L2 should keep (the MMA warp waits ~9 % of its time for operands, and the panels
+// are re-read ~6x from DRAM).  With GemmParams::stream_stores (default on, LRP_GEMM_STREAM_STORES=0 for A/B runs) the output stores are
+// st.global.cs (evict-first), so that they do not push operand lines out.
+__device__ __forceinline__ void epi_store(bool stream, uint4* dst, uint4 v) {
+  if (stream) __stcs(dst, v);
+  else *dst = v;
+}
+__device__ __forceinline__ void epi_store(bool stream, float4* dst, float4 v) {
+  if (stream) __stcs(dst, v);
+  else *dst = v;
+}
+
 struct GemmParams {
   int M, N, K;
   // epilogue
@@ -30,6 +43,8 @@ struct GemmParams {
   int group_m;  // rasterisation: `group_m` m-blocks share each streamed B panel through L2
   int batch;              // strided-batched form (one-CTA kernel only): `batch` independent problems in one launch
   int64_t batch_stride_c; // element distance between consecutive problems in out / resid / shadow
+  int stream_stores;      // evict-first output stores (see epi_store)
+  long long* dbg;         // LRP_GEMM_DEBUG=1: per CTA pair {total, wait tmem_empty, wait full, tiles} cycles of the MMA warp
 };
 
 __device__ __forceinline__ float gemm_act_eval(float x, int act) {
@@ -103,9 +118,9 @@ __device__ __forceinline__ void gemm_epilogue_act_pair_t(const GemmParams& p, co
       pu[j] = pack_bf16x2(u0, u1);
       pa[j] = pack_bf16x2(gemm_act_fast<ACT>(bf16_lo(pg[j])) * bf16_lo(pu[j]), gemm_act_fast<ACT>(bf16_hi(pg[j])) * bf16_hi(pu[j]));
     }
-    *reinterpret_cast<uint4*>(grow + j8 * 8) = make_uint4(pg[0], pg[1], pg[2], pg[3]);
-    *reinterpret_cast<uint4*>(grow + 32 + j8 * 8) = make_uint4(pu[0], pu[1], pu[2], pu[3]);
-    *reinterpret_cast<uint4*>(arow + j8 * 8) = make_uint4(pa[0], pa[1], pa[2], pa[3]);
+    epi_store(p.stream_stores != 0, reinterpret_cast<uint4*>(grow + j8 * 8), make_uint4(pg[0], pg[1], pg[2], pg[3]));
+    epi_store(p.stream_stores != 0, reinterpret_cast<uint4*>(grow + 32 + j8 * 8), make_uint4(pu[0], pu[1], pu[2], pu[3]));
+    epi_store(p.stream_stores != 0, reinterpret_cast<uint4*>(arow + j8 * 8), make_uint4(pa[0], pa[1], pa[2], pa[3]));
   }
 }
 
@@ -153,8 +168,8 @@ __device__ __forceinline__ void gemm_epilogue_gated_bwd_t(const GemmParams& p, c
       og[j] = pack_bf16x2(rg[0], rg[1]);
       ou[j] = pack_bf16x2(ru[0], ru[1]);
     }
-    *reinterpret_cast<uint4*>(p.gated_out + goff + j8 * 8) = make_uint4(og[0], og[1], og[2], og[3]);
-    *reinterpret_cast<uint4*>(p.gated_out + goff + uo + j8 * 8) = make_uint4(ou[0], ou[1], ou[2], ou[3]);
+    epi_store(p.stream_stores != 0, reinterpret_cast<uint4*>(p.gated_out + goff + j8 * 8), make_uint4(og[0], og[1], og[2], og[3]));
+    epi_store(p.stream_stores != 0, reinterpret_cast<uint4*>(p.gated_out + goff + uo + j8 * 8), make_uint4(ou[0], ou[1], ou[2], ou[3]));
   }
 }
 
@@ -201,17 +216,16 @@ __device__ __forceinline__ float gemm_epilogue_chunk(const GemmParams& p, const 
       }
       if (p.out_is_f32) {
         float* o = reinterpret_cast<float*>(p.out) + row_off + n;
-        *reinterpret_cast<float4*>(o) = make_float4(f[0], f[1], f[2], f[3]);
-        *reinterpret_cast<float4*>(o + 4) = make_float4(f[4], f[5], f[6], f[7]);
+        epi_store(p.stream_stores != 0, reinterpret_cast<float4*>(o), make_float4(f[0], f[1], f[2], f[3]));
+        epi_store(p.stream_stores != 0, reinterpret_cast<float4*>(o + 4), make_float4(f[4], f[5], f[6], f[7]));
       } else {
         __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + row_off + n;
-        *reinterpret_cast<uint4*>(o) = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]),
-                                                  pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+        epi_store(p.stream_stores != 0, reinterpret_cast<uint4*>(o), make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]),
+                                                  pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7])));
       }
       if (p.shadow != nullptr) {
-        *reinterpret_cast<uint4*>(p.shadow + row_off + n) =
-            make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]),
-                       pack_bf16x2(f[6], f[7]));
+        epi_store(p.stream_stores != 0, reinterpret_cast<uint4*>(p.shadow + row_off + n),
+                  make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7])));
       }
       if (p.delta_o != nullptr) {
         const uint4 uo = *reinterpret_cast<const uint4*>(p.delta_o + row_off + n);

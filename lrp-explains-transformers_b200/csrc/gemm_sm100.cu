@@ -23,6 +23,12 @@
 
 namespace lrp {
 
+static int stream_stores_default() {
+  static const int v = getenv("LRP_GEMM_STREAM_STORES") != nullptr ? atoi(getenv("LRP_GEMM_STREAM_STORES")) : 1;
+  return v;
+}
+
+
 constexpr int BM = 128;
 constexpr int BK = 64;  // 64 bf16 = 128 B = one swizzle row
 constexpr int UMMA_K = 16;
@@ -304,6 +310,7 @@ int gemm_bf16_batched(const void* A, int64_t lda, int64_t stride_a, int a_layout
     return set_error(LRP_ERR_ARG, "gemm_batched: needs a plain epilogue with an output");
   GemmParams p;
   memset(&p, 0, sizeof(p));
+  p.stream_stores = stream_stores_default();
   p.M = M; p.N = N; p.K = K;
   p.out = epi->out;
   p.shadow = reinterpret_cast<__nv_bfloat16*>(epi->shadow_bf16);
@@ -337,6 +344,7 @@ int gemm_bf16(const void* A, int64_t lda, const void* B, int64_t ldb, int b_layo
   if ((epi->ldc % 8) != 0) return set_error(LRP_ERR_ARG, "gemm: ldc must be a multiple of 8");
   GemmParams p;
   memset(&p, 0, sizeof(p));
+  p.stream_stores = stream_stores_default();
   p.batch = 1;
   p.M = M; p.N = N; p.K = K;
   p.out = epi->out;
