@@ -5,7 +5,9 @@ The CPU oracle cannot cover these sizes in seconds, so the checks are relations 
     not depend on which other prompts share its micro-batch (the property the multi-GPU sharding rests on);
   * activation-store policy is an implementation detail: store="sqrt" (segment recompute) == store="all";
   * the engine is deterministic up to fp32 atomic ordering in dQ (the bf16 rounding of dQ can flip in the last bit:
-    ~5e-5 rel-L2 run to run), so the relations are asserted to 1e-3."""
+    ~5e-5 rel-L2 run to run; measured over 48 repeats it is bimodal — now and then one rounding of a last-token-row gradient, through
+    which all relevance of the upper layers flows, flips and moves the result by 3.7e-4, tools/gpu_job_rep.sh), so every relation is
+    asserted to 1e-3.  `LRP_ATTN_BWD=v2` selects the atomic-free, bit-reproducible backward."""
 import pytest
 import torch
 
@@ -32,7 +34,7 @@ def test_batch_permutation_equivariance_and_micro_batch_invariance(setup):
     assert rel_l2(eng.attribute_device(ids[perm]), rel[perm]) < 1e-3
     singles = torch.cat([eng.attribute_device(ids[i:i + 1]).clone() for i in range(4)], 0)   # micro-batch of 1
     assert rel_l2(singles, rel) < 1e-3
-    assert rel_l2(eng.attribute_device(ids), rel) < 5e-4                                      # run-to-run
+    assert rel_l2(eng.attribute_device(ids), rel) < 1e-3                                      # run-to-run
 
 
 def test_sqrt_checkpoint_schedule_equals_full_store(setup):
@@ -47,4 +49,4 @@ def test_sqrt_checkpoint_schedule_equals_full_store(setup):
 def test_public_api_matches_device_path(setup):
     dims, eng, ids = setup
     host = eng.attribute(ids.cpu().pin_memory())
-    assert rel_l2(host, eng.attribute_device(ids).cpu()) < 5e-4
+    assert rel_l2(host, eng.attribute_device(ids).cpu()) < 1e-3
