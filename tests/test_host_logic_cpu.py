@@ -145,3 +145,30 @@ def test_install_as_lxt_registers_the_reference_module_names():
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     r = subprocess.run([sys.executable, "-c", code], cwd=root, capture_output=True, text=True)
     assert r.returncode == 0 and "ok" in r.stdout, r.stderr[-2000:]
+
+
+def test_explicit_module_initialisers_share_tensors_and_geometry():
+    """lxt.explicit.modules initialisers (reference modules.py:127-214): replacements are built from the original's constructor
+    arguments, share its parameters, and the packed in-projection of nn.MultiheadAttention becomes three views"""
+    import torch.nn as nn
+    import lxt_b200.explicit.modules as lm
+    E = 128
+    mha = nn.MultiheadAttention(E, 2, batch_first=True)
+    cp = lm.initialize_MHA(mha, lm.MultiheadAttention_CP)
+    assert (cp.embed_dim, cp.num_heads, cp.head_dim, cp.batch_first) == (E, 2, 64, True)
+    assert torch.equal(cp.q_proj_weight, mha.in_proj_weight[:E]) and torch.equal(cp.k_proj_weight, mha.in_proj_weight[E:2 * E])
+    assert torch.equal(cp.v_proj.weight, mha.in_proj_weight[2 * E:]) and torch.equal(cp.bias_k, mha.in_proj_bias[E:2 * E])
+    assert cp.q_proj_weight.data_ptr() == mha.in_proj_weight.data_ptr() and cp.out_proj.weight is mha.out_proj.weight
+    cp2 = lm.initialize_MHA(nn.MultiheadAttention(E, 2, kdim=64, vdim=32), lm.MultiheadAttention_CP)
+    assert cp2.k_proj_weight.shape == (E, 64) and cp2.v_proj.weight.shape == (E, 32) and cp2.batch_first is False
+    with pytest.raises(NotImplementedError):
+        lm.initialize_MHA(nn.MultiheadAttention(E, 2, add_bias_kv=True), lm.MultiheadAttention_CP)
+    lin = nn.Linear(8, 4, bias=False)
+    le = lm.initialize_bias(lin, lm.LinearEpsilon)
+    assert isinstance(le, lm.LinearEpsilon) and le.bias is None and le.weight is lin.weight and le.epsilon == 1e-6
+    ln = nn.LayerNorm(16)
+    l2 = lm.initialize_bias(ln, lm.LayerNormEpsilon)
+    assert l2.weight is ln.weight and l2.bias is ln.bias and l2.eps == ln.eps
+    sm = lm.initialize_generic(nn.Softmax(dim=-1), lm.SoftmaxDT)
+    assert sm.dim == -1 and sm.temperature == 1.0 and sm.dtype is None
+    assert set(lm.INIT_MODULE_MAPPING) == {lm.SoftmaxDT, lm.LinearEpsilon, lm.RMSNormIdentity, lm.LayerNormEpsilon, lm.MultiheadAttention_CP}
