@@ -28,10 +28,13 @@ def test_gather_relevance_world2_gloo(n_total):
     S, world = 6, 2
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 29500 + (os.getpid() % 2000) + n_total
+    import socket
+    with socket.socket() as sk:                  # a port the kernel just handed out is free (a pid-derived one can collide)
+        sk.bind(("127.0.0.1", 0))
+        port = sk.getsockname()[1]
     procs = [ctx.Process(target=_worker, args=(r, world, port, n_total, S, q)) for r in range(world)]
     [p.start() for p in procs]
-    got = dict(q.get(timeout=120) for _ in range(world))
+    got = dict(q.get(timeout=300) for _ in range(world))
     [p.join(timeout=60) for p in procs]
     expect = torch.arange(n_total, dtype=torch.float32)[:, None] * 1000 + torch.arange(S, dtype=torch.float32)[None, :]
     for r in range(world):
